@@ -1,0 +1,201 @@
+"""Generate golden vectors by running the UNMODIFIED reference in this container.
+
+Usage (build container only; needs /root/reference):
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  Each file stores the seeded inputs, every injected random
+draw and the reference's outputs, plus torch/numpy versions.  Weights are not stored:
+they are re-created from ``torch.manual_seed(20220414)`` (the reference's own seed,
+object_level/run_nerf.py:1130) and guarded by a checksum.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import refshim  # noqa: E402
+from oracle import nerf_oracle as orc  # noqa: E402  (only for the synthetic ray generators)
+
+SEED = 20220414
+
+
+def wsum(net):
+    return float(sum(v.double().abs().sum() for v in net.state_dict().values()))
+
+
+def opaque_(net):
+    with torch.no_grad():
+        net.alpha_linear.bias += 1.0
+        net.pts_linears[7].weight *= 3.0
+
+
+def tonp(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def meta():
+    return dict(torch_version=np.array(torch.__version__), numpy_version=np.array(np.__version__), seed=np.array(SEED))
+
+
+def object_fixtures():
+    rn, rh, cl = refshim.load_object_level()
+    os.makedirs("/tmp/_inrf_ref_logs/x", exist_ok=True)
+    torch.manual_seed(SEED)
+    kw_train, kw_test, *_ = rn.create_nerf(refshim.object_args())
+    coarse, fine = kw_test["network_fn"], kw_test["network_fine"]
+    sums = np.array([wsum(coarse), wsum(fine)])
+    opaque_(coarse), opaque_(fine)
+
+    # ---- stage vectors -------------------------------------------------------------
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(40, 3, generator=g) * 8 - 4)
+    x[0] = torch.tensor([0.0, 1e-3, -6.0])
+    emb10, _ = rh.get_embedder(10, 0)
+    emb4, _ = rh.get_embedder(4, 0)
+    e_pts, e_dir = emb10(x), emb4(x / x.norm(dim=-1, keepdim=True))
+    with torch.no_grad():
+        mlp_out = coarse(torch.cat([e_pts, e_dir], -1))
+    raw = torch.randn(6, 64, 11, generator=g)
+    raw[..., [0, 1, 2, 4, 5, 6, 7, 8, 9, 10]] = torch.sigmoid(raw[..., [0, 1, 2, 4, 5, 6, 7, 8, 9, 10]])
+    raw[..., 3] = raw[..., 3] * 3.0
+    raw[5, :, 3] = -1.0                       # fully transparent ray -> NaN disp (appendix A8)
+    z = torch.sort(torch.rand(6, 64, generator=g) * 4 + 2, dim=-1)[0]
+    rd = torch.randn(6, 3, generator=g)
+    r2o = {}
+    for wb in (False, True):
+        o = rn.raw2outputs(raw, z, rd, 0, wb)
+        for name, t in zip(("rgb", "disp", "acc", "weights", "depth", "albedo", "shading", "residual"), o):
+            r2o[f"wb{int(wb)}_{name}"] = t
+    bins = torch.sort(torch.rand(7, 63, generator=g) * 4 + 2, dim=-1)[0]
+    w = torch.rand(7, 62, generator=g) ** 4
+    w[1] = 0.0                                 # all-zero weights -> uniform pdf
+    w[2, :] = 0.0
+    w[2, 30] = 5.0                             # one spike -> denom<1e-5 bins
+    s_det = rh.sample_pdf(bins, w, 128, det=True)
+    u = torch.rand(7, 128, generator=g)
+    u[3, 0], u[3, 1] = 0.0, 1.0 - 1e-7
+    # reference draws u internally; replay through the pytest hook is numpy-only, so for the
+    # random branch we patch torch.rand for the duration of the call.
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: u.clone()
+    try:
+        s_rnd = rh.sample_pdf(bins, w, 128, det=False)
+    finally:
+        torch.rand = real_rand
+    np.savez_compressed(os.path.join(HERE, "object_stages.npz"), **meta(), weight_abs_sums=sums,
+                        **tonp(dict(x=x, emb_pts=e_pts, emb_dir=e_dir, mlp_out=mlp_out, raw=raw, z=z, rays_d=rd,
+                                    bins=bins, w=w, s_det=s_det, u=u, s_rnd=s_rnd)), **tonp(r2o))
+
+    # ---- end-to-end render_rays ----------------------------------------------------
+    rays_img = orc.blender_rays(8, 8)                       # 64 rays through the object centre
+    idx = torch.tensor([0, 7, 18, 27, 28, 35, 36, 45, 56, 63])
+    rays = rays_img[idx].contiguous()
+    strip = lambda d: {k: v for k, v in d.items() if k not in ("use_viewdirs", "ndc", "near", "far")}
+    kw = strip(kw_test)
+    with torch.no_grad():
+        det = rn.render_rays(rays, retraw=True, **kw)
+    out = {"rays": rays}
+    out.update({"det_" + k: v for k, v in det.items()})
+    # stochastic branch through the reference's own pytest hooks (np.random.seed(0) draws)
+    kw2 = strip(kw_train)
+    kw2.update(perturb=1.0, raw_noise_std=1.0)
+    with torch.no_grad():
+        sto = rn.render_rays(rays, retraw=True, pytest=True, **kw2)
+    out.update({"sto_" + k: v for k, v in sto.items()})
+    # lindisp + black background
+    kw3 = strip(kw_test)
+    kw3.update(lindisp=True, white_bkgd=False)
+    with torch.no_grad():
+        lin = rn.render_rays(rays, retraw=False, **kw3)
+    out.update({"lin_" + k: v for k, v in lin.items()})
+    # coarse only (BASELINE config 1 shape: N_importance=0)
+    kw4 = strip(kw_test)
+    kw4.update(N_importance=0, network_fine=None)
+    with torch.no_grad():
+        co = rn.render_rays(rays, **kw4)
+    out.update({"co_" + k: v for k, v in co.items()})
+    # full render() on a 6x6 view (ray generation + packing + reshape)
+    K = np.array(orc.blender_intrinsics(6, 6))
+    c2w = orc.pose_spherical(-180.0, -30.0, 4.0)[:3, :4]
+    with torch.no_grad():
+        r = rn.render(6, 6, K, chunk=32768, c2w=c2w, near=2.0, far=6.0, **kw_test)
+    for name, t in zip(("rgb", "disp", "acc", "albedo", "shading", "residual"), r[:6]):
+        out["img_" + name] = t
+    out.update({"img_" + k: v for k, v in r[6].items()})
+    np.savez_compressed(os.path.join(HERE, "object_render.npz"), **meta(), weight_abs_sums=sums, **tonp(out))
+    print("object fixtures written; weight sums", sums)
+
+
+def ssr_fixtures(C=28):
+    sn, mu, ry, tr, tu, scl = refshim.load_ssr()
+    torch.manual_seed(SEED)
+    emb_fn, in_ch = sn.get_embedder(10, 0, scalar_factor=10)
+    embd_fn, in_v = sn.get_embedder(4, 0, scalar_factor=1)
+    mk = lambda: sn.Semantic_NeRF(enable_semantic=True, num_semantic_classes=C, D=8, W=256, input_ch=in_ch,
+                                  output_ch=5, skips=[4], input_ch_views=in_v, use_viewdirs=True)
+    coarse, fine = mk(), mk()
+    sums = np.array([wsum(coarse), wsum(fine)])
+    opaque_(coarse), opaque_(fine)
+    T = tr.SSRTrainer.__new__(tr.SSRTrainer)
+    T.N_samples, T.N_importance, T.perturb, T.raw_noise_std = 64, 128, 1, 1.0
+    T.white_bkgd, T.enable_semantic, T.num_valid_semantic_class, T.endpoint_feat = False, True, C, False
+    T.netchunk, T.chunk = 32768, 32768
+    T.ssr_net_coarse, T.ssr_net_fine, T.embed_fn, T.embeddirs_fn = coarse, fine, emb_fn, embd_fn
+    rays_img = orc.replica_rays(6, 8)
+    rays = rays_img[torch.tensor([0, 5, 13, 20, 27, 34, 41, 47])].contiguous()
+    out = {"rays": rays, "C": np.array(C)}
+    T.training = False
+    with torch.no_grad():
+        ev = T.render_rays(rays)
+    out.update({"eval_" + k: v for k, v in ev.items() if not k.startswith("raw")})
+    out["eval_raw_fine_head"] = ev["raw_fine"][:2]
+    # training mode: record the reference's own random draws in call order
+    T.training = True
+    draws = []
+    real_rand, real_randn = torch.rand, torch.randn
+
+    def rec(fn):
+        def f(*a, **k):
+            t = fn(*a, **k)
+            draws.append(t.clone())
+            return t
+        return f
+    torch.manual_seed(7)
+    torch.rand, torch.randn = rec(real_rand), rec(real_randn)
+    try:
+        with torch.no_grad():
+            trn = T.render_rays(rays)
+    finally:
+        torch.rand, torch.randn = real_rand, real_randn
+    assert len(draws) == 4, [d.shape for d in draws]     # t_rand, noise_c, u, noise_f
+    out.update(train_t_rand=draws[0], train_noise_coarse=draws[1], train_u=draws[2], train_noise_fine=draws[3])
+    out.update({"train_" + k: v for k, v in trn.items() if not k.startswith("raw")})
+    # endpoint feature variant
+    T.training, T.endpoint_feat = False, True
+    with torch.no_grad():
+        ep = T.render_rays(rays)
+    out["ep_feat_map_fine"] = ep["feat_map_fine"]
+    out["ep_rgb_fine"] = ep["rgb_fine"]
+    # stage: Semantic_NeRF forward incl. endpoint
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(24, 3, generator=g) * 6 - 3
+    d = torch.randn(24, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    emb = torch.cat([emb_fn(x), embd_fn(d)], -1)
+    with torch.no_grad():
+        out["mlp_x"], out["mlp_d"] = x, d
+        out["mlp_out"] = fine(emb)
+        out["mlp_out_endpoint"] = fine(emb, True)
+    np.savez_compressed(os.path.join(HERE, "ssr_render.npz"), **meta(), weight_abs_sums=sums, **tonp(out))
+    print("ssr fixtures written; weight sums", sums)
+
+
+if __name__ == "__main__":
+    assert refshim.available(), "reference checkout not found"
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    object_fixtures()
+    ssr_fixtures()
