@@ -1,0 +1,223 @@
+/*
+ * inrf.h - C ABI of libinrf.so: the B200 (sm_100a) implementation of IntrinsicNeRF's
+ * volumetric ray-marching hot path and reflectance clustering.
+ *
+ * The reference (zju3dv/IntrinsicNeRF) is pure Python/PyTorch and has no FFI: its
+ * "operator interface" for this path is a set of module-level Python functions.  Each
+ * entry point below names the reference function (file:line under the reference
+ * checkout) whose arithmetic it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked host;
+ *   - all tensors are fp32, row-major, contiguous, unless stated otherwise;
+ *   - the caller owns every buffer (inputs, outputs, workspace, packed weights);
+ *     the library allocates nothing persistent;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises the device;
+ *   - every entry returns 0 on success and a negative INRF_E* code on failure; the
+ *     message is available from inrf_last_error_string() (thread-local).  Unsupported
+ *     configurations are rejected - there is no fallback path.
+ */
+#ifndef INRF_H_
+#define INRF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INRF_OK            0
+#define INRF_EINVAL       -1   /* bad argument (null pointer, negative size, bad enum) */
+#define INRF_EUNSUPPORTED -2   /* configuration outside what the kernels implement */
+#define INRF_ECUDA        -3   /* CUDA runtime error (message carries cudaGetErrorString) */
+#define INRF_EWORKSPACE   -4   /* workspace too small */
+
+/* Network variants.  Both are the 8x256 trunk with skip at layer 4, PE L=10 / L=4. */
+#define INRF_NET_OBJECT 0      /* NeRF           object_level/run_nerf_helpers.py:247-325 */
+#define INRF_NET_SSR    1      /* Semantic_NeRF  SSR/models/semantic_nerf.py:74-181       */
+
+/* MLP arithmetic. */
+#define INRF_PREC_TC   0       /* tcgen05 tensor cores: fp16 operands (RN), fp32 accumulate in
+                                  TMEM, sigma head and all epilogues in fp32 */
+#define INRF_PREC_FP32 1       /* CUDA-core fp32 FFMA everywhere (validation / strict mode) */
+
+/* Channel layout of a per-sample "raw" row (reference: run_nerf_helpers.py:321,
+ * semantic_nerf.py:171-181):  rgb[0:3] sigma[3] albedo[4:7] shading[7] residual[8:11]
+ * sem_logits[11:11+C] endpoint_feature[.. +128].                                        */
+#define INRF_RAW_BASE 11
+
+/* Per-ray output record written by inrf_raw2outputs / inrf_render_fwd
+ * (reference: run_nerf.py:398-412, model_utils.py:84-116):
+ *   rgb[0:3] disp[3] acc[4] albedo[5:8] shading[8] residual[9:12] depth[12] sem[13:13+C]
+ *   feat[13+C : 13+C+128] (only when endpoint_feat).                                     */
+#define INRF_REC_BASE 13
+
+const char* inrf_last_error_string(void);
+int inrf_version(void);
+
+/* ---------------------------------------------------------------------------------
+ * Weights
+ * --------------------------------------------------------------------------------- */
+/* Number of fp32 values in the canonical flat parameter vector of one network:
+ * for each layer in the order
+ *   pts_linears.0..7, alpha, feature, views_linears.0, albedo1, albedo2, shading1,
+ *   shading2, residual, [sem1, sem2 when n_classes>0]
+ * the weight ([out,in] row-major, exactly nn.Linear.weight) followed by the bias.
+ * (object fork: shading1/2 = test_linear1/2, residual = shading_linear;
+ *  run_nerf_helpers.py:259-279.  SSR fork: semantic_nerf.py:96-118.)
+ * Returns a negative code for unsupported (variant, n_classes).                        */
+int64_t inrf_flat_param_count(int variant, int n_classes);
+
+/* Bytes of the packed weight blob consumed by the kernels. */
+int64_t inrf_packed_bytes(int variant, int n_classes);
+
+/* flat_params (fp32, canonical order) -> packed blob (fp32 transposed copy for the
+ * CUDA-core path, fp16 pre-swizzled UMMA operand blocks in MMA issue order for the
+ * tensor-core path, fp32 biases).  Call again after every optimizer step.              */
+int inrf_pack_weights(const float* flat_params, int variant, int n_classes,
+                      void* packed, int64_t packed_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Stage entry points (one per reference primitive; used by the drop-in Python layer
+ * and by the parity tests)
+ * --------------------------------------------------------------------------------- */
+/* Embedder.embed  (run_nerf_helpers.py:195-225; semantic_nerf.py:14-65):
+ * x[M,3] -> out[M,3+6L];  x is divided by `scalar_factor` first (1 for the object fork). */
+int inrf_embed(const float* x, int64_t M, int n_freqs, float scalar_factor, float* out, void* stream);
+
+/* run_network (run_nerf.py:42-56; model_utils.py:19-35) fused with the Embedder and the
+ * network forward: pts[M,3], viewdirs[M,3] (one row per SAMPLE) -> raw[M,out_ch] with
+ * out_ch = 11 + n_classes + (endpoint ? 128 : 0).                                       */
+int inrf_mlp_fwd(const void* packed, int variant, int n_classes, int endpoint_feat,
+                 float pe_scalar_factor, const float* pts, const float* viewdirs, int64_t M,
+                 float* raw, int precision, void* stream);
+
+/* NeRF.forward / Semantic_NeRF.forward on rows that are ALREADY embedded
+ * (run_nerf_helpers.py:284, semantic_nerf.py:123): emb[M,90] = gamma(x)[63] | gamma(d)[27].  */
+int inrf_mlp_fwd_embedded(const void* packed, int variant, int n_classes, int endpoint_feat,
+                          const float* emb, int64_t M, float* raw, int precision, void* stream);
+
+/* Same network evaluation addressed by rays: sample (n,s) sits at o_n + d_n * z[n,s]
+ * (run_nerf.py:488,504) with view direction rays[n,8:11].  rays[N,11], z[N,S] -> raw[N,S,out_ch]. */
+int inrf_mlp_fwd_rays(const void* packed, int variant, int n_classes, int endpoint_feat,
+                      float pe_scalar_factor, const float* rays, const float* z, int64_t N, int S,
+                      float* raw, int precision, void* stream);
+
+/* raw2outputs (run_nerf.py:359-412; model_utils.py:39-116).
+ * raw[N,S,ch], z[N,S], rays_d given as rays_d[N,ld] with row stride ld floats (ld=3 for a
+ * packed [N,3] tensor, 11 to address columns 3:6 of a ray record - pass rays+3).
+ * noise[N,S] (already multiplied by raw_noise_std) may be NULL.
+ * Outputs: rec[N, 13 + n_classes + (endpoint?128:0)], weights[N,S] (may be NULL).        */
+int inrf_raw2outputs(const float* raw, const float* z, const float* rays_d, int ld_rays_d,
+                     const float* noise, int64_t N, int S, int n_classes, int endpoint_feat,
+                     int white_bkgd, float* rec, float* weights, void* stream);
+
+/* sample_pdf (run_nerf_helpers.py:402-445; SSR/models/rays.py:176-220).
+ * bins[N,B], weights given with row stride ld_w and B-1 used entries per row
+ * (pass weights_coarse+1 with ld_w=S to express weights[...,1:-1]).
+ * u[N,n_samples] or NULL for det (u = linspace(0,1,n_samples), passed by the caller in
+ * u_det[n_samples] so that it carries torch.linspace's exact values).
+ * Outputs: samples[N,n_samples]; inds[N,n_samples] int64 (searchsorted(cdf,u,right=True),
+ * may be NULL); cdf_out[N,B] (may be NULL).                                              */
+int inrf_sample_pdf(const float* bins, const float* weights, int ld_w, const float* u,
+                    const float* u_det, int64_t N, int B, int n_samples,
+                    float* samples, int64_t* inds, float* cdf_out, void* stream);
+
+/* Inversion only, for a caller-supplied cdf[N,B] (the exact-index contract of SURVEY 7.3). */
+int inrf_invert_cdf(const float* bins, const float* cdf, const float* u, int64_t N, int B,
+                    int n_samples, float* samples, int64_t* inds, void* stream);
+
+/* sort(cat([z_vals, z_samples])) and std(z_samples, unbiased=False)
+ * (run_nerf.py:503,519; trainer.py:766,800).  z_a[N,Sa], z_b[N,Sb] -> z_out[N,Sa+Sb]
+ * ascending, z_std[N] over z_b (may be NULL).  Sa+Sb <= 1024.                            */
+int inrf_merge_sorted(const float* z_a, const float* z_b, int64_t N, int Sa, int Sb,
+                      float* z_out, float* z_std, void* stream);
+
+/* Coarse sample depths (run_nerf.py:464-486; trainer.py:730-746): t_vals[S] is
+ * torch.linspace(0,1,S); t_rand[N,S] or NULL (no stratified jitter). rays[N,11] -> z[N,S]. */
+int inrf_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S,
+                  int lindisp, float* z, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Fused renderer: render_rays (run_nerf.py:415-528) / SSRTrainer.volumetric_rendering
+ * (SSR/training/trainer.py:717-808) for one chunk of rays.
+ * --------------------------------------------------------------------------------- */
+typedef struct InrfRenderCfg {
+  int32_t variant;         /* INRF_NET_*                                                 */
+  int32_t n_classes;       /* semantic classes C (0 = no semantic head)                  */
+  int32_t n_samples;       /* coarse samples Sc (<= 256)                                 */
+  int32_t n_importance;    /* fine samples Sf (0 = coarse pass only); Sc+Sf <= 1024      */
+  int32_t lindisp;         /* sample linearly in inverse depth (object fork only)        */
+  int32_t white_bkgd;
+  int32_t endpoint_feat;   /* fine pass appends the 128-d endpoint feature (SSR)         */
+  int32_t precision;       /* INRF_PREC_*                                                */
+  float   pe_scalar_factor;/* 1 (object) or 10 (SSR points); directions always use 1     */
+  int32_t reserved[7];
+} InrfRenderCfg;
+
+/* Workspace bytes needed by inrf_render_fwd for N rays (raw_* buffers included unless the
+ * caller passes its own). */
+int64_t inrf_render_workspace_bytes(const InrfRenderCfg* cfg, int64_t N);
+
+/* rays[N,11] = o3 d3 near far viewdir3.  Randomness is injected: t_rand[N,Sc] (NULL = no
+ * jitter), u[N,Sf] (NULL = det), noise_coarse[N,Sc] / noise_fine[N,Sc+Sf] already scaled
+ * by raw_noise_std (NULL = none).  t_vals[Sc], u_det[Sf] are torch.linspace(0,1,.).
+ * Outputs (each may be NULL when not wanted, except rec_fine / rec_coarse):
+ *   rec_coarse[N,13+C], rec_fine[N,13+C(+128)], z_std[N],
+ *   raw_coarse[N,Sc,11+C], raw_fine[N,Sc+Sf,11+C(+128)]  (taken from the workspace when NULL),
+ *   z_fine[N,Sc+Sf] (merged sorted depths), weights_fine[N,Sc+Sf].                        */
+int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, const void* packed_fine,
+                    const InrfRenderCfg* cfg, const float* t_vals, const float* u_det,
+                    const float* t_rand, const float* u, const float* noise_coarse,
+                    const float* noise_fine, float* rec_coarse, float* rec_fine, float* z_std,
+                    float* raw_coarse, float* raw_fine, float* z_fine, float* weights_fine,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Reflectance clustering (object_level/cluster.py, SSR/training/cluster.py)
+ * --------------------------------------------------------------------------------- */
+/* Cluster.mapping_color (cluster.py:266-275): rgb[P,3] -> d[P,3] = (I/3*f, g/I, b/I), I=r+g+b. */
+int inrf_mapping_color(const float* rgb, int64_t P, float intensity_factor, float* out, void* stream);
+
+/* Cluster.nearest_anchor over mapping_color(rgb) (cluster.py:217-252): for each pixel the
+ * index of the anchor minimising |a|^2+|p|^2-2a.p (first minimum wins, as torch.argmin).
+ * rgb[P,3], anchors[A,3] -> idx[P] int64.  map_color!=0 applies mapping_color first.       */
+int inrf_nearest_anchor(const float* rgb, int64_t P, const float* anchors, int64_t A,
+                        int map_color, float intensity_factor, int64_t* idx, void* stream);
+
+/* Cluster.dest_color / dest_class (cluster.py:217-239): nearest anchor, then
+ * out_rgb[P,3] = rgb_centers[links[idx]] and/or out_class[P] = links[idx].                 */
+int inrf_dest_color(const float* rgb, int64_t P, const float* anchors, const int64_t* links,
+                    int64_t A, const float* rgb_centers, int64_t K, float intensity_factor,
+                    float* out_rgb, int64_t* out_class, void* stream);
+
+/* Cluster.choose_anchors (cluster.py:150-176): voxelise mapped colours at leaf 0.01 into a
+ * 100^3 grid; per occupied voxel keep the pixel closest to the voxel centre (ties: lowest
+ * index - the deterministic statement of the reference's sort+last-write-wins scatter).
+ * pixels[P,3] (already mapped), labels[P] int64; voxel_key[1e6] uint64 scratch.
+ * Outputs anchors[<=1e6,3], links[<=1e6] int64 in ascending voxel order, *n_anchors (device). */
+int inrf_choose_anchors(const float* pixels, const int64_t* labels, int64_t P,
+                        unsigned long long* voxel_key, float* anchors, int64_t* links,
+                        int32_t* n_anchors, void* stream);
+
+/* One flat-kernel mean-shift sweep for a set of seeds (sklearn _mean_shift_single_seed as
+ * called from cluster.py:139-140): iterate mean of points within `bandwidth` until the
+ * shift is < 1e-3*bandwidth or max_iter.  points[P,3], seeds[Q,3] -> centers[Q,3],
+ * n_within[Q] int32 (points inside the final window), n_iter[Q] int32.                      */
+int inrf_meanshift_seeds(const float* points, int64_t P, const float* seeds, int64_t Q,
+                         float bandwidth, int max_iter, float* centers, int32_t* n_within,
+                         int32_t* n_iter, void* stream);
+
+/* sklearn.estimate_bandwidth core: for each query (a subsample of the points) the distance
+ * to its k-th nearest neighbour among points[P,3] (k counts the query itself, as
+ * NearestNeighbors.kneighbors on the fitted data does).  queries[Q,3] -> kth_dist[Q].      */
+int inrf_kth_neighbor_dist(const float* points, int64_t P, const float* queries, int64_t Q,
+                           int k, float* kth_dist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INRF_H_ */

@@ -1,0 +1,133 @@
+// Shared definitions for libinrf.so (sm_100a).  See include/inrf.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/inrf.h"
+
+namespace inrf {
+
+// ---------------------------------------------------------------------------------
+// error plumbing (thread-local message, integer codes across the C boundary)
+// ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define INRF_CHECK_ARG(cond, msg)                                   \
+  do {                                                              \
+    if (!(cond)) { ::inrf::set_error("%s: %s", __func__, msg); return INRF_EINVAL; } \
+  } while (0)
+#define INRF_CHECK_SUPPORTED(cond, msg)                             \
+  do {                                                              \
+    if (!(cond)) { ::inrf::set_error("%s: unsupported: %s", __func__, msg); return INRF_EUNSUPPORTED; } \
+  } while (0)
+#define INRF_CUDA(call)                                             \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return ::inrf::cuda_fail(e__, #call);   \
+  } while (0)
+#define INRF_LAUNCH_CHECK() INRF_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------
+// Network description (fixed architecture: D=8, W=256, skips=[4], PE L=10 / L=4)
+// ---------------------------------------------------------------------------------
+constexpr int W_HID = 256;
+constexpr int PE_PTS = 63;    // 3 + 6*10
+constexpr int PE_DIR = 27;    // 3 + 6*4
+constexpr int MAX_CLASSES = 112;   // 11 + C + 128 endpoint must stay <= 256 raw channels
+
+enum LayerId {
+  L_T0 = 0, L_T1, L_T2, L_T3, L_T4, L_T5, L_T6, L_T7,
+  L_ALPHA, L_FEAT, L_VIEWS, L_ALB1, L_ALB2, L_SH1, L_SH2, L_RES, L_SEM1, L_SEM2,
+  L_COUNT
+};
+
+struct LayerDims { int K, N; };
+
+__host__ __device__ inline LayerDims layer_dims(int l, int n_classes) {
+  switch (l) {
+    case L_T0: return {PE_PTS, W_HID};
+    case L_T5: return {PE_PTS + W_HID, W_HID};
+    case L_T1: case L_T2: case L_T3: case L_T4: case L_T6: case L_T7: return {W_HID, W_HID};
+    case L_ALPHA: return {W_HID, 1};
+    case L_FEAT: return {W_HID, W_HID};
+    case L_VIEWS: return {W_HID + PE_DIR, 128};
+    case L_ALB1: case L_SH1: case L_SEM1: return {W_HID, 128};
+    case L_ALB2: case L_RES: return {128, 3};
+    case L_SH2: return {128, 1};
+    case L_SEM2: return {128, n_classes};
+    default: return {0, 0};
+  }
+}
+
+// Offsets (in floats) of each layer's weight / bias inside the canonical flat parameter
+// vector, and inside the fp32 section of the packed blob.
+struct NetLayout {
+  int variant, n_classes, n_layers;
+  int64_t flat_w[L_COUNT], flat_b[L_COUNT];   // canonical flat vector
+  int64_t flat_count;
+  // packed blob (byte offsets)
+  int64_t f32_wt[L_COUNT];   // fp32 weights: transposed [K][N] for N>=128, else original [N][K]
+  int64_t f32_b[L_COUNT];    // fp32 bias
+  int64_t comp;              // fp32 composed views' weight [128][256] followed by its bias [128]
+  int64_t tc_bias;           // fp32 bias table for the tensor-core kernel (see mlp_tc.cu)
+  int64_t tc_blocks;         // fp16 pre-swizzled operand blocks
+  int64_t tc_blocks_bytes;
+  int64_t total_bytes;
+};
+
+int make_layout(int variant, int n_classes, NetLayout* out);   // returns INRF_* code
+
+inline int raw_channels(int n_classes, int endpoint) { return INRF_RAW_BASE + n_classes + (endpoint ? 128 : 0); }
+inline int rec_channels(int n_classes, int endpoint) { return INRF_REC_BASE + n_classes + (endpoint ? 128 : 0); }
+
+// ---------------------------------------------------------------------------------
+// Tensor-core operand block table (pack.cu builds the blob in this order, mlp_tc.cu
+// streams it in the same order).  One block = rows x 64 fp16 (128 B per row), stored in
+// the UMMA canonical K-major SWIZZLE_128B layout: 8-row atoms of 1024 B, the 16-byte
+// unit index XORed with (row & 7).
+// ---------------------------------------------------------------------------------
+struct TcBlock {
+  int16_t layer;     // source layer, or -1 for a composed matrix (views' = views o feature)
+  int16_t rows;      // N rows in this block (128, 16 or 32)
+  int16_t n0;        // first output row of the source matrix
+  int16_t k0;        // first source K column (may be negative for padding layouts)
+  int16_t kcols;     // valid source columns in this block (<=64), rest zero
+  int16_t kind;      // 0: plain rows of `layer`; 1: views' (composed); 2: head-pair block-diag
+  int32_t byte_off;  // offset inside the tc_blocks section
+};
+constexpr int TC_MAX_BLOCKS = 128;
+constexpr int TC_SLOT_BYTES = 16384;
+
+struct TcProgram {
+  int n_blocks;
+  int bytes;
+  TcBlock blk[TC_MAX_BLOCKS];
+};
+int make_tc_program(int variant, int n_classes, TcProgram* prog);
+
+// ---------------------------------------------------------------------------------
+// launchers implemented in the .cu files
+// ---------------------------------------------------------------------------------
+struct MlpArgs {
+  const void* packed;
+  int variant, n_classes, endpoint;
+  float pe_scale;            // scalar_factor for points
+  // addressing mode A: explicit points
+  const float* pts;          // [M,3] or null
+  const float* viewdirs;     // [M,3] or null
+  // addressing mode C: rows already embedded (NeRF.forward's own input), [M,90] = gamma(x) | gamma(d)
+  const float* emb;
+  // addressing mode B: rays + depths
+  const float* rays;         // [N,11] or null
+  const float* z;            // [N,S]
+  int S;
+  int64_t M;                 // total rows (N*S in ray mode)
+  float* raw;                // [M,out_ch]
+};
+int launch_mlp_fp32(const MlpArgs& a, cudaStream_t st);
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t st);
+
+}  // namespace inrf

@@ -1,0 +1,295 @@
+"""Drop-in for the renderer half of ``object_level/run_nerf.py`` and the model/sampling half
+of ``object_level/run_nerf_helpers.py``: same names, same signatures, same return layout.
+
+  render           run_nerf.py:74-139       batchify_rays   run_nerf.py:59-71
+  render_rays      run_nerf.py:415-528      run_network     run_nerf.py:42-56
+  raw2outputs      run_nerf.py:359-412      batchify        run_nerf.py:32-39
+  sample_pdf       run_nerf_helpers.py:402  create_nerf     run_nerf.py:275-356
+  get_rays/ndc_rays  run_nerf_helpers.py:359-398 (ray generation stays PyTorch: SURVEY 8f row 1)
+
+When ``network_fn``/``network_fine`` are :class:`intrinsicnerf_b200.nerf.NeRF` modules the
+whole chunk goes through one ``inrf_render_fwd`` call (PE + MLP + compositing + resampling
+on the GPU, nothing materialised per layer).  With foreign callables the stage kernels
+(sampling, compositing, merge) still run, around the caller's network.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+from .nerf import NeRF, Embedder, get_embedder  # noqa: F401  (re-exported like `from run_nerf_helpers import *`)
+
+DEBUG = False
+
+# keys of the 13(+C)-wide per-ray record (include/inrf.h)
+_REC = dict(rgb=(0, 3), disp=(3, 4), acc=(4, 5), albedo=(5, 8), shading=(8, 9), residual=(9, 12), depth=(12, 13))
+
+
+def _split_rec(rec, key):
+    a, b = _REC[key]
+    v = rec[:, a:b]
+    return v if b - a > 1 else v[:, 0]
+
+
+def batchify(fn, chunk):
+    """Apply ``fn`` in slices of ``chunk`` rows (kept for API parity; the fused kernels need no
+    netchunk, so ``chunk=None`` is the efficient setting)."""
+    if chunk is None:
+        return fn
+
+    def run(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+    return run
+
+
+class _FusedQuery:
+    """The ``network_query_fn`` create_nerf hands out: callable like the reference's lambda,
+    and recognisable by render_rays so that it can fuse the whole chunk."""
+
+    def __init__(self, embed_fn, embeddirs_fn, netchunk):
+        self.embed_fn, self.embeddirs_fn, self.netchunk = embed_fn, embeddirs_fn, netchunk
+
+    def __call__(self, inputs, viewdirs, network_fn):
+        return run_network(inputs, viewdirs, network_fn, self.embed_fn, self.embeddirs_fn, self.netchunk)
+
+    def fusable_with(self, *nets):
+        ok_emb = isinstance(self.embed_fn, Embedder) and isinstance(self.embeddirs_fn, Embedder) \
+            and self.embed_fn.n_freqs == 10 and self.embeddirs_fn.n_freqs == 4 and self.embeddirs_fn.scalar_factor == 1.0
+        return ok_emb and all(n is None or isinstance(n, NeRF) for n in nets)
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """inputs [N,S,3], viewdirs [N,3] -> [N,S,out].  With our modules the embedding and the
+    network are one kernel launch; otherwise embed -> fn like the reference."""
+    if isinstance(fn, NeRF) and isinstance(embed_fn, Embedder) and isinstance(embeddirs_fn, Embedder) \
+            and viewdirs is not None and embed_fn.n_freqs == 10 and embeddirs_fn.n_freqs == 4:
+        fn._no_grad_guard(inputs)
+        dirs = viewdirs[:, None].expand(inputs.shape)
+        out = ops.mlp_forward(fn.packed(), fn.variant, 0, inputs.reshape(-1, 3), dirs.reshape(-1, 3),
+                              False, embed_fn.scalar_factor)
+        return out.reshape(list(inputs.shape[:-1]) + [out.shape[-1]])
+    flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(flat)
+    if viewdirs is not None:
+        dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded = torch.cat([embedded, embeddirs_fn(torch.reshape(dirs, [-1, dirs.shape[-1]]))], -1)
+    out = batchify(fn, netchunk)(embedded)
+    return torch.reshape(out, list(inputs.shape[:-1]) + [out.shape[-1]])
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+    """-> (rgb_map, disp_map, acc_map, weights, depth_map, albedo_map, shading_map, residual_map)."""
+    noise = None
+    if raw_noise_std > 0.:
+        if pytest:
+            np.random.seed(0)
+            noise = torch.Tensor(np.random.rand(*list(raw[..., 3].shape))).to(raw.device) * raw_noise_std
+        else:
+            noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std
+    rec, w = ops.raw2outputs_rec(raw[..., :11], z_vals, rays_d, noise, white_bkgd)
+    g = lambda k: _split_rec(rec, k)  # noqa: E731
+    return g("rgb"), g("disp"), g("acc"), w, g("depth"), g("albedo"), g("shading"), g("residual")
+
+
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    u = None
+    if pytest:
+        np.random.seed(0)
+        shape = list(bins.shape[:-1]) + [N_samples]
+        u = np.broadcast_to(np.linspace(0., 1., N_samples), shape) if det else np.random.rand(*shape)
+        u = torch.Tensor(np.ascontiguousarray(u)).to(bins.device)
+    elif not det:
+        u = torch.rand(list(bins.shape[:-1]) + [N_samples], device=bins.device)
+    return ops.sample_pdf(bins, weights, N_samples, u)[0]
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False):
+    N = ray_batch.shape[0]
+    dev = ray_batch.device
+    if ray_batch.shape[-1] != 11:
+        raise NotImplementedError("the CUDA renderer needs use_viewdirs=True ray records [N,11]")
+    St = N_samples + N_importance
+
+    def draw_uniform(*shape):
+        if pytest:
+            np.random.seed(0)
+            return torch.Tensor(np.random.rand(*shape)).to(dev)
+        return torch.rand(*shape, device=dev)
+
+    def draw_noise(*shape):
+        if raw_noise_std <= 0.:
+            return None
+        if pytest:
+            return draw_uniform(*shape) * raw_noise_std
+        return torch.randn(*shape, device=dev) * raw_noise_std
+
+    t_rand = draw_uniform(N, N_samples) if perturb > 0. else None
+    u = draw_uniform(N, N_importance) if (N_importance > 0 and perturb != 0.) else None
+
+    fused = isinstance(network_query_fn, _FusedQuery) and network_query_fn.fusable_with(network_fn, network_fine)
+    ret = {}
+    if fused:
+        network_fn._no_grad_guard(ray_batch)
+        fine = network_fine if network_fine is not None else network_fn
+        o = ops.render_chunk(ray_batch, network_fn.packed(), fine.packed() if N_importance > 0 else None,
+                             variant=network_fn.variant, n_samples=N_samples, n_importance=N_importance,
+                             lindisp=lindisp, white_bkgd=white_bkgd,
+                             pe_scalar_factor=network_query_fn.embed_fn.scalar_factor, t_rand=t_rand, u=u,
+                             noise_coarse=draw_noise(N, N_samples),
+                             noise_fine=draw_noise(N, St) if N_importance > 0 else None, want_raw=retraw)
+        rec = o["rec_fine"] if N_importance > 0 else o["rec_coarse"]
+        for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
+            ret[k + "_map"] = _split_rec(rec, k)
+        if retraw:
+            ret["raw"] = o["raw_fine"] if N_importance > 0 else o["raw_coarse"]
+        if N_importance > 0:
+            for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
+                ret[k + "0"] = _split_rec(o["rec_coarse"], k)
+            ret["z_std"] = o["z_std"]
+    else:
+        rays_d, viewdirs = ray_batch[:, 3:6], ray_batch[:, -3:]
+        rays_o = ray_batch[:, 0:3]
+        z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand)
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+        raw = network_query_fn(pts, viewdirs, network_fn)
+        rec, weights = ops.raw2outputs_rec(raw[..., :11], z_vals, rays_d, draw_noise(N, N_samples), white_bkgd)
+        rec0 = rec
+        if N_importance > 0:
+            z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+            z_samples = ops.sample_pdf(z_mid, weights[..., 1:-1], N_importance, u)[0]
+            z_vals, z_std = ops.merge_sorted(z_vals, z_samples)
+            pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+            raw = network_query_fn(pts, viewdirs, network_fn if network_fine is None else network_fine)
+            rec, weights = ops.raw2outputs_rec(raw[..., :11], z_vals, rays_d, draw_noise(N, St), white_bkgd)
+        for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
+            ret[k + "_map"] = _split_rec(rec, k)
+        if retraw:
+            ret["raw"] = raw
+        if N_importance > 0:
+            for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
+                ret[k + "0"] = _split_rec(rec0, k)
+            ret["z_std"] = z_std
+    if DEBUG:
+        for k in ret:
+            if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
+                print(f"! [Numerical Error] {k} contains nan or inf.")
+    return ret
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """Chunked render_rays.  ``chunk`` only bounds the scratch memory (raw tensors); results
+    do not depend on it."""
+    pieces = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        r = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k, v in r.items():
+            pieces.setdefault(k, []).append(v)
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in pieces.items()}
+
+
+def get_rays(H, W, K, c2w):
+    c2w = torch.as_tensor(c2w, dtype=torch.float32)
+    dev = c2w.device
+    jj, ii = torch.meshgrid(torch.linspace(0, H - 1, H, device=dev), torch.linspace(0, W - 1, W, device=dev), indexing="ij")
+    dirs = torch.stack([(ii - K[0][2]) / K[0][0], -(jj - K[1][2]) / K[1][1], -torch.ones_like(ii)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
+def get_rays_np(H, W, K, c2w):
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing="xy")
+    dirs = np.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -np.ones_like(i)], -1)
+    rays_d = np.sum(dirs[..., np.newaxis, :] * c2w[:3, :3], -1)
+    rays_o = np.broadcast_to(c2w[:3, -1], np.shape(rays_d))
+    return rays_o, rays_d
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """Forward-facing (LLFF) NDC warp, run_nerf_helpers.py:381-398."""
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    rays_o = rays_o + t[..., None] * rays_d
+    sx, sy = -1. / (W / (2. * focal)), -1. / (H / (2. * focal))
+    o = torch.stack([sx * rays_o[..., 0] / rays_o[..., 2], sy * rays_o[..., 1] / rays_o[..., 2],
+                     1. + 2. * near / rays_o[..., 2]], -1)
+    d = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2]),
+                     sy * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2]),
+                     -2. * near / rays_o[..., 2]], -1)
+    return o, d
+
+
+def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, **kwargs):
+    """-> [rgb_map, disp_map, acc_map, albedo_map, shading_map, residual_map, extras_dict]."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w)
+    else:
+        rays_o, rays_d = rays
+    if not use_viewdirs:
+        raise NotImplementedError("the CUDA renderer implements use_viewdirs=True (what every reference config sets)")
+    viewdirs = rays_d
+    if c2w_staticcam is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
+    viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+    viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    sh = rays_d.shape
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    packed = torch.cat([rays_o, rays_d, near, far, viewdirs], -1)
+    all_ret = batchify_rays(packed, chunk, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    main = ["rgb_map", "disp_map", "acc_map", "albedo_map", "shading_map", "residual_map"]
+    return [all_ret[k] for k in main] + [{k: v for k, v in all_ret.items() if k not in main}]
+
+
+def create_nerf(args, device=None):
+    """-> (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer), with the
+    reference's kwargs keys and checkpoint format ('network_fn_state_dict', ...)."""
+    device = device or torch.device("cuda")
+    embed_fn, input_ch = get_embedder(args.multires, args.i_embed)
+    if not args.use_viewdirs:
+        raise NotImplementedError("use_viewdirs=False is not implemented by the CUDA path")
+    embeddirs_fn, input_ch_views = get_embedder(args.multires_views, args.i_embed)
+    output_ch = 5 if args.N_importance > 0 else 4
+    model = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, output_ch=output_ch, skips=[4],
+                 input_ch_views=input_ch_views, use_viewdirs=True).to(device)
+    grad_vars = list(model.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, input_ch=input_ch, output_ch=output_ch,
+                          skips=[4], input_ch_views=input_ch_views, use_viewdirs=True).to(device)
+        grad_vars += list(model_fine.parameters())
+    query = _FusedQuery(embed_fn, embeddirs_fn, args.netchunk)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    start = 0
+    if getattr(args, "ft_path", None) not in (None, "None"):
+        ckpts = [args.ft_path]
+    else:
+        d = os.path.join(args.basedir, args.expname)
+        ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if "tar" in f] if os.path.isdir(d) else []
+    print("Found ckpts", ckpts)
+    if ckpts and not args.no_reload:
+        print("Reloading from", ckpts[-1])
+        ck = torch.load(ckpts[-1], map_location=device)
+        start = ck["global_step"]
+        optimizer.load_state_dict(ck["optimizer_state_dict"])
+        model.load_state_dict(ck["network_fn_state_dict"])
+        if model_fine is not None:
+            model_fine.load_state_dict(ck["network_fine_state_dict"])
+    train = dict(network_query_fn=query, perturb=args.perturb, N_importance=args.N_importance, network_fine=model_fine,
+                 N_samples=args.N_samples, network_fn=model, use_viewdirs=args.use_viewdirs,
+                 white_bkgd=args.white_bkgd, raw_noise_std=args.raw_noise_std)
+    if args.dataset_type != "llff" or args.no_ndc:
+        print("Not ndc!")
+        train["ndc"] = False
+        train["lindisp"] = args.lindisp
+    test = dict(train)
+    test["perturb"] = False
+    test["raw_noise_std"] = 0.
+    return train, test, start, grad_vars, optimizer

@@ -1,0 +1,238 @@
+"""Tensor-level wrappers over the C ABI.  Inputs must be CUDA float32 tensors; everything
+is enqueued on torch's current stream.  No CPU path exists."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import PREC_FP32, PREC_TC, RAW_BASE, REC_BASE, RenderCfg, check  # noqa: F401
+
+_DEFAULT_PRECISION = PREC_TC
+
+
+def set_default_precision(p):
+    """'tc' (tcgen05 fp16-operand / fp32-accumulate, default) or 'fp32' (CUDA-core FFMA)."""
+    global _DEFAULT_PRECISION
+    _DEFAULT_PRECISION = {"tc": PREC_TC, "fp32": PREC_FP32, PREC_TC: PREC_TC, PREC_FP32: PREC_FP32}[p]
+
+
+def default_precision():
+    return _DEFAULT_PRECISION
+
+
+def _prec(p):
+    if p is None:
+        return _DEFAULT_PRECISION
+    return {"tc": PREC_TC, "fp32": PREC_FP32, PREC_TC: PREC_TC, PREC_FP32: PREC_FP32}[p]
+
+
+def _f32(t, name):
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: intrinsicnerf_b200 runs on CUDA tensors only (got {t.device}); there is no CPU fallback")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_LINSPACE = {}
+
+
+def linspace01(n, device):
+    """torch.linspace(0,1,n) on `device`, cached (t_vals / deterministic u)."""
+    key = (n, str(device))
+    t = _LINSPACE.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, steps=n).to(device)   # CPU values, bit-identical to the reference's
+        _LINSPACE[key] = t
+    return t
+
+
+def flat_param_count(variant, n_classes):
+    return check(_lib.lib().inrf_flat_param_count(variant, n_classes))
+
+
+def pack_weights(flat, variant, n_classes):
+    flat = _f32(flat, "flat_params")
+    n = flat_param_count(variant, n_classes)
+    if flat.numel() != n:
+        raise ValueError(f"flat parameter vector has {flat.numel()} values, expected {n}")
+    nbytes = check(_lib.lib().inrf_packed_bytes(variant, n_classes))
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+    with torch.cuda.device(flat.device):
+        check(_lib.lib().inrf_pack_weights(_ptr(flat), variant, n_classes, _ptr(packed), nbytes, _stream()))
+    return packed
+
+
+def embed(x, n_freqs, scalar_factor=1.0):
+    x = _f32(x, "x")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, 3)
+    out = torch.empty(x2.shape[0], 3 + 6 * n_freqs, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().inrf_embed(_ptr(x2), x2.shape[0], n_freqs, float(scalar_factor), _ptr(out), _stream()))
+    return out.reshape(*lead, out.shape[-1])
+
+
+def mlp_forward(packed, variant, n_classes, pts, viewdirs, endpoint=False, pe_scalar_factor=1.0, precision=None):
+    pts, viewdirs = _f32(pts, "pts").reshape(-1, 3), _f32(viewdirs, "viewdirs").reshape(-1, 3)
+    M = pts.shape[0]
+    if viewdirs.shape[0] != M:
+        raise ValueError("pts and viewdirs must have one row per sample")
+    raw = torch.empty(M, RAW_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        check(_lib.lib().inrf_mlp_fwd(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor),
+                                      _ptr(pts), _ptr(viewdirs), M, _ptr(raw), _prec(precision), _stream()))
+    return raw
+
+
+def mlp_forward_embedded(packed, variant, n_classes, emb, endpoint=False, precision=None):
+    emb = _f32(emb, "embedded")
+    if emb.shape[-1] != 90:
+        raise ValueError("embedded input must be [...,90] = gamma(x)[63] | gamma(d)[27]")
+    lead = emb.shape[:-1]
+    e2 = emb.reshape(-1, 90)
+    raw = torch.empty(e2.shape[0], RAW_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        check(_lib.lib().inrf_mlp_fwd_embedded(_ptr(packed), variant, n_classes, int(endpoint), _ptr(e2), e2.shape[0],
+                                               _ptr(raw), _prec(precision), _stream()))
+    return raw.reshape(*lead, raw.shape[-1])
+
+
+def mlp_forward_rays(packed, variant, n_classes, rays, z, endpoint=False, pe_scalar_factor=1.0, precision=None):
+    rays, z = _f32(rays, "rays"), _f32(z, "z")
+    N, S = z.shape
+    raw = torch.empty(N, S, RAW_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        check(_lib.lib().inrf_mlp_fwd_rays(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor),
+                                           _ptr(rays), _ptr(z), N, S, _ptr(raw), _prec(precision), _stream()))
+    return raw
+
+
+def raw2outputs_rec(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, endpoint=False, want_weights=True):
+    raw, z_vals, rays_d = _f32(raw, "raw"), _f32(z_vals, "z_vals"), _f32(rays_d, "rays_d")
+    N, S, ch = raw.shape
+    if ch != RAW_BASE + n_classes + (128 if endpoint else 0):
+        raise ValueError(f"raw has {ch} channels, expected {RAW_BASE + n_classes + (128 if endpoint else 0)}")
+    rec = torch.empty(N, REC_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=raw.device)
+    weights = torch.empty(N, S, dtype=torch.float32, device=raw.device) if want_weights else None
+    noise = None if noise is None else _f32(noise, "noise")
+    with torch.cuda.device(raw.device):
+        check(_lib.lib().inrf_raw2outputs(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S, n_classes,
+                                          int(endpoint), int(bool(white_bkgd)), _ptr(rec), _ptr(weights), _stream()))
+    return rec, weights
+
+
+def sample_pdf(bins, weights, n_samples, u=None, want_inds=False, want_cdf=False):
+    bins, weights = _f32(bins, "bins"), _f32(weights, "weights")
+    N, B = bins.shape
+    if weights.shape != (N, B - 1):
+        raise ValueError("weights must be [N, bins-1]")
+    u = None if u is None else _f32(u, "u")
+    u_det = linspace01(n_samples, bins.device) if u is None else None
+    samples = torch.empty(N, n_samples, dtype=torch.float32, device=bins.device)
+    inds = torch.empty(N, n_samples, dtype=torch.int64, device=bins.device) if want_inds else None
+    cdf = torch.empty(N, B, dtype=torch.float32, device=bins.device) if want_cdf else None
+    with torch.cuda.device(bins.device):
+        check(_lib.lib().inrf_sample_pdf(_ptr(bins), _ptr(weights), B - 1, _ptr(u), _ptr(u_det), N, B, n_samples,
+                                         _ptr(samples), _ptr(inds), _ptr(cdf), _stream()))
+    return samples, inds, cdf
+
+
+def invert_cdf(bins, cdf, u):
+    bins, cdf, u = _f32(bins, "bins"), _f32(cdf, "cdf"), _f32(u, "u")
+    N, B = bins.shape
+    n = u.shape[1]
+    samples = torch.empty(N, n, dtype=torch.float32, device=bins.device)
+    inds = torch.empty(N, n, dtype=torch.int64, device=bins.device)
+    with torch.cuda.device(bins.device):
+        check(_lib.lib().inrf_invert_cdf(_ptr(bins), _ptr(cdf), _ptr(u), N, B, n, _ptr(samples), _ptr(inds), _stream()))
+    return samples, inds
+
+
+def merge_sorted(z_a, z_b, want_std=True):
+    z_a, z_b = _f32(z_a, "z_a"), _f32(z_b, "z_b")
+    N, Sa = z_a.shape
+    Sb = z_b.shape[1]
+    out = torch.empty(N, Sa + Sb, dtype=torch.float32, device=z_a.device)
+    std = torch.empty(N, dtype=torch.float32, device=z_a.device) if want_std else None
+    with torch.cuda.device(z_a.device):
+        check(_lib.lib().inrf_merge_sorted(_ptr(z_a), _ptr(z_b), N, Sa, Sb, _ptr(out), _ptr(std), _stream()))
+    return out, std
+
+
+def coarse_z(rays, n_samples, lindisp=False, t_rand=None):
+    rays = _f32(rays, "rays")
+    N = rays.shape[0]
+    z = torch.empty(N, n_samples, dtype=torch.float32, device=rays.device)
+    t_rand = None if t_rand is None else _f32(t_rand, "t_rand")
+    with torch.cuda.device(rays.device):
+        check(_lib.lib().inrf_coarse_z(_ptr(rays), _ptr(linspace01(n_samples, rays.device)), _ptr(t_rand), N, n_samples,
+                                       int(bool(lindisp)), _ptr(z), _stream()))
+    return z
+
+
+class _Workspace:
+    """Grow-only scratch buffer per device (the library allocates nothing itself)."""
+    bufs = {}
+
+    @classmethod
+    def get(cls, device, nbytes):
+        key = str(device)
+        b = cls.bufs.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=device)
+            cls.bufs[key] = b
+        return b
+
+
+def render_chunk(rays, packed_coarse, packed_fine, variant=0, n_classes=0, n_samples=64, n_importance=128,
+                 lindisp=False, white_bkgd=False, endpoint=False, pe_scalar_factor=1.0, precision=None,
+                 t_rand=None, u=None, noise_coarse=None, noise_fine=None, want_raw=False, want_z=False,
+                 want_weights=False):
+    """One inrf_render_fwd call.  Returns a dict of packed outputs:
+    rec_coarse [N,13+C], rec_fine [N,13+C(+128)], z_std [N] (+ raw_coarse/raw_fine/z_fine/weights_fine)."""
+    rays = _f32(rays, "rays")
+    if rays.ndim != 2 or rays.shape[1] != 11:
+        raise ValueError("rays must be [N,11] = o3 d3 near far viewdir3 (use_viewdirs=True)")
+    dev, N = rays.device, rays.shape[0]
+    St = n_samples + n_importance
+    cfg = RenderCfg(variant=variant, n_classes=n_classes, n_samples=n_samples, n_importance=n_importance,
+                    lindisp=int(bool(lindisp)), white_bkgd=int(bool(white_bkgd)), endpoint_feat=int(bool(endpoint)),
+                    precision=_prec(precision), pe_scalar_factor=float(pe_scalar_factor))
+    L = _lib.lib()
+    ws_bytes = check(L.inrf_render_workspace_bytes(C.byref(cfg), N))
+    ws = _Workspace.get(dev, ws_bytes)
+    new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    out = {"rec_coarse": new(N, REC_BASE + n_classes)}
+    if n_importance > 0:
+        out["rec_fine"] = new(N, REC_BASE + n_classes + (128 if endpoint else 0))
+        out["z_std"] = new(N)
+    if want_raw:
+        out["raw_coarse"] = new(N, n_samples, RAW_BASE + n_classes)
+        if n_importance > 0:
+            out["raw_fine"] = new(N, St, RAW_BASE + n_classes + (128 if endpoint else 0))
+    if want_z and n_importance > 0:
+        out["z_fine"] = new(N, St)
+    if want_weights and n_importance > 0:
+        out["weights_fine"] = new(N, St)
+    opt = lambda t, name: None if t is None else _f32(t, name)  # noqa: E731
+    t_rand, u = opt(t_rand, "t_rand"), opt(u, "u")
+    noise_coarse, noise_fine = opt(noise_coarse, "noise_coarse"), opt(noise_fine, "noise_fine")
+    u_det = linspace01(n_importance, dev) if (n_importance > 0 and u is None) else None
+    with torch.cuda.device(dev):
+        check(L.inrf_render_fwd(_ptr(rays), N, _ptr(packed_coarse), _ptr(packed_fine), C.byref(cfg),
+                                _ptr(linspace01(n_samples, dev)), _ptr(u_det), _ptr(t_rand), _ptr(u),
+                                _ptr(noise_coarse), _ptr(noise_fine), _ptr(out["rec_coarse"]), _ptr(out.get("rec_fine")),
+                                _ptr(out.get("z_std")), _ptr(out.get("raw_coarse")), _ptr(out.get("raw_fine")),
+                                _ptr(out.get("z_fine")), _ptr(out.get("weights_fine")), _ptr(ws), ws.numel(), _stream()))
+    return out

@@ -1,0 +1,160 @@
+"""Drop-in for the scene-level (Semantic-NeRF) fork's renderer.
+
+  run_network / raw2outputs     SSR/models/model_utils.py:19-35, 39-116
+  sample_pdf                    SSR/models/rays.py:176-220
+  batchify / batchify_rays      SSR/training/training_utils.py:5-29
+  SSRRenderer.render_rays / .volumetric_rendering / .create_ssr
+                                SSR/training/trainer.py:693-715, 717-808, 811-849
+
+``SSRRenderer`` is a mixin carrying exactly the three trainer methods on the hot path; it reads
+the same attributes the reference trainer sets (N_samples, N_importance, perturb, training,
+raw_noise_std, white_bkgd, enable_semantic, num_valid_semantic_class, endpoint_feat, chunk,
+netchunk, ssr_net_coarse, ssr_net_fine, embed_fn, embeddirs_fn).  ``install_into(trainer_cls)``
+rebinds them on the reference's ``SSRTrainer`` so ``train_SSR_main.py`` runs unchanged.
+"""
+import torch
+
+from . import ops
+from .nerf import Embedder, Semantic_NeRF, get_embedder  # noqa: F401
+from .object_level import batchify, _split_rec  # noqa: F401
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    net = getattr(fn, "_inrf_net", fn)
+    endpoint = bool(getattr(fn, "_inrf_endpoint", False))
+    if isinstance(net, Semantic_NeRF) and isinstance(embed_fn, Embedder) and isinstance(embeddirs_fn, Embedder) \
+            and viewdirs is not None and embed_fn.n_freqs == 10 and embeddirs_fn.n_freqs == 4:
+        net._no_grad_guard(inputs)
+        dirs = viewdirs[:, None].expand(inputs.shape)
+        out = ops.mlp_forward(net.packed(), net.variant, net.n_classes, inputs.reshape(-1, 3), dirs.reshape(-1, 3),
+                              endpoint, embed_fn.scalar_factor)
+        return out.reshape(list(inputs.shape[:-1]) + [out.shape[-1]])
+    flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(flat)
+    if viewdirs is not None:
+        dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded = torch.cat([embedded, embeddirs_fn(torch.reshape(dirs, [-1, dirs.shape[-1]]))], -1)
+    out = batchify(fn, netchunk)(embedded)
+    return torch.reshape(out, list(inputs.shape[:-1]) + [out.shape[-1]])
+
+
+def with_endpoint(net, endpoint):
+    """The reference passes ``lambda x: ssr_net_fine(x, endpoint_feat)``; this is the same
+    callable, but still recognisable by run_network for the fused path."""
+    def f(x):
+        return net(x, endpoint)
+    f._inrf_net, f._inrf_endpoint = net, endpoint
+    return f
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, enable_semantic=True, num_sem_class=0,
+                endpoint_feat=False):
+    """-> (rgb, disp, acc, weights, depth, sem_map, feat_map, albedo, shading, residual)."""
+    C = num_sem_class if enable_semantic else 0
+    if enable_semantic and num_sem_class <= 0:
+        raise AssertionError("num_sem_class must be positive when enable_semantic")
+    noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std if raw_noise_std > 0. else None
+    ch = raw.shape[-1]
+    if endpoint_feat and ch != 11 + C + 128:
+        raw = torch.cat([raw[..., :11 + C], raw[..., -128:]], -1)
+    elif not endpoint_feat and ch != 11 + C:
+        raw = raw[..., :11 + C]
+    rec, w = ops.raw2outputs_rec(raw, z_vals, rays_d, noise, white_bkgd, C, endpoint_feat)
+    g = lambda k: _split_rec(rec, k)  # noqa: E731
+    sem = rec[:, 13:13 + C] if C > 0 else torch.tensor(0)
+    feat = rec[:, 13 + C:13 + C + 128] if endpoint_feat else torch.tensor(0)
+    return g("rgb"), g("disp"), g("acc"), w, g("depth"), sem, feat, g("albedo"), g("shading"), g("residual")
+
+
+def sample_pdf(bins, weights, N_samples, det=False):
+    u = None if det else torch.rand(list(bins.shape[:-1]) + [N_samples], device=bins.device)
+    return ops.sample_pdf(bins, weights, N_samples, u)[0]
+
+
+def batchify_rays(render_fn, rays_flat, chunk=1024 * 32):
+    pieces = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        for k, v in render_fn(rays_flat[i:i + chunk]).items():
+            pieces.setdefault(k, []).append(v)
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in pieces.items()}
+
+
+class SSRRenderer:
+    """The hot-path methods of SSRTrainer."""
+
+    def render_rays(self, flat_rays):
+        shape = flat_rays.shape
+        out = batchify_rays(self.volumetric_rendering, flat_rays, self.chunk)
+        return {k: torch.reshape(v, list(shape[:-1]) + list(v.shape[1:])) for k, v in out.items()}
+
+    def volumetric_rendering(self, ray_batch):
+        N, dev = ray_batch.shape[0], ray_batch.device
+        Sc, Sf = self.N_samples, self.N_importance
+        C = self.num_valid_semantic_class if self.enable_semantic else 0
+        training = bool(self.training)
+        jitter = self.perturb > 0. and training
+        t_rand = torch.rand(N, Sc, device=dev) if jitter else None
+        std = self.raw_noise_std if training else 0
+        noise_c = torch.randn(N, Sc, device=dev) * std if std > 0 else None
+        det = (self.perturb == 0.) or (not training)
+        u = None if (det or Sf == 0) else torch.rand(N, Sf, device=dev)
+        noise_f = torch.randn(N, Sc + Sf, device=dev) * std if (std > 0 and Sf > 0) else None
+        coarse, fine = self.ssr_net_coarse, self.ssr_net_fine
+        if not (isinstance(coarse, Semantic_NeRF) and (fine is None or isinstance(fine, Semantic_NeRF))
+                and isinstance(self.embed_fn, Embedder) and isinstance(self.embeddirs_fn, Embedder)):
+            raise NotImplementedError("SSRRenderer needs intrinsicnerf_b200 Semantic_NeRF networks and embedders "
+                                      "(build them with create_ssr); there is no fallback path")
+        coarse._no_grad_guard(ray_batch)
+        o = ops.render_chunk(ray_batch, coarse.packed(), (fine or coarse).packed() if Sf > 0 else None,
+                             variant=coarse.variant, n_classes=C, n_samples=Sc, n_importance=Sf, lindisp=False,
+                             white_bkgd=self.white_bkgd, endpoint=bool(self.endpoint_feat) and Sf > 0,
+                             pe_scalar_factor=self.embed_fn.scalar_factor, t_rand=t_rand, u=u, noise_coarse=noise_c,
+                             noise_fine=noise_f, want_raw=True)
+        ret = {"raw_coarse": o["raw_coarse"]}
+        names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual")
+        for k in names:
+            ret[k + "_coarse"] = _split_rec(o["rec_coarse"], k)
+        if C > 0:
+            ret["sem_logits_coarse"] = o["rec_coarse"][:, 13:13 + C]
+        if Sf > 0:
+            for k in names:
+                ret[k + "_fine"] = _split_rec(o["rec_fine"], k)
+            if C > 0:
+                ret["sem_logits_fine"] = o["rec_fine"][:, 13:13 + C]
+            ret["z_std"] = o["z_std"]
+            ret["raw_fine"] = o["raw_fine"]
+            if self.endpoint_feat:
+                ret["feat_map_fine"] = o["rec_fine"][:, 13 + C:13 + C + 128]
+        for k in ret:
+            if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
+                print(f"! [Numerical Error] {k} contains nan or inf.")
+        return ret
+
+    def create_ssr(self):
+        cfg = self.config
+        embed_fn, input_ch = get_embedder(cfg["render"]["multires"], cfg["render"]["i_embed"], scalar_factor=10)
+        if not cfg["render"]["use_viewdirs"]:
+            raise NotImplementedError("use_viewdirs=False is not implemented by the CUDA path")
+        embeddirs_fn, input_ch_views = get_embedder(cfg["render"]["multires_views"], cfg["render"]["i_embed"], scalar_factor=1)
+        output_ch = 5 if self.N_importance > 0 else 4
+
+        def make(depth, width):
+            return Semantic_NeRF(enable_semantic=self.enable_semantic, num_semantic_classes=self.num_valid_semantic_class,
+                                 D=depth, W=width, input_ch=input_ch, output_ch=output_ch, skips=[4],
+                                 input_ch_views=input_ch_views, use_viewdirs=True).cuda()
+        model = make(cfg["model"]["netdepth"], cfg["model"]["netwidth"])
+        grad_vars = list(model.parameters())
+        model_fine = None
+        if self.N_importance > 0:
+            model_fine = make(cfg["model"]["netdepth_fine"], cfg["model"]["netwidth_fine"])
+            grad_vars += list(model_fine.parameters())
+        self.optimizer = torch.optim.Adam(params=grad_vars, lr=self.lrate)
+        self.ssr_net_coarse, self.ssr_net_fine = model, model_fine
+        self.embed_fn, self.embeddirs_fn = embed_fn, embeddirs_fn
+
+
+def install_into(trainer_cls):
+    """Rebind the hot-path methods of the reference's SSRTrainer."""
+    for name in ("render_rays", "volumetric_rendering", "create_ssr"):
+        setattr(trainer_cls, name, getattr(SSRRenderer, name))
+    return trainer_cls
