@@ -1,4 +1,684 @@
+// Tensor-core evaluation of the intrinsic field network on sm_100a (INRF_PREC_TC).
+//
+// One persistent CTA per SM walks 128-sample tiles.  Per tile the whole network
+// (NeRF.forward, object_level/run_nerf_helpers.py:284-325 / Semantic_NeRF.forward,
+// SSR/models/semantic_nerf.py:123-181, fused with the Embedder and run_network's
+// per-sample view-direction expansion) runs without touching HBM in between:
+//
+//   warp 0      weight producer : streams the pre-swizzled fp16 operand blocks of the packed
+//                                 blob (pack.cu, MMA issue order) into a shared-memory ring with
+//                                 cp.async.bulk + mbarrier complete_tx (TMA bulk copies)
+//   warp 1      MMA issuer      : one thread issues tcgen05.mma (kind::f16, M=128, N=128/16..112,
+//                                 K=16) with fp32 accumulators in TMEM; tcgen05.commit signals
+//                                 "accumulator half ready", "weight slot free", "A chunk free"
+//   warps 4-7   front end       : sample position (o + d z), range-reduced sin/cos positional
+//                                 encoding of the NEXT tile, written as fp16 UMMA operand tiles
+//   warps 8-15  epilogue        : tcgen05.ld accumulator -> +bias, ReLU (fp32) -> fp16 -> the next
+//                                 layer's A operand (SWIZZLE_128B K-major), in place; sigma head as
+//                                 an fp32 dot product on the un-rounded trunk output; sigmoid heads;
+//                                 packed raw rows to HBM
+//
+// The accumulator of layer l (TMEM columns (l&1)*256..) is drained by the epilogue in two N
+// halves while the tensor pipe already runs layer l's second half / layer l+1, so the tensor
+// core only waits for the first A chunk of each layer.
+//
+// Arithmetic: operands rounded to fp16 (RN, 11-bit significand), products and sums in fp32.
+// feature_linear has no activation, so views_linears.0 o feature_linear is composed into one
+// 128x256 matrix at pack time (pack.cu) - one 256x256 GEMM per sample less than the literal graph.
 #include "common.cuh"
+#include <stdlib.h>
+
 namespace inrf {
-int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) { set_error("tc path not built yet"); return INRF_EUNSUPPORTED; }
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 512;
+constexpr int NS = 6;                       // weight ring stages
+constexpr int CHUNK = 16384;                // 128 rows x 64 fp16, SWIZZLE_128B
+// shared memory map (bytes)
+constexpr int SM_H = 0;                     // 4 chunks: hidden activations (A operand), in place
+constexpr int SM_PE = SM_H + 4 * CHUNK;     // gamma(x): 63 cols + zero
+constexpr int SM_DIR = SM_PE + CHUNK;       // gamma(d): 27 cols + zeros (only K=32 is multiplied)
+constexpr int SM_V = SM_DIR + CHUNK;        // 2 chunks: relu(views')
+constexpr int SM_RING = SM_V + 2 * CHUNK;
+constexpr int SM_SIG = SM_RING + NS * TC_SLOT_BYTES;   // [128][2] fp32 sigma partials
+constexpr int SM_BAR = SM_SIG + 1024;
+constexpr int SM_TOTAL = SM_BAR + 512;
+static_assert(SM_TOTAL <= 232448, "shared memory budget");
+
+// bias table offsets (floats), written by pack.cu:k_pack_tc_bias
+constexpr int TCB_VIEWS = 2048, TCB_SEM1 = 2176, TCB_ALBSH = 2304, TCB_ALPHA_W = 2560, TCB_ALPHA_B = 2816,
+              TCB_ALB2 = 2817, TCB_SH2 = 2820, TCB_RES = 2821, TCB_SEM2 = 2824;
+
+// barrier ids
+enum {
+  B_WFULL = 0,                 // [NS]
+  B_WEMPTY = B_WFULL + NS,     // [NS]
+  B_PE_READY = B_WEMPTY + NS, B_PE_FREE, B_DIR_READY, B_DIR_FREE,
+  B_A_READY,                   // [4]
+  B_A_FREE = B_A_READY + 4,    // [4]
+  B_ACC_FULL = B_A_FREE + 4,   // [4] = parity*2 + half
+  B_V_READY = B_ACC_FULL + 4,  // [2]
+  B_V_FREE = B_V_READY + 2,
+  B_SMALL_FULL, B_SEM2_FULL, B_TAIL_DONE,
+  B_COUNT
+};
+static_assert(B_COUNT <= 48, "barrier ids must fit the 64-bit phase mask and the 512 B area");
+
+struct Params {
+  MlpArgs a;
+  const unsigned char* blocks;    // fp16 operand blocks
+  const float* bias;              // fp32 bias table
+  int n_blocks;
+  int block_off[TC_MAX_BLOCKS];   // byte offsets
+  int block_bytes[TC_MAX_BLOCKS];
+  int out_ch, C, sem_rows;
+  int* dbg;                       // [16] watchdog record (device)
+};
+
+__device__ int g_dbg[16];
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp):
+//  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024>>4 |
+//  [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// barrier bookkeeping with a watchdog: a stuck wait records who/where, raises a global abort
+// flag and lets every role run to the end (garbage out, but no hung GPU and no lost context)
+// ------------------------------------------------------------------------------------------
+struct Sync {
+  uint32_t bar0;          // smem address of barrier 0
+  uint64_t phase;         // one parity bit per barrier id
+  int* dbg;
+  bool dead;
+  int tile;
+  __device__ __forceinline__ uint32_t addr(int id) const { return bar0 + 8u * id; }
+  __device__ __forceinline__ void wait(int id) {
+    const uint32_t parity = (uint32_t)((phase >> id) & 1ull);
+    phase ^= (1ull << id);
+    if (dead) return;
+    if (mbar_try(addr(id), parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try(addr(id), parity)) {
+      if ((++spins & 0x3ff) == 0) {
+        if (*(volatile int*)dbg != 0) { dead = true; return; }
+        if (clock64() - t0 > 3000000000LL) {
+          if (atomicCAS(dbg, 0, 1) == 0) {
+            dbg[1] = id; dbg[2] = threadIdx.x >> 5; dbg[3] = tile; dbg[4] = blockIdx.x; dbg[5] = (int)parity;
+            __threadfence();
+          }
+          dead = true;
+          return;
+        }
+      }
+    }
+  }
+};
+
+// one K-major SWIZZLE_128B row address: 8-row atoms of 1024 B, 16-byte unit XOR (row & 7)
+__device__ __forceinline__ uint32_t swz(uint32_t chunk_base, int row, int unit) {
+  return chunk_base + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------
+// front end: positional encoding with one shared range reduction per coordinate.
+// sin(2^k x) = sin(2 pi frac(2^k x/(2 pi))): x/(2 pi) is formed as a two-float product, scaling by
+// 2^k and taking the fractional part are exact, so the argument error does not grow with k.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pe_coord(float x, int n_freqs, float* s, float* c) {
+  const float HI = 0.15915494f, LO = 6.4206383e-09f, TWO_PI = 6.2831855f;
+  float p = x * HI;
+  float e = fmaf(x, HI, -p);
+  float lo = fmaf(x, LO, e);
+  float sc = 1.f;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    if (k < n_freqs) {
+      float ph = p * sc;
+      float r = (ph - rintf(ph)) + lo * sc;
+      float ang = r * TWO_PI;
+      s[k] = __sinf(ang);
+      c[k] = __cosf(ang);
+    }
+    sc *= 2.f;
+  }
+}
+
+__device__ __forceinline__ void write_units(uint32_t chunk, int row, const float* v, int n_units) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    if (u < n_units)
+      st_shared_v4(swz(chunk, row, u), pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
+                   pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7]));
+  }
+}
+
+__device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row, int64_t n_tiles) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    sy.tile = (int)tile;
+    int64_t m = tile * TILE_M + row;
+    if (m >= P.a.M) m = P.a.M - 1;
+    float x[3], d[3];
+    const bool pre_embedded = P.a.emb != nullptr;
+    const float* e = pre_embedded ? P.a.emb + m * (PE_PTS + PE_DIR) : nullptr;
+    if (!pre_embedded) {
+      if (P.a.rays != nullptr) {
+        const int64_t n = m / P.a.S;
+        const float* ray = P.a.rays + n * 11;
+        const float zv = __ldg(P.a.z + m);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          x[i] = __fadd_rn(__ldg(ray + i), __fmul_rn(__ldg(ray + 3 + i), zv));   // o + d z (run_nerf.py:488)
+          d[i] = __ldg(ray + 8 + i);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { x[i] = __ldg(P.a.pts + m * 3 + i); d[i] = __ldg(P.a.viewdirs + m * 3 + i); }
+      }
+      if (P.a.pe_scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[i] = __fdiv_rn(x[i], P.a.pe_scale);
+      }
+    }
+    {
+      float pe[64];
+      if (pre_embedded) {
+#pragma unroll
+        for (int i = 0; i < 63; ++i) pe[i] = __ldg(e + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float s[10], c[10];
+          pe_coord(x[i], 10, s, c);
+          pe[i] = x[i];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) { pe[3 + 6 * k + i] = s[k]; pe[3 + 6 * k + 3 + i] = c[k]; }
+        }
+      }
+      pe[63] = 0.f;
+      sy.wait(B_PE_FREE);
+      write_units(smem_base + SM_PE, row, pe, 8);
+      fence_async_smem();
+      mbar_arrive(sy.addr(B_PE_READY));
+    }
+    {
+      float de[32];
+      if (pre_embedded) {
+#pragma unroll
+        for (int i = 0; i < 27; ++i) de[i] = __ldg(e + 63 + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float s[10], c[10];
+          pe_coord(d[i], 4, s, c);
+          de[i] = d[i];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { de[3 + 6 * k + i] = s[k]; de[3 + 6 * k + 3 + i] = c[k]; }
+        }
+      }
+#pragma unroll
+      for (int i = 27; i < 32; ++i) de[i] = 0.f;
+      sy.wait(B_DIR_FREE);
+      write_units(smem_base + SM_DIR, row, de, 4);
+      fence_async_smem();
+      mbar_arrive(sy.addr(B_DIR_READY));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight producer
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t smem_base, int64_t n_tiles) {
+  int slot = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    sy.tile = (int)tile;
+    for (int b = 0; b < P.n_blocks; ++b) {
+      sy.wait(B_WEMPTY + slot);
+      if (!sy.dead) {
+        mbar_expect_tx(sy.addr(B_WFULL + slot), (uint32_t)P.block_bytes[b]);
+        bulk_g2s(smem_base + SM_RING + slot * TC_SLOT_BYTES, P.blocks + P.block_off[b], (uint32_t)P.block_bytes[b],
+                 sy.addr(B_WFULL + slot));
+      }
+      slot = (slot + 1 == NS) ? 0 : slot + 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MMA issuer (one thread)
+// ------------------------------------------------------------------------------------------
+struct Issuer {
+  Sync& sy;
+  uint32_t smem_base, tmem;
+  int slot;
+  // one operand block: A chunk (K = 16*ksteps) x ring slot -> accumulator columns [col, col+n)
+  __device__ __forceinline__ void block(uint32_t a_chunk, int ksteps, int n, uint32_t col, bool first) {
+    sy.wait(B_WFULL + slot);
+    tc_fence_after();
+    const uint64_t ad = make_desc(a_chunk);
+    const uint64_t bd = make_desc(smem_base + SM_RING + slot * TC_SLOT_BYTES);
+    const uint32_t id = make_idesc(n);
+#pragma unroll 4
+    for (int k = 0; k < ksteps; ++k)
+      tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+    tc_commit(sy.addr(B_WEMPTY + slot));
+    slot = (slot + 1 == NS) ? 0 : slot + 1;
+  }
+};
+
+__device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int64_t n_tiles) {
+  Issuer I{sy, smem_base, tmem, 0};
+  const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    sy.tile = (int)tile;
+    sy.wait(B_TAIL_DONE);               // previous tile's accumulators drained
+    tc_fence_after();
+    // ---- trunk layer 0: K = 64 (gamma(x)) ------------------------------------------------
+    sy.wait(B_PE_READY);
+    tc_fence_after();
+    for (int h = 0; h < 2; ++h) {
+      I.block(PE, 4, 128, h * 128, true);
+      tc_commit(sy.addr(B_ACC_FULL + h));
+    }
+    // ---- trunk layers 1..7 -----------------------------------------------------------------
+    for (int l = 1; l < 8; ++l) {
+      const uint32_t acc = (l & 1) * 256;
+      for (int h = 0; h < 2; ++h) {
+        bool first = true;
+        if (l == 5) {                    // skip connection: [gamma(x), h] -> K = 64 + 256
+          I.block(PE, 4, 128, acc + h * 128, true);
+          first = false;
+          if (h == 1) tc_commit(sy.addr(B_PE_FREE));
+        }
+        for (int c = 0; c < 4; ++c) {
+          if (h == 0) { sy.wait(B_A_READY + c); tc_fence_after(); }
+          I.block(H + c * CHUNK, 4, 128, acc + h * 128, first);
+          first = false;
+          if (h == 1) tc_commit(sy.addr(B_A_FREE + c));
+        }
+        tc_commit(sy.addr(B_ACC_FULL + (l & 1) * 2 + h));
+      }
+    }
+    // ---- views' = relu(W' h + Wd gamma(d) + b')  -> accumulator 0, half 0 ----------------------
+    for (int c = 0; c < 4; ++c) {
+      sy.wait(B_A_READY + c);
+      tc_fence_after();
+      I.block(H + c * CHUNK, 4, 128, 0, c == 0);
+    }
+    sy.wait(B_DIR_READY);
+    tc_fence_after();
+    I.block(DIR, 2, 128, 0, false);
+    tc_commit(sy.addr(B_DIR_FREE));
+    tc_commit(sy.addr(B_ACC_FULL + 0));
+    // ---- semantic hidden layer -> accumulator 0, half 1 ----------------------------------------
+    if (P.C > 0) {
+      for (int c = 0; c < 4; ++c) I.block(H + c * CHUNK, 4, 128, 128, c == 0);
+      tc_commit(sy.addr(B_ACC_FULL + 1));
+    }
+    // ---- albedo1 | shading1 -> accumulator 1 ----------------------------------------------------
+    for (int h = 0; h < 2; ++h) {
+      for (int c = 0; c < 4; ++c) {
+        I.block(H + c * CHUNK, 4, 128, 256 + h * 128, c == 0);
+        if (h == 1) tc_commit(sy.addr(B_A_FREE + c));
+      }
+      tc_commit(sy.addr(B_ACC_FULL + 2 + h));
+    }
+    // ---- residual head on relu(views'): 16 x 128 -> accumulator 0 cols [0,16) -------------------
+    for (int c = 0; c < 2; ++c) {
+      sy.wait(B_V_READY + c);
+      tc_fence_after();
+      I.block(V + c * CHUNK, 4, 16, 0, c == 0);
+    }
+    tc_commit(sy.addr(B_V_FREE));
+    // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> cols [16,32) ---------------
+    for (int c = 0; c < 4; ++c) {
+      sy.wait(B_A_READY + c);
+      tc_fence_after();
+      I.block(H + c * CHUNK, 4, 16, 16, c == 0);
+      tc_commit(sy.addr(B_A_FREE + c));
+    }
+    tc_commit(sy.addr(B_SMALL_FULL));
+    // ---- semantic logits on relu(sem1): C x 128 -> accumulator 1 cols [0, sem_rows) ---------------
+    if (P.C > 0) {
+      for (int c = 0; c < 2; ++c) {
+        sy.wait(B_A_READY + c);
+        tc_fence_after();
+        I.block(H + c * CHUNK, 4, P.sem_rows, 256, c == 0);
+        tc_commit(sy.addr(B_A_FREE + c));
+      }
+      tc_commit(sy.addr(B_SEM2_FULL));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue warps
+// ------------------------------------------------------------------------------------------
+// 32 accumulator columns of this thread's row: +bias, optional ReLU, optional sigma partial,
+// fp16 pack, 4 swizzled 16-byte stores into the destination A chunk.
+template <bool RELU>
+__device__ __forceinline__ void epi_pass(uint32_t taddr, const float* __restrict__ bias, uint32_t dst_chunk, int row,
+                                         int unit0, Sync& sy, int free_bar, const float* __restrict__ alpha_w,
+                                         float* sigma_acc, float* gout) {
+  uint32_t v[32];
+  float b[32];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(bias) + i);
+    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  }
+  tmem_ld32(taddr, v);
+  tmem_ld_wait();
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float x = __uint_as_float(v[i]) + b[i];
+    f[i] = RELU ? fmaxf(x, 0.f) : x;
+  }
+  if (alpha_w != nullptr) {
+    float s = *sigma_acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(alpha_w) + i);
+      s = fmaf(f[4 * i], t.x, s); s = fmaf(f[4 * i + 1], t.y, s); s = fmaf(f[4 * i + 2], t.z, s); s = fmaf(f[4 * i + 3], t.w, s);
+    }
+    *sigma_acc = s;
+  }
+  if (gout != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) gout[i] = f[i];
+  }
+  if (free_bar >= 0) sy.wait(free_bar);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    st_shared_v4(swz(dst_chunk, row, unit0 + u), pack_h2(f[8 * u], f[8 * u + 1]), pack_h2(f[8 * u + 2], f[8 * u + 3]),
+                 pack_h2(f[8 * u + 4], f[8 * u + 5]), pack_h2(f[8 * u + 6], f[8 * u + 7]));
+}
+
+__device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* smem, uint32_t smem_base, uint32_t tmem,
+                                         int q, int j, int lane, int64_t n_tiles) {
+  const int row = q * 32 + lane;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  float* s_sig = reinterpret_cast<float*>(smem + SM_SIG);
+  const uint32_t H = smem_base + SM_H, V = smem_base + SM_V;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    sy.tile = (int)tile;
+    const int64_t m = tile * TILE_M + row;
+    const bool valid = m < P.a.M;
+    float* grow = P.a.raw + (valid ? m : 0) * P.out_ch;
+    // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
+    float sig = 0.f;
+    for (int l = 0; l < 8; ++l) {
+      for (int h = 0; h < 2; ++h) {
+        sy.wait(B_ACC_FULL + (l & 1) * 2 + h);
+        tc_fence_after();
+        const int c = 2 * h + j;                       // destination chunk (64 columns)
+#pragma unroll 1
+        for (int p2 = 0; p2 < 2; ++p2) {
+          const int col = h * 128 + j * 64 + p2 * 32;
+          epi_pass<true>(lane_addr + (l & 1) * 256 + col, P.bias + l * 256 + col, H + c * CHUNK, row, p2 * 4, sy,
+                         p2 == 0 ? B_A_FREE + c : -1, l == 7 ? P.bias + TCB_ALPHA_W + col : nullptr, &sig, nullptr);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(sy.addr(B_A_READY + c));
+      }
+    }
+    s_sig[row * 2 + j] = sig;                          // fixed-order sum later: deterministic sigma
+    // ---- relu(views') -> V chunk j (and the endpoint feature rows) --------------------------------
+    sy.wait(B_ACC_FULL + 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int p2 = 0; p2 < 2; ++p2) {
+      const int col = j * 64 + p2 * 32;
+      float* g = (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C + col : nullptr;
+      epi_pass<true>(lane_addr + col, P.bias + TCB_VIEWS + col, V + j * CHUNK, row, p2 * 4, sy,
+                     p2 == 0 ? B_V_FREE : -1, nullptr, nullptr, g);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    mbar_arrive(sy.addr(B_V_READY + j));
+    // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ------------------------------
+    for (int h = 0; h < 2; ++h) {
+      sy.wait(B_ACC_FULL + 2 + h);
+      tc_fence_after();
+      const int c = 2 * h + j;
+#pragma unroll 1
+      for (int p2 = 0; p2 < 2; ++p2) {
+        const int col = h * 128 + j * 64 + p2 * 32;
+        epi_pass<true>(lane_addr + 256 + col, P.bias + TCB_ALBSH + col, H + c * CHUNK, row, p2 * 4, sy,
+                       p2 == 0 ? B_A_FREE + c : -1, nullptr, nullptr, nullptr);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(sy.addr(B_A_READY + c));
+    }
+    // ---- relu(sem1) -> H chunk j (after the albedo2/shading2 MMAs released it) ------------------------
+    if (P.C > 0) {
+      sy.wait(B_ACC_FULL + 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int p2 = 0; p2 < 2; ++p2) {
+        const int col = j * 64 + p2 * 32;
+        epi_pass<true>(lane_addr + 128 + col, P.bias + TCB_SEM1 + col, H + j * CHUNK, row, p2 * 4, sy,
+                       p2 == 0 ? B_A_FREE + j : -1, nullptr, nullptr, nullptr);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(sy.addr(B_A_READY + j));
+    }
+    // ---- heads -> raw row ------------------------------------------------------------------------------
+    sy.wait(B_SMALL_FULL);
+    if (P.C > 0) sy.wait(B_SEM2_FULL);
+    tc_fence_after();
+    __syncwarp();
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // both sigma partials of every row are in smem
+    if (j == 0) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + 0, v);
+      tmem_ld_wait();
+      if (valid) {
+        float res[3], alb[3], sh;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) res[i] = sigmoid_(__uint_as_float(v[i]) + __ldg(P.bias + TCB_RES + i));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) alb[i] = sigmoid_(__uint_as_float(v[16 + i]) + __ldg(P.bias + TCB_ALB2 + i));
+        sh = sigmoid_(__uint_as_float(v[19]) + __ldg(P.bias + TCB_SH2));
+        const float sigma = (s_sig[row * 2] + s_sig[row * 2 + 1]) + __ldg(P.bias + TCB_ALPHA_B);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grow[i] = __fadd_rn(__fmul_rn(alb[i], sh), res[i]);
+        grow[3] = sigma;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grow[4 + i] = alb[i];
+        grow[7] = sh;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grow[8 + i] = res[i];
+      }
+    } else if (P.C > 0) {
+      for (int c0 = 0; c0 < P.C; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + 256 + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < P.C) grow[INRF_RAW_BASE + c0 + i] = __uint_as_float(v[i]) + __ldg(P.bias + TCB_SEM2 + c0 + i);
+        }
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // s_sig may be rewritten by the next tile
+    mbar_arrive(sy.addr(B_TAIL_DONE));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant__ Params P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * B_COUNT);
+  const int64_t n_tiles = (P.a.M + TILE_M - 1) / TILE_M;
+
+  Sync sy;
+  sy.bar0 = smem_base + SM_BAR;
+  sy.dbg = P.dbg;
+  sy.dead = false;
+  sy.tile = -1;
+  sy.phase = 0;
+  if ((smem_base & 1023u) != 0) {                    // SWIZZLE_128B atoms need 1024 B alignment
+    if (threadIdx.x == 0 && atomicCAS(P.dbg, 0, 2) == 0) P.dbg[1] = (int)smem_base;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), 1); }
+    mbar_init(sy.addr(B_PE_READY), 128); mbar_init(sy.addr(B_PE_FREE), 1);
+    mbar_init(sy.addr(B_DIR_READY), 128); mbar_init(sy.addr(B_DIR_FREE), 1);
+    for (int c = 0; c < 4; ++c) { mbar_init(sy.addr(B_A_READY + c), 128); mbar_init(sy.addr(B_A_FREE + c), 1); mbar_init(sy.addr(B_ACC_FULL + c), 1); }
+    for (int c = 0; c < 2; ++c) mbar_init(sy.addr(B_V_READY + c), 128);
+    mbar_init(sy.addr(B_V_FREE), 1);
+    mbar_init(sy.addr(B_SMALL_FULL), 1); mbar_init(sy.addr(B_SEM2_FULL), 1);
+    mbar_init(sy.addr(B_TAIL_DONE), 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // "free"-type barriers start released: the first wait must pass on a fresh barrier
+  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_PE_FREE) | (1ull << B_DIR_FREE) |
+                            (0xFull << B_A_FREE) | (1ull << B_V_FREE) | (1ull << B_TAIL_DONE);
+  sy.phase = released;
+
+  if (warp == 0) {
+    if (lane == 0) producer(P, sy, smem_base, n_tiles);
+  } else if (warp == 1) {
+    if (lane == 0) issuer(P, sy, smem_base, tmem, n_tiles);
+  } else if (warp >= 4 && warp < 8) {
+    front_end(P, sy, smem_base, (warp - 4) * 32 + lane, n_tiles);
+  } else if (warp >= 8) {
+    epilogue(P, sy, smem, smem_base, tmem, warp & 3, (warp - 8) >> 2, lane, n_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+}  // namespace tc
+
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
+  if (a.M == 0) return INRF_OK;
+  NetLayout L;
+  int rc = make_layout(a.variant, a.n_classes, &L);
+  if (rc) return rc;
+  TcProgram prog;
+  rc = make_tc_program(a.variant, a.n_classes, &prog);
+  if (rc) return rc;
+  tc::Params P;
+  P.a = a;
+  const unsigned char* blob = static_cast<const unsigned char*>(a.packed);
+  P.blocks = blob + L.tc_blocks;
+  P.bias = reinterpret_cast<const float*>(blob + L.tc_bias);
+  P.n_blocks = prog.n_blocks;
+  for (int i = 0; i < prog.n_blocks; ++i) { P.block_off[i] = prog.blk[i].byte_off; P.block_bytes[i] = prog.blk[i].rows * 128; }
+  P.out_ch = raw_channels(a.n_classes, a.endpoint);
+  P.C = a.n_classes;
+  P.sem_rows = (a.n_classes + 15) / 16 * 16;
+  int* dbg = nullptr;
+  INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, tc::g_dbg));
+  P.dbg = dbg;
+  static const bool checked = getenv("INRF_TC_CHECK") != nullptr && getenv("INRF_TC_CHECK")[0] == '1';
+  if (checked) INRF_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(int), st));
+  INRF_CUDA(cudaFuncSetAttribute(tc::k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
+  int dev = 0, sms = 148;
+  INRF_CUDA(cudaGetDevice(&dev));
+  INRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t tiles = (a.M + tc::TILE_M - 1) / tc::TILE_M;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  tc::k_mlp_tc<<<grid, tc::NUM_THREADS, tc::SM_TOTAL, st>>>(P);
+  INRF_LAUNCH_CHECK();
+  if (checked) {      // debug mode: synchronise and surface watchdog records as errors
+    int h[16];
+    INRF_CUDA(cudaStreamSynchronize(st));
+    INRF_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[0] == 1) { set_error("mlp_tc watchdog: barrier %d stuck (warp %d, tile %d, cta %d, parity %d)", h[1], h[2], h[3], h[4], h[5]); return INRF_ECUDA; }
+    if (h[0] == 2) { set_error("mlp_tc: dynamic shared memory base 0x%x is not 1024-byte aligned", h[1]); return INRF_ECUDA; }
+  }
+  return INRF_OK;
+}
+
+}  // namespace inrf

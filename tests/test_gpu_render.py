@@ -1,0 +1,170 @@
+"""GPU parity of the fused renderer (render_rays / volumetric_rendering / render) against the
+CPU oracle and the reference's golden vectors.  Tolerance: 1e-4 relative (floor 1e-3 on the
+denominator), the bound BASELINE.json's north_star states, on the well-conditioned 'opaque'
+weight set."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as orc
+from tests.util import build_nets, load_golden, rec_get, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+KEYS = ("rgb", "disp", "acc", "albedo", "shading", "residual")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def obj_nets():
+    return build_nets("object")
+
+
+def _object_kwargs(coarse, fine, **over):
+    from intrinsicnerf_b200 import object_level as ol
+    e, _ = ol.get_embedder(10, 0)
+    ed, _ = ol.get_embedder(4, 0)
+    kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=ol._FusedQuery(e, ed, 65536), N_samples=64,
+              N_importance=128, perturb=0., white_bkgd=True, raw_noise_std=0.)
+    kw.update(over)
+    return kw
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_render_rays_golden(dev, golden_dir, obj_nets, precision):
+    """The reference's own outputs (golden) for the deterministic, stochastic (pytest hooks),
+    lindisp/black-background and coarse-only configurations."""
+    from intrinsicnerf_b200 import object_level as ol, ops
+    coarse, fine, pc, pf = obj_nets
+    g = load_golden(golden_dir, "object_render.npz")
+    rays = torch.from_numpy(g["rays"]).to(dev)
+    ops.set_default_precision(precision)
+    try:
+        with torch.no_grad():
+            det = ol.render_rays(rays, retraw=True, **_object_kwargs(coarse, fine))
+            sto = ol.render_rays(rays, pytest=True, **_object_kwargs(coarse, fine, perturb=1.0, raw_noise_std=1.0))
+            lin = ol.render_rays(rays, **_object_kwargs(coarse, fine, lindisp=True, white_bkgd=False))
+            co = ol.render_rays(rays, **_object_kwargs(coarse, None, N_importance=0))
+    finally:
+        ops.set_default_precision("tc")
+    for prefix, res in (("det_", det), ("sto_", sto), ("lin_", lin)):
+        for k in KEYS:
+            assert rel_err(res[k + "_map"], g[prefix + k + "_map"]) < TOL, (prefix, k, rel_err(res[k + "_map"], g[prefix + k + "_map"]))
+            assert rel_err(res[k + "0"], g[prefix + k + "0"]) < TOL, (prefix, k)
+        assert rel_err(res["z_std"], g[prefix + "z_std"]) < TOL
+    assert set(co.keys()) == {k + "_map" for k in KEYS}
+    for k in KEYS:
+        assert rel_err(co[k + "_map"], g["co_" + k + "_map"]) < TOL
+    assert det["raw"].shape == (rays.shape[0], 192, 11)
+    assert rel_err(det["raw"], g["det_raw"], floor=1e-2) < 5e-4       # per-sample raw: fine z differs by rounding
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_render_image_api_and_chunking(dev, golden_dir, obj_nets, precision):
+    """render(): ray generation, packing, chunk loop, reshape and the 7-entry return list."""
+    from intrinsicnerf_b200 import object_level as ol, ops
+    coarse, fine, pc, pf = obj_nets
+    g = load_golden(golden_dir, "object_render.npz")
+    K = np.array(orc.blender_intrinsics(6, 6))
+    c2w = orc.pose_spherical(-180.0, -30.0, 4.0)[:3, :4].to(dev)
+    kw = _object_kwargs(coarse, fine)
+    ops.set_default_precision(precision)
+    try:
+        with torch.no_grad():
+            out = ol.render(6, 6, K, chunk=32768, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+            out_small = ol.render(6, 6, K, chunk=7, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+    finally:
+        ops.set_default_precision("tc")
+    assert len(out) == 7 and out[0].shape == (6, 6, 3) and out[1].shape == (6, 6)
+    for i, k in enumerate(KEYS):
+        assert rel_err(out[i], g["img_" + k]) < TOL, k
+        assert torch.equal(out[i], out_small[i]), "results must not depend on the chunk size"
+    for k in ("rgb0", "disp0", "acc0", "albedo0", "shading0", "residual0", "z_std"):
+        assert rel_err(out[6][k], g["img_" + k]) < TOL, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_ssr_renderer_golden(dev, golden_dir, precision):
+    from intrinsicnerf_b200 import ops, ssr
+    g = load_golden(golden_dir, "ssr_render.npz")
+    C = int(g["C"])
+    coarse, fine, pc, pf = build_nets("ssr", C)
+
+    class T(ssr.SSRRenderer):
+        pass
+    t = T()
+    t.N_samples, t.N_importance, t.perturb, t.raw_noise_std = 64, 128, 1, 1.0
+    t.white_bkgd, t.enable_semantic, t.num_valid_semantic_class, t.endpoint_feat = False, True, C, False
+    t.netchunk = t.chunk = 32768
+    t.ssr_net_coarse, t.ssr_net_fine = coarse, fine
+    t.embed_fn, _ = ssr.get_embedder(10, 0, scalar_factor=10)
+    t.embeddirs_fn, _ = ssr.get_embedder(4, 0, scalar_factor=1)
+    rays = torch.from_numpy(g["rays"]).to(dev)
+    ops.set_default_precision(precision)
+    try:
+        t.training = False
+        with torch.no_grad():
+            ev = t.render_rays(rays)
+            t.endpoint_feat = True
+            ep = t.render_rays(rays)
+    finally:
+        ops.set_default_precision("tc")
+    names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual", "sem_logits")
+    for k in names:
+        for lvl in ("coarse", "fine"):
+            assert rel_err(ev[f"{k}_{lvl}"], g[f"eval_{k}_{lvl}"]) < TOL, (k, lvl, rel_err(ev[f"{k}_{lvl}"], g[f"eval_{k}_{lvl}"]))
+    assert rel_err(ev["z_std"], g["eval_z_std"]) < TOL
+    assert ev["raw_coarse"].shape == (rays.shape[0], 64, 11 + C) and ev["raw_fine"].shape == (rays.shape[0], 192, 11 + C)
+    assert rel_err(ep["feat_map_fine"], g["ep_feat_map_fine"]) < TOL
+    assert ep["raw_fine"].shape[-1] == 11 + C + 128
+
+
+def test_ssr_training_mode_replay_against_oracle(dev, golden_dir):
+    """Training-mode randomness (jitter, sigma noise, random u) injected identically into the
+    oracle and the kernels (fp32 mode)."""
+    from intrinsicnerf_b200 import ops
+    g = load_golden(golden_dir, "ssr_render.npz")
+    C = int(g["C"])
+    coarse, fine, pc, pf = build_nets("ssr", C)
+    rays = torch.from_numpy(g["rays"])
+    rnd = {k: torch.from_numpy(g["train_" + k]) for k in ("t_rand", "u", "noise_coarse", "noise_fine")}
+    o = ops.render_chunk(rays.to(dev), coarse.packed(), fine.packed(), variant=1, n_classes=C, pe_scalar_factor=10.0,
+                         precision="fp32", **{k: v.to(dev) for k, v in rnd.items()})
+    names = dict(rgb="rgb", disp="disp", acc="acc", depth="depth", albedo="albedo", shading="shading", residual="residual")
+    for k in names:
+        assert rel_err(rec_get(o["rec_fine"], k), g[f"train_{k}_fine"]) < TOL, k
+        assert rel_err(rec_get(o["rec_coarse"], k), g[f"train_{k}_coarse"]) < TOL, k
+    assert rel_err(o["rec_fine"][:, 13:13 + C], g["train_sem_logits_fine"]) < TOL
+
+
+def test_tc_matches_fp32_on_larger_batch(dev, obj_nets):
+    """Tensor-core path vs the strict fp32 path on 4096 rays (sizes the CPU oracle would need
+    minutes for): every map within 1e-4, merged depths within 2e-6."""
+    from intrinsicnerf_b200 import ops
+    coarse, fine, pc, pf = obj_nets
+    rays = orc.blender_rays(64, 64).to(dev)
+    a = ops.render_chunk(rays, coarse.packed(), fine.packed(), white_bkgd=True, precision="fp32", want_z=True)
+    b = ops.render_chunk(rays, coarse.packed(), fine.packed(), white_bkgd=True, precision="tc", want_z=True)
+    for k in KEYS:
+        assert rel_err(rec_get(b["rec_fine"], k), rec_get(a["rec_fine"], k)) < TOL, k
+        assert rel_err(rec_get(b["rec_coarse"], k), rec_get(a["rec_coarse"], k)) < TOL, k
+    assert (a["z_fine"] - b["z_fine"]).abs().max() < 1e-3
+    assert bool((b["z_fine"][:, 1:] >= b["z_fine"][:, :-1]).all())      # sortedness at full size
+
+
+def test_oracle_end_to_end_medium(dev, obj_nets):
+    """256 rays through the full CPU oracle vs the kernels (both precisions)."""
+    from intrinsicnerf_b200 import ops
+    coarse, fine, pc, pf = obj_nets
+    rays = orc.blender_rays(16, 16)
+    want = orc.render_rays(rays, pc, pf, white_bkgd=True)
+    for prec in ("fp32", "tc"):
+        o = ops.render_chunk(rays.to(dev), coarse.packed(), fine.packed(), white_bkgd=True, precision=prec)
+        for k in KEYS:
+            assert rel_err(rec_get(o["rec_fine"], k), want["fine"][k]) < TOL, (prec, k)
+            assert rel_err(rec_get(o["rec_coarse"], k), want["coarse"][k]) < TOL, (prec, k)
+        assert rel_err(o["z_std"], want["z_std"]) < TOL

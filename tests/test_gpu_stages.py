@@ -1,0 +1,154 @@
+"""GPU parity: every stage kernel against the CPU oracle (and the reference's golden vectors)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as orc
+from tests.util import build_nets, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_embed_matches_oracle_and_golden(dev, golden_dir):
+    from intrinsicnerf_b200 import ops
+    g = load_golden(golden_dir, "object_stages.npz")
+    x = torch.from_numpy(g["x"])
+    out = ops.embed(x.to(dev), 10).cpu()
+    # |x*2^9| reaches ~2e3 rad: CUDA sinf/cosf (<=2 ulp) vs ATen's vectorised sin (<=1 ulp)
+    assert np.abs(out.numpy() - g["emb_pts"]).max() < 5e-7
+    d = x / x.norm(dim=-1, keepdim=True)
+    assert np.abs(ops.embed(d.to(dev), 4).cpu().numpy() - g["emb_dir"]).max() < 5e-7
+    out10 = ops.embed(x.to(dev), 10, 10.0).cpu()
+    assert (out10 - orc.posenc(x, 10, 10.0)).abs().max() < 5e-7
+    assert ops.embed(torch.zeros(0, 3, device=dev), 10).shape == (0, 63)      # empty input
+
+
+def test_coarse_z_bitexact(dev):
+    from intrinsicnerf_b200 import ops
+    rays = orc.blender_rays(5, 7)
+    rays[:, 6] = torch.linspace(0.5, 2.0, rays.shape[0])
+    g = torch.Generator().manual_seed(0)
+    t_rand = torch.rand(rays.shape[0], 64, generator=g)
+    for lindisp in (False, True):
+        for tr in (None, t_rand):
+            want = orc.coarse_z(rays[:, 6:7], rays[:, 7:8], 64, lindisp, tr)
+            got = ops.coarse_z(rays.to(dev), 64, lindisp, None if tr is None else tr.to(dev)).cpu()
+            assert torch.equal(got, want), (lindisp, tr is None, (got - want).abs().max())
+
+
+@pytest.mark.parametrize("variant,C", [("object", 0), ("ssr", 28), ("ssr", 0)])
+def test_mlp_fp32_matches_oracle(dev, variant, C):
+    from intrinsicnerf_b200 import ops
+    coarse, fine, pc, pf = build_nets(variant, C)
+    g = torch.Generator().manual_seed(5)
+    M = 200                                            # not a multiple of the 64-row tile
+    pts = torch.rand(M, 3, generator=g) * 8 - 4
+    vd = torch.randn(M, 3, generator=g)
+    vd = vd / vd.norm(dim=-1, keepdim=True)
+    scale = 1.0 if variant == "object" else 10.0
+    emb = torch.cat([orc.posenc(pts, 10, scale), orc.posenc(vd, 4)], -1)
+    for endpoint in ([False] if variant == "object" else [False, True]):
+        want = orc.mlp_forward(pf, emb, variant, C, endpoint)
+        got = ops.mlp_forward(fine.packed(), fine.variant, C, pts.to(dev), vd.to(dev), endpoint, scale, "fp32").cpu()
+        assert got.shape == want.shape
+        assert rel_err(got, want) < 2e-5, rel_err(got, want)
+        got_e = ops.mlp_forward_embedded(fine.packed(), fine.variant, C, emb.to(dev), endpoint, "fp32").cpu()
+        assert rel_err(got_e, want) < 2e-5
+
+
+def test_module_forward_and_run_network(dev):
+    """NeRF.forward on embedded rows and run_network on points give the same rows."""
+    from intrinsicnerf_b200 import object_level as ol, ops
+    ops.set_default_precision("fp32")
+    try:
+        coarse, fine, pc, pf = build_nets("object")
+        embed_fn, _ = ol.get_embedder(10, 0)
+        embeddirs_fn, _ = ol.get_embedder(4, 0)
+        g = torch.Generator().manual_seed(9)
+        pts = (torch.rand(7, 64, 3, generator=g) * 6 - 3).to(dev)
+        vd = torch.nn.functional.normalize(torch.randn(7, 3, generator=g), dim=-1).to(dev)
+        with torch.no_grad():
+            a = ol.run_network(pts, vd, coarse, embed_fn, embeddirs_fn)
+            emb = torch.cat([embed_fn(pts.reshape(-1, 3)), embeddirs_fn(vd[:, None].expand(pts.shape).reshape(-1, 3))], -1)
+            b = coarse(emb).reshape(7, 64, 11)
+        assert rel_err(a, b) < 1e-5
+        want = orc.query_field(pts.cpu(), vd.cpu(), pc)
+        assert rel_err(a, want) < 2e-5
+        with pytest.raises(NotImplementedError):          # forward-only in round 1: loud, not silent
+            coarse(emb)
+    finally:
+        ops.set_default_precision("tc")
+
+
+def test_raw2outputs_golden_and_variants(dev, golden_dir):
+    from intrinsicnerf_b200 import object_level as ol, ops, ssr
+    g = load_golden(golden_dir, "object_stages.npz")
+    raw, z, rd = (torch.from_numpy(g[k]).to(dev) for k in ("raw", "z", "rays_d"))
+    for wb in (0, 1):
+        out = ol.raw2outputs(raw, z, rd, 0, bool(wb))
+        for name, t in zip(("rgb", "disp", "acc", "weights", "depth", "albedo", "shading", "residual"), out):
+            assert rel_err(t, g[f"wb{wb}_{name}"], floor=1e-2) < 2e-5, name
+    assert torch.isnan(ol.raw2outputs(raw, z, rd)[1][5])                 # NaN disparity is preserved (A8)
+    # semantic + endpoint channels, white background, noise
+    gen = torch.Generator().manual_seed(2)
+    C = 28
+    raw2 = torch.randn(9, 192, 11 + C + 128, generator=gen)
+    z2 = torch.sort(torch.rand(9, 192, generator=gen) * 9 + 0.1, dim=-1)[0]
+    rd2 = torch.randn(9, 3, generator=gen)
+    noise = torch.randn(9, 192, generator=gen)
+    want = orc.composite(raw2, z2, rd2, noise, True, C, True)
+    rec, w = ops.raw2outputs_rec(raw2.to(dev), z2.to(dev), rd2.to(dev), noise.to(dev), True, C, True)
+    assert rel_err(w, want["weights"], floor=1e-4) < 1e-4
+    assert rel_err(rec[:, 13:13 + C], want["sem"], floor=1e-2) < 2e-5
+    assert rel_err(rec[:, 13 + C:], want["feat"], floor=1e-2) < 2e-5
+    assert rel_err(rec[:, 0:3], want["rgb"], floor=1e-2) < 2e-5
+    assert rel_err(rec[:, 9:12], want["residual"], floor=1e-2) < 2e-5
+    tup = ssr.raw2outputs(raw2[..., :11 + C].to(dev), z2.to(dev), rd2.to(dev), 0, False, True, C, False)
+    want2 = orc.composite(raw2[..., :11 + C], z2, rd2, None, False, C, False)
+    assert len(tup) == 10 and rel_err(tup[5], want2["sem"], floor=1e-2) < 2e-5
+    assert rel_err(tup[4], want2["depth"], floor=1e-2) < 2e-5
+
+
+def test_sample_pdf_indices_exact_given_cdf(dev, golden_dir):
+    """for identical cdf and u the indices equal searchsorted(right=True) exactly,
+    including u=0, u=1, all-zero weights and single-spike weights (appendix A7)."""
+    from intrinsicnerf_b200 import ops
+    g = load_golden(golden_dir, "object_stages.npz")
+    bins, w, u = (torch.from_numpy(g[k]) for k in ("bins", "w", "u"))
+    cdf = orc.build_cdf(w)
+    for uu in (u, torch.linspace(0, 1, 128).expand(7, 128).contiguous()):
+        want_s, want_i = orc.invert_cdf(bins, cdf, uu)
+        got_s, got_i = ops.invert_cdf(bins.to(dev), cdf.to(dev), uu.to(dev))
+        assert torch.equal(got_i.cpu(), want_i)
+        assert torch.equal(got_s.cpu(), want_s)
+    # the library's own cdf: golden samples reproduced to rounding, indices self-consistent
+    s, inds, cdf_k = ops.sample_pdf(bins.to(dev), w.to(dev), 128, None, True, True)
+    assert np.abs(s.cpu().numpy() - g["s_det"]).max() < 2e-6
+    assert (cdf_k.cpu() - cdf).abs().max() < 2e-7
+    assert torch.equal(inds.cpu(), torch.searchsorted(cdf_k.cpu(), torch.linspace(0, 1, 128).expand(7, 128).contiguous(), right=True))
+    assert int(inds.min()) >= 1 and int(inds.max()) <= 63
+    s2 = ops.sample_pdf(bins.to(dev), w.to(dev), 128, u.to(dev))[0]
+    assert np.abs(s2.cpu().numpy() - g["s_rnd"]).max() < 5e-6
+
+
+def test_merge_sorted_exact(dev):
+    from intrinsicnerf_b200 import ops
+    gen = torch.Generator().manual_seed(4)
+    for Sa, Sb in ((64, 128), (64, 0), (5, 3), (1, 1), (300, 724)):
+        za = torch.sort(torch.rand(11, Sa, generator=gen) * 4 + 2, dim=-1)[0]
+        zb = torch.rand(11, Sb, generator=gen) * 4 + 2
+        if Sb > 2:
+            zb[:, 1] = zb[:, 0]                         # duplicates
+        out, std = ops.merge_sorted(za.to(dev), zb.to(dev), Sb > 0)
+        want = torch.sort(torch.cat([za, zb], -1), -1)[0]
+        assert torch.equal(out.cpu(), want)
+        if Sb > 0:
+            assert rel_err(std, torch.std(zb, dim=-1, unbiased=False), floor=1e-3) < 1e-5
+    from intrinsicnerf_b200._lib import InrfError
+    with pytest.raises(InrfError):
+        ops.merge_sorted(torch.zeros(2, 1000, device=dev), torch.zeros(2, 100, device=dev))

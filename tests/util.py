@@ -1,0 +1,54 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+import torch
+
+from oracle import nerf_oracle as orc
+
+SEED = 20220414
+
+
+def rel_err(a, b, floor=1e-3):
+    """max |a-b| / max(|b|, floor), NaNs must coincide."""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    na, nb = torch.isnan(a), torch.isnan(b)
+    assert torch.equal(na, nb), "NaN pattern differs"
+    a, b = a[~na], b[~nb]
+    if a.numel() == 0:
+        return 0.0
+    return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
+
+
+def build_nets(variant="object", n_classes=0, opaque=True, device="cuda"):
+    """Our modules with the reference's seeded init (+ optional 'opaque' tweak), and the same
+    weights as oracle parameter dicts on the CPU."""
+    import intrinsicnerf_b200 as inrf
+    torch.manual_seed(SEED)
+    if variant == "object":
+        mk = lambda: inrf.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)  # noqa: E731
+    else:
+        mk = lambda: inrf.Semantic_NeRF(n_classes > 0, n_classes, D=8, W=256, input_ch=63, output_ch=5, skips=[4],  # noqa: E731
+                                        input_ch_views=27, use_viewdirs=True)
+    coarse, fine = mk(), mk()
+    if opaque:
+        with torch.no_grad():
+            for net in (coarse, fine):
+                net.alpha_linear.bias += 1.0
+                net.pts_linears[7].weight *= 3.0
+    pc = {k: v.detach().clone() for k, v in coarse.state_dict().items()}
+    pf = {k: v.detach().clone() for k, v in fine.state_dict().items()}
+    return coarse.to(device), fine.to(device), pc, pf
+
+
+REC = dict(rgb=(0, 3), disp=(3, 4), acc=(4, 5), albedo=(5, 8), shading=(8, 9), residual=(9, 12), depth=(12, 13))
+
+
+def rec_get(rec, key):
+    a, b = REC[key]
+    v = rec[:, a:b]
+    return v if b - a > 1 else v[:, 0]
+
+
+def load_golden(golden_dir, name):
+    import os
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name), allow_pickle=False).items()}
