@@ -194,8 +194,35 @@ def ssr_fixtures(C=28):
     print("ssr fixtures written; weight sums", sums)
 
 
-if __name__ == "__main__":
+def main():
     assert refshim.available(), "reference checkout not found"
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if "--cluster" in sys.argv:
+        cluster_fixtures()
+        return
     object_fixtures()
     ssr_fixtures()
+    cluster_fixtures()
+
+
+def cluster_fixtures():
+    """Reference Cluster on the CPU (object_level/cluster.py) on 6000 synthetic albedo pixels."""
+    from oracle import cluster_oracle as co
+    import sklearn
+    rn, rh, cl = refshim.load_object_level()
+    px, which = co.synthetic_albedo(6000, n_modes=5, seed=3)
+    c = cl.Cluster(device=torch.device("cpu"))
+    c.update_center(px.numpy(), quantile=0.3, n_samples=5000, band_factor=0.5)
+    q, _ = co.synthetic_albedo(500, n_modes=5, seed=4)
+    q[0] = 0.0                                      # black pixel -> NaN mapped colour
+    dest = c.dest_color(q)
+    dcls = c.dest_class(q)
+    mapped = c.mapping_color(q)
+    np.savez_compressed(os.path.join(HERE, "cluster.npz"), **meta(), sklearn_version=np.array(sklearn.__version__),
+                        **tonp(dict(pixels=px, anchors=c.anchors, links=c.links, rgb_centers=c.rgb_centers, query=q,
+                                    dest_color=dest, dest_class=dcls, mapped=mapped)))
+    print("cluster fixtures written:", c.anchors.shape, c.rgb_centers.shape)
+
+
+if __name__ == "__main__":
+    main()

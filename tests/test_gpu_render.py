@@ -116,7 +116,12 @@ def test_ssr_renderer_golden(dev, golden_dir, precision):
     names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual", "sem_logits")
     for k in names:
         for lvl in ("coarse", "fine"):
-            assert rel_err(ev[f"{k}_{lvl}"], g[f"eval_{k}_{lvl}"]) < TOL, (k, lvl, rel_err(ev[f"{k}_{lvl}"], g[f"eval_{k}_{lvl}"]))
+            ref = g[f"eval_{k}_{lvl}"]
+            # semantic logits are unbounded, cross zero and are O(0.05) for these weights: their
+            # error is taken relative to the map's own scale instead of the 1e-3 floor
+            floor = max(1e-3, float(np.abs(ref).max())) if k == "sem_logits" else 1e-3
+            e = rel_err(ev[f"{k}_{lvl}"], ref, floor=floor)
+            assert e < TOL, (k, lvl, e)
     assert rel_err(ev["z_std"], g["eval_z_std"]) < TOL
     assert ev["raw_coarse"].shape == (rays.shape[0], 64, 11 + C) and ev["raw_fine"].shape == (rays.shape[0], 192, 11 + C)
     assert rel_err(ep["feat_map_fine"], g["ep_feat_map_fine"]) < TOL
@@ -138,7 +143,8 @@ def test_ssr_training_mode_replay_against_oracle(dev, golden_dir):
     for k in names:
         assert rel_err(rec_get(o["rec_fine"], k), g[f"train_{k}_fine"]) < TOL, k
         assert rel_err(rec_get(o["rec_coarse"], k), g[f"train_{k}_coarse"]) < TOL, k
-    assert rel_err(o["rec_fine"][:, 13:13 + C], g["train_sem_logits_fine"]) < TOL
+    sem = g["train_sem_logits_fine"]
+    assert rel_err(o["rec_fine"][:, 13:13 + C], sem, floor=float(np.abs(sem).max())) < TOL
 
 
 def test_tc_matches_fp32_on_larger_batch(dev, obj_nets):

@@ -1,0 +1,66 @@
+"""World-size-2 (and 3) gloo tests of the ray-sharding host logic on CPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from intrinsicnerf_b200 import parallel
+
+
+def test_ray_shard_partitions_exactly():
+    for n in (0, 1, 127, 128, 129, 640000, 76800, 1024, 2048):
+        for world in (1, 2, 3, 4, 8):
+            spans = [parallel.ray_shard(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, b0), (a1, b1) in zip(spans, spans[1:]):
+                assert b0 == a1 and a0 <= b0
+            assert all(a % parallel.TILE == 0 for a, _ in spans if a < n)
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= parallel.TILE or n < parallel.TILE * world
+    assert parallel.image_shard(100, 3, 8) == list(range(3, 100, 8))
+    assert sorted(sum((parallel.image_shard(100, r, 8) for r in range(8)), [])) == list(range(100))
+
+
+def _fake_render(rays):
+    # deterministic per-ray function standing in for the renderer (rays are independent)
+    return {"rgb_map": torch.sin(rays[:, :3]) + rays[:, 3:6], "acc_map": rays[:, 6] * 2 + rays[:, 7], "z_std": rays.sum(-1)}
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    rays = torch.randn(n, 11, generator=g)
+    full = parallel.render_rays_sharded(rays, _fake_render)
+    ref = _fake_render(rays)
+    ok = all(torch.equal(full[k], ref[k]) for k in ref)
+    lin = torch.nn.Linear(4, 4)
+    if rank != 0:
+        with torch.no_grad():
+            lin.weight.zero_()
+    parallel.broadcast_weights(lin, 0)
+    w = [torch.zeros_like(lin.weight) for _ in range(world)]
+    dist.all_gather(w, lin.weight.data)
+    ok &= all(torch.equal(w[0], x) for x in w) and bool(w[0].abs().sum() > 0)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1000), (3, 129), (2, 5)])
+def test_sharded_equals_single_process(world, n):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=60) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

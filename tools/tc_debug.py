@@ -39,7 +39,7 @@ def run(variant, C, M, endpoint=False):
     rows = err.max(dim=1)[0]
     bad = (rows > 1e-2).nonzero().flatten()
     print(f"   rows with abs err > 1e-2: {bad.numel()} / {M}   first: {bad[:16].tolist()}")
-    return bool(rel.max() < 1e-2)
+    return bool(err.max() < 1e-3)
 
 
 if __name__ == "__main__":
