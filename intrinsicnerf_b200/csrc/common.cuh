@@ -95,8 +95,10 @@ struct TcBlock {
   int16_t n0;        // first output row of the source matrix
   int16_t k0;        // first source K column (may be negative for padding layouts)
   int16_t kcols;     // valid source columns in this block (<=64), rest zero
-  int16_t kind;      // 0: plain rows of `layer`; 1: views' (composed); 2: head-pair block-diag
+  int16_t kind;      // 0: plain rows of `layer`; 1: views' (composed); 2: head-pair block-diag;
+                     // 3: bias block (128 rows x K=16, no-swizzle core-matrix layout, cols 0..2 = hi/lo/lo2)
   int32_t byte_off;  // offset inside the tc_blocks section
+  int32_t bytes;
 };
 constexpr int TC_MAX_BLOCKS = 128;
 constexpr int TC_SLOT_BYTES = 16384;

@@ -42,7 +42,9 @@ constexpr int SM_DIR = SM_PE + CHUNK;       // gamma(d): 27 cols + zeros (only K
 constexpr int SM_V = SM_DIR + CHUNK;        // 2 chunks: relu(views')
 constexpr int SM_RING = SM_V + 2 * CHUNK;
 constexpr int SM_SIG = SM_RING + NS * TC_SLOT_BYTES;   // [128][2] fp32 sigma partials
-constexpr int SM_BAR = SM_SIG + 1024;
+constexpr int SM_ALPHA = SM_SIG + 1024;                // alpha_linear weight row, fp32 [256]
+constexpr int SM_ONES = SM_ALPHA + 1024;               // 8 x 16 fp16 "ones" A operand for the bias MMAs
+constexpr int SM_BAR = SM_ONES + 256;
 constexpr int SM_TOTAL = SM_BAR + 512;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 
@@ -73,6 +75,8 @@ struct Params {
   int block_off[TC_MAX_BLOCKS];   // byte offsets
   int block_bytes[TC_MAX_BLOCKS];
   int out_ch, C, sem_rows;
+  int bias_mma;                   // 1: accumulators are initialised with the bias by an MMA (default)
+  int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
   int* dbg;                       // [16] watchdog record (device)
 };
 
@@ -102,6 +106,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t mbar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(mbar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -130,6 +150,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //  [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// no-swizzle K-major core-matrix layout (layout type 0): 8 rows x 16 B contiguous, the two K halves
+// LBO bytes apart, 8-row groups SBO bytes apart.  SBO = 0 replays one 8-row group for all 128 rows.
+__device__ __forceinline__ uint64_t make_desc_flat(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
@@ -215,8 +240,9 @@ __device__ __forceinline__ void write_units(uint32_t chunk, int row, const float
   }
 }
 
-__device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row, int64_t n_tiles) {
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+__device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
+  for (int it = 0; it < P.n_iter; ++it) {
+    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
     sy.tile = (int)tile;
     int64_t m = tile * TILE_M + row;
     if (m >= P.a.M) m = P.a.M - 1;
@@ -291,16 +317,24 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
 // ------------------------------------------------------------------------------------------
 // weight producer
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t smem_base, int64_t n_tiles) {
+__device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t smem_base, int cl, int rank) {
   int slot = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    sy.tile = (int)tile;
+  const uint16_t mask = (uint16_t)((1u << cl) - 1u);
+  for (int it = 0; it < P.n_iter; ++it) {
+    sy.tile = it;
     for (int b = 0; b < P.n_blocks; ++b) {
-      sy.wait(B_WEMPTY + slot);
+      sy.wait(B_WEMPTY + slot);           // every CTA of the cluster has consumed this slot
       if (!sy.dead) {
-        mbar_expect_tx(sy.addr(B_WFULL + slot), (uint32_t)P.block_bytes[b]);
-        bulk_g2s(smem_base + SM_RING + slot * TC_SLOT_BYTES, P.blocks + P.block_off[b], (uint32_t)P.block_bytes[b],
-                 sy.addr(B_WFULL + slot));
+        const uint32_t bytes = (uint32_t)P.block_bytes[b];
+        const uint32_t dst = smem_base + SM_RING + slot * TC_SLOT_BYTES;
+        mbar_expect_tx(sy.addr(B_WFULL + slot), bytes);
+        if (cl == 1) {
+          bulk_g2s(dst, P.blocks + P.block_off[b], bytes, sy.addr(B_WFULL + slot));
+        } else {
+          // each CTA fetches 1/cl of the block from L2 and multicasts it into every CTA's slot
+          const uint32_t part = bytes / (uint32_t)cl;
+          bulk_g2s_mc(dst + rank * part, P.blocks + P.block_off[b] + rank * part, part, sy.addr(B_WFULL + slot), mask);
+        }
       }
       slot = (slot + 1 == NS) ? 0 : slot + 1;
     }
@@ -314,6 +348,8 @@ struct Issuer {
   Sync& sy;
   uint32_t smem_base, tmem;
   int slot;
+  int cl;
+  int bias_mma;
   // one operand block: A chunk (K = 16*ksteps) x ring slot -> accumulator columns [col, col+n)
   __device__ __forceinline__ void block(uint32_t a_chunk, int ksteps, int n, uint32_t col, bool first) {
     sy.wait(B_WFULL + slot);
@@ -324,15 +360,31 @@ struct Issuer {
 #pragma unroll 4
     for (int k = 0; k < ksteps; ++k)
       tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
-    tc_commit(sy.addr(B_WEMPTY + slot));
+    release();
+  }
+  __device__ __forceinline__ void release() {
+    if (cl == 1) tc_commit(sy.addr(B_WEMPTY + slot));
+    else tc_commit_mc(sy.addr(B_WEMPTY + slot), (uint16_t)((1u << cl) - 1u));   // release the slot in every CTA
     slot = (slot + 1 == NS) ? 0 : slot + 1;
+  }
+  // accumulator columns [col, col+128) := bias (one K=16 MMA of the constant "ones" tile with the
+  // hi/lo/lo2 bias columns).  Returns true when the accumulator was initialised.
+  __device__ __forceinline__ bool bias(uint32_t col) {
+    sy.wait(B_WFULL + slot);
+    tc_fence_after();
+    if (bias_mma)
+      tc_mma(tmem + col, make_desc_flat(smem_base + SM_ONES, 128, 0),
+             make_desc_flat(smem_base + SM_RING + slot * TC_SLOT_BYTES, 128, 256), make_idesc(128), 0u);
+    release();
+    return bias_mma != 0;
   }
 };
 
-__device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int64_t n_tiles) {
-  Issuer I{sy, smem_base, tmem, 0};
+__device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl) {
+  Issuer I{sy, smem_base, tmem, 0, cl, P.bias_mma};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int it = 0; it < P.n_iter; ++it) {
+    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
     sy.tile = (int)tile;
     sy.wait(B_TAIL_DONE);               // previous tile's accumulators drained
     tc_fence_after();
@@ -340,16 +392,17 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
     sy.wait(B_PE_READY);
     tc_fence_after();
     for (int h = 0; h < 2; ++h) {
-      I.block(PE, 4, 128, h * 128, true);
+      const bool init = I.bias(h * 128);
+      I.block(PE, 4, 128, h * 128, !init);
       tc_commit(sy.addr(B_ACC_FULL + h));
     }
     // ---- trunk layers 1..7 -----------------------------------------------------------------
     for (int l = 1; l < 8; ++l) {
       const uint32_t acc = (l & 1) * 256;
       for (int h = 0; h < 2; ++h) {
-        bool first = true;
+        bool first = !I.bias(acc + h * 128);
         if (l == 5) {                    // skip connection: [gamma(x), h] -> K = 64 + 256
-          I.block(PE, 4, 128, acc + h * 128, true);
+          I.block(PE, 4, 128, acc + h * 128, first);
           first = false;
           if (h == 1) tc_commit(sy.addr(B_PE_FREE));
         }
@@ -363,10 +416,13 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
       }
     }
     // ---- views' = relu(W' h + Wd gamma(d) + b')  -> accumulator 0, half 0 ----------------------
-    for (int c = 0; c < 4; ++c) {
-      sy.wait(B_A_READY + c);
-      tc_fence_after();
-      I.block(H + c * CHUNK, 4, 128, 0, c == 0);
+    {
+      const bool init = I.bias(0);
+      for (int c = 0; c < 4; ++c) {
+        sy.wait(B_A_READY + c);
+        tc_fence_after();
+        I.block(H + c * CHUNK, 4, 128, 0, c == 0 && !init);
+      }
     }
     sy.wait(B_DIR_READY);
     tc_fence_after();
@@ -375,13 +431,15 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
     tc_commit(sy.addr(B_ACC_FULL + 0));
     // ---- semantic hidden layer -> accumulator 0, half 1 ----------------------------------------
     if (P.C > 0) {
-      for (int c = 0; c < 4; ++c) I.block(H + c * CHUNK, 4, 128, 128, c == 0);
+      const bool init = I.bias(128);
+      for (int c = 0; c < 4; ++c) I.block(H + c * CHUNK, 4, 128, 128, c == 0 && !init);
       tc_commit(sy.addr(B_ACC_FULL + 1));
     }
     // ---- albedo1 | shading1 -> accumulator 1 ----------------------------------------------------
     for (int h = 0; h < 2; ++h) {
+      const bool init = I.bias(256 + h * 128);
       for (int c = 0; c < 4; ++c) {
-        I.block(H + c * CHUNK, 4, 128, 256 + h * 128, c == 0);
+        I.block(H + c * CHUNK, 4, 128, 256 + h * 128, c == 0 && !init);
         if (h == 1) tc_commit(sy.addr(B_A_FREE + c));
       }
       tc_commit(sy.addr(B_ACC_FULL + 2 + h));
@@ -417,56 +475,86 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
 // ------------------------------------------------------------------------------------------
 // epilogue warps
 // ------------------------------------------------------------------------------------------
-// 32 accumulator columns of this thread's row: +bias, optional ReLU, optional sigma partial,
-// fp16 pack, 4 swizzled 16-byte stores into the destination A chunk.
-template <bool RELU>
-__device__ __forceinline__ void epi_pass(uint32_t taddr, const float* __restrict__ bias, uint32_t dst_chunk, int row,
-                                         int unit0, Sync& sy, int free_bar, const float* __restrict__ alpha_w,
+// 64 accumulator columns of this thread's row -> ReLU -> fp16 -> 8 swizzled 16-byte stores into
+// the destination A chunk.  With the bias already in the accumulator (bias MMA) the ReLU runs on
+// packed halves (relu(round(x)) == round(relu(x))), 1 cvt + 1 max per two columns.
+struct RowAddr {
+  uint32_t unit[8];   // byte offset of 16-byte unit u of this thread's row inside a chunk (swizzled)
+};
+
+__device__ __forceinline__ uint32_t relu_h2(uint32_t h2) {
+  __half2 v = *reinterpret_cast<__half2*>(&h2);
+  v = __hmax2(v, __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <bool ADD_BIAS>
+__device__ __forceinline__ void epi_half(uint32_t taddr, const float* __restrict__ bias, uint32_t dst_chunk,
+                                         const RowAddr& ra, Sync& sy, int free_bar, const float* alpha_w_smem,
                                          float* sigma_acc, float* gout) {
-  uint32_t v[32];
-  float b[32];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(bias) + i);
-    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
-  }
+  uint32_t v[64];
   tmem_ld32(taddr, v);
+  tmem_ld32(taddr + 32, v + 32);
   tmem_ld_wait();
-  float f[32];
+  if (ADD_BIAS) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = __uint_as_float(v[i]) + b[i];
-    f[i] = RELU ? fmaxf(x, 0.f) : x;
+    for (int i = 0; i < 16; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(bias) + i);
+      v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + t.x);
+      v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + t.y);
+      v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + t.z);
+      v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + t.w);
+    }
   }
-  if (alpha_w != nullptr) {
+  if (alpha_w_smem != nullptr) {              // sigma head: fp32 dot on the un-rounded ReLU output
     float s = *sigma_acc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(alpha_w) + i);
-      s = fmaf(f[4 * i], t.x, s); s = fmaf(f[4 * i + 1], t.y, s); s = fmaf(f[4 * i + 2], t.z, s); s = fmaf(f[4 * i + 3], t.w, s);
+    for (int i = 0; i < 16; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(alpha_w_smem + 4 * i);
+      s = fmaf(fmaxf(__uint_as_float(v[4 * i]), 0.f), t.x, s);
+      s = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), t.y, s);
+      s = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), t.z, s);
+      s = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), t.w, s);
     }
     *sigma_acc = s;
   }
-  if (gout != nullptr) {
+  if (gout != nullptr) {                      // endpoint feature rows (fp32, post-ReLU)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) gout[i] = f[i];
+    for (int i = 0; i < 64; ++i) gout[i] = fmaxf(__uint_as_float(v[i]), 0.f);
   }
   if (free_bar >= 0) sy.wait(free_bar);
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-    st_shared_v4(swz(dst_chunk, row, unit0 + u), pack_h2(f[8 * u], f[8 * u + 1]), pack_h2(f[8 * u + 2], f[8 * u + 3]),
-                 pack_h2(f[8 * u + 4], f[8 * u + 5]), pack_h2(f[8 * u + 6], f[8 * u + 7]));
+  for (int u = 0; u < 8; ++u) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      pk[i] = relu_h2(pack_h2(__uint_as_float(v[8 * u + 2 * i]), __uint_as_float(v[8 * u + 2 * i + 1])));
+    st_shared_v4(dst_chunk + ra.unit[u], pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+__device__ __forceinline__ void epi_dispatch(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst_chunk,
+                                             const RowAddr& ra, Sync& sy, int free_bar, const float* alpha_w_smem,
+                                             float* sigma_acc, float* gout) {
+  if (add_bias) epi_half<true>(taddr, bias, dst_chunk, ra, sy, free_bar, alpha_w_smem, sigma_acc, gout);
+  else epi_half<false>(taddr, bias, dst_chunk, ra, sy, free_bar, alpha_w_smem, sigma_acc, gout);
 }
 
 __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* smem, uint32_t smem_base, uint32_t tmem,
-                                         int q, int j, int lane, int64_t n_tiles) {
+                                         int q, int j, int lane) {
   const int row = q * 32 + lane;
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
   float* s_sig = reinterpret_cast<float*>(smem + SM_SIG);
+  const float* s_alpha = reinterpret_cast<const float*>(smem + SM_ALPHA);
   const uint32_t H = smem_base + SM_H, V = smem_base + SM_V;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const bool add_bias = P.bias_mma == 0;
+  RowAddr ra;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
+  for (int it = 0; it < P.n_iter; ++it) {
+    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
     sy.tile = (int)tile;
     const int64_t m = tile * TILE_M + row;
     const bool valid = m < P.a.M;
@@ -477,13 +565,10 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
       for (int h = 0; h < 2; ++h) {
         sy.wait(B_ACC_FULL + (l & 1) * 2 + h);
         tc_fence_after();
-        const int c = 2 * h + j;                       // destination chunk (64 columns)
-#pragma unroll 1
-        for (int p2 = 0; p2 < 2; ++p2) {
-          const int col = h * 128 + j * 64 + p2 * 32;
-          epi_pass<true>(lane_addr + (l & 1) * 256 + col, P.bias + l * 256 + col, H + c * CHUNK, row, p2 * 4, sy,
-                         p2 == 0 ? B_A_FREE + c : -1, l == 7 ? P.bias + TCB_ALPHA_W + col : nullptr, &sig, nullptr);
-        }
+        const int c = 2 * h + j;                       // destination chunk = my 64 accumulator columns
+        const int col = h * 128 + j * 64;
+        epi_dispatch(add_bias, lane_addr + (l & 1) * 256 + col, P.bias + l * 256 + col, H + c * CHUNK, ra, sy,
+                     B_A_FREE + c, l == 7 ? s_alpha + col : nullptr, &sig, nullptr);
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(sy.addr(B_A_READY + c));
@@ -493,12 +578,10 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     // ---- relu(views') -> V chunk j (and the endpoint feature rows) --------------------------------
     sy.wait(B_ACC_FULL + 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int p2 = 0; p2 < 2; ++p2) {
-      const int col = j * 64 + p2 * 32;
+    {
+      const int col = j * 64;
       float* g = (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C + col : nullptr;
-      epi_pass<true>(lane_addr + col, P.bias + TCB_VIEWS + col, V + j * CHUNK, row, p2 * 4, sy,
-                     p2 == 0 ? B_V_FREE : -1, nullptr, nullptr, g);
+      epi_dispatch(add_bias, lane_addr + col, P.bias + TCB_VIEWS + col, V + j * CHUNK, ra, sy, B_V_FREE, nullptr, nullptr, g);
     }
     fence_async_smem();
     tc_fence_before();
@@ -508,12 +591,9 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
       sy.wait(B_ACC_FULL + 2 + h);
       tc_fence_after();
       const int c = 2 * h + j;
-#pragma unroll 1
-      for (int p2 = 0; p2 < 2; ++p2) {
-        const int col = h * 128 + j * 64 + p2 * 32;
-        epi_pass<true>(lane_addr + 256 + col, P.bias + TCB_ALBSH + col, H + c * CHUNK, row, p2 * 4, sy,
-                       p2 == 0 ? B_A_FREE + c : -1, nullptr, nullptr, nullptr);
-      }
+      const int col = h * 128 + j * 64;
+      epi_dispatch(add_bias, lane_addr + 256 + col, P.bias + TCB_ALBSH + col, H + c * CHUNK, ra, sy, B_A_FREE + c,
+                   nullptr, nullptr, nullptr);
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(sy.addr(B_A_READY + c));
@@ -522,12 +602,9 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     if (P.C > 0) {
       sy.wait(B_ACC_FULL + 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int p2 = 0; p2 < 2; ++p2) {
-        const int col = j * 64 + p2 * 32;
-        epi_pass<true>(lane_addr + 128 + col, P.bias + TCB_SEM1 + col, H + j * CHUNK, row, p2 * 4, sy,
-                       p2 == 0 ? B_A_FREE + j : -1, nullptr, nullptr, nullptr);
-      }
+      const int col = j * 64;
+      epi_dispatch(add_bias, lane_addr + 128 + col, P.bias + TCB_SEM1 + col, H + j * CHUNK, ra, sy, B_A_FREE + j,
+                   nullptr, nullptr, nullptr);
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(sy.addr(B_A_READY + j));
@@ -580,12 +657,13 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
+template <int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * B_COUNT);
-  const int64_t n_tiles = (P.a.M + TILE_M - 1) / TILE_M;
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
 
   Sync sy;
   sy.bar0 = smem_base + SM_BAR;
@@ -595,10 +673,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   sy.phase = 0;
   if ((smem_base & 1023u) != 0) {                    // SWIZZLE_128B atoms need 1024 B alignment
     if (threadIdx.x == 0 && atomicCAS(P.dbg, 0, 2) == 0) P.dbg[1] = (int)smem_base;
-    return;
+    return;                                            // same for every CTA of the launch
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), CL); }
     mbar_init(sy.addr(B_PE_READY), 128); mbar_init(sy.addr(B_PE_FREE), 1);
     mbar_init(sy.addr(B_DIR_READY), 128); mbar_init(sy.addr(B_DIR_FREE), 1);
     for (int c = 0; c < 4; ++c) { mbar_init(sy.addr(B_A_READY + c), 128); mbar_init(sy.addr(B_A_FREE + c), 1); mbar_init(sy.addr(B_ACC_FULL + c), 1); }
@@ -608,12 +686,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     mbar_init(sy.addr(B_TAIL_DONE), 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 2) {
+    // constant operands: alpha_linear row (fp32) and the "ones" tile of the bias MMAs:
+    // 2 core matrices of 8 rows x 8 halves; K columns 0..2 are 1.0, the rest 0
+    float* s_alpha = reinterpret_cast<float*>(smem + SM_ALPHA);
+    for (int i = lane; i < 256; i += 32) s_alpha[i] = __ldg(P.bias + TCB_ALPHA_W + i);
+    __half* ones = reinterpret_cast<__half*>(smem + SM_ONES);
+    for (int i = lane; i < 128; i += 32) {
+      const int k = (i >> 6) * 8 + (i & 7);          // element i = core*64 + row*8 + kk
+      ones[i] = __float2half_rn(k < 3 ? 1.f : 0.f);
+    }
+    fence_async_smem();
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // peers' barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -623,16 +714,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   sy.phase = released;
 
   if (warp == 0) {
-    if (lane == 0) producer(P, sy, smem_base, n_tiles);
+    if (lane == 0) producer(P, sy, smem_base, CL, rank);
   } else if (warp == 1) {
-    if (lane == 0) issuer(P, sy, smem_base, tmem, n_tiles);
+    if (lane == 0) issuer(P, sy, smem_base, tmem, CL);
   } else if (warp >= 4 && warp < 8) {
-    front_end(P, sy, smem_base, (warp - 4) * 32 + lane, n_tiles);
+    front_end(P, sy, smem_base, (warp - 4) * 32 + lane);
   } else if (warp >= 8) {
-    epilogue(P, sy, smem, smem_base, tmem, warp & 3, (warp - 8) >> 2, lane, n_tiles);
+    epilogue(P, sy, smem, smem_base, tmem, warp & 3, (warp - 8) >> 2, lane);
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into this CTA
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -654,23 +746,42 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   P.blocks = blob + L.tc_blocks;
   P.bias = reinterpret_cast<const float*>(blob + L.tc_bias);
   P.n_blocks = prog.n_blocks;
-  for (int i = 0; i < prog.n_blocks; ++i) { P.block_off[i] = prog.blk[i].byte_off; P.block_bytes[i] = prog.blk[i].rows * 128; }
+  for (int i = 0; i < prog.n_blocks; ++i) { P.block_off[i] = prog.blk[i].byte_off; P.block_bytes[i] = prog.blk[i].bytes; }
   P.out_ch = raw_channels(a.n_classes, a.endpoint);
   P.C = a.n_classes;
   P.sem_rows = (a.n_classes + 15) / 16 * 16;
+  static const int bias_mma_env = getenv("INRF_TC_BIASMMA") ? atoi(getenv("INRF_TC_BIASMMA")) : 1;
+  P.bias_mma = bias_mma_env ? 1 : 0;
   int* dbg = nullptr;
   INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, tc::g_dbg));
   P.dbg = dbg;
   static const bool checked = getenv("INRF_TC_CHECK") != nullptr && getenv("INRF_TC_CHECK")[0] == '1';
   if (checked) INRF_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(int), st));
-  INRF_CUDA(cudaFuncSetAttribute(tc::k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
   int dev = 0, sms = 148;
   INRF_CUDA(cudaGetDevice(&dev));
   INRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static const int cl_env = getenv("INRF_TC_CLUSTER") ? atoi(getenv("INRF_TC_CLUSTER")) : 2;
   const int64_t tiles = (a.M + tc::TILE_M - 1) / tc::TILE_M;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  tc::k_mlp_tc<<<grid, tc::NUM_THREADS, tc::SM_TOTAL, st>>>(P);
-  INRF_LAUNCH_CHECK();
+  int cl = (cl_env == 4) ? 4 : (cl_env == 1 ? 1 : 2);
+  if (tiles < cl) cl = 1;
+  int grid = (int)(tiles < sms ? tiles : sms);
+  grid = grid / cl * cl;                       // whole clusters only
+  P.n_iter = (int)((tiles + grid - 1) / grid);
+  void (*kern)(tc::Params) = cl == 4 ? tc::k_mlp_tc<4> : (cl == 2 ? tc::k_mlp_tc<2> : tc::k_mlp_tc<1>);
+  INRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.dynamicSmemBytes = tc::SM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  INRF_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   if (checked) {      // debug mode: synchronise and surface watchdog records as errors
     int h[16];
     INRF_CUDA(cudaStreamSynchronize(st));

@@ -70,14 +70,18 @@ static void push(TcProgram* p, int layer, int rows, int n0, int k0, int kcols, i
   TcBlock& b = p->blk[p->n_blocks++];
   b.layer = (int16_t)layer; b.rows = (int16_t)rows; b.n0 = (int16_t)n0; b.k0 = (int16_t)k0;
   b.kcols = (int16_t)kcols; b.kind = (int16_t)kind; b.byte_off = p->bytes;
-  p->bytes += rows * 128;
+  b.bytes = (kind == 3) ? 4096 : rows * 128;
+  p->bytes += (b.bytes + 1023) / 1024 * 1024;       // keep every block 1024-byte aligned in the blob
 }
+// bias of `layer` rows [n0, n0+128) as a K=16 operand (accumulator initialisation by MMA)
+static void push_bias(TcProgram* p, int layer, int n0) { push(p, layer, 128, n0, 0, 3, 3); }
 
 int make_tc_program(int variant, int n_classes, TcProgram* p) {
   p->n_blocks = 0; p->bytes = 0;
-  // trunk
+  // trunk: per (layer, N half): bias block, then the K chunks
   for (int l = 0; l < 8; ++l) {
     for (int h = 0; h < 2; ++h) {
+      push_bias(p, L_T0 + l, 128 * h);
       if (l == 0) { push(p, L_T0, 128, 128 * h, 0, PE_PTS, 0); continue; }
       if (l == 5) push(p, L_T5, 128, 128 * h, 0, PE_PTS, 0);
       int base = (l == 5) ? PE_PTS : 0;
@@ -85,12 +89,18 @@ int make_tc_program(int variant, int n_classes, TcProgram* p) {
     }
   }
   // views' (composed with feature_linear): K = 256 (h) + 27 (dir PE)
+  push_bias(p, -1, 0);
   for (int c = 0; c < 4; ++c) push(p, -1, 128, 0, 64 * c, 64, 1);
   push(p, L_VIEWS, 128, 0, W_HID, PE_DIR, 0);
   // semantic hidden layer
-  if (n_classes > 0) for (int c = 0; c < 4; ++c) push(p, L_SEM1, 128, 0, 64 * c, 64, 0);
+  if (n_classes > 0) {
+    push_bias(p, L_SEM1, 0);
+    for (int c = 0; c < 4; ++c) push(p, L_SEM1, 128, 0, 64 * c, 64, 0);
+  }
   // albedo1 | shading1 as the two N halves of one 256-wide GEMM
+  push_bias(p, L_ALB1, 0);
   for (int c = 0; c < 4; ++c) push(p, L_ALB1, 128, 0, 64 * c, 64, 0);
+  push_bias(p, L_SH1, 0);
   for (int c = 0; c < 4; ++c) push(p, L_SH1, 128, 0, 64 * c, 64, 0);
   // residual head on relu(views'):  16 x 128
   for (int c = 0; c < 2; ++c) push(p, L_RES, 16, 0, 64 * c, 64, 0);
@@ -179,6 +189,22 @@ __global__ void k_pack_tc_blocks(const float* __restrict__ flat, unsigned char* 
   const TcBlock b = prog.blk[blockIdx.x];
   __half* dst = reinterpret_cast<__half*>(packed + P.L.tc_blocks + b.byte_off);
   const float* comp = reinterpret_cast<const float*>(packed + P.L.comp);
+  if (b.kind == 3) {
+    // no-swizzle K-major core matrices: 8 rows x 8 halves = 128 B contiguous; K halves 128 B apart
+    // (LBO), 8-row groups 256 B apart (SBO).  bias = hi + lo + lo2 in three fp16 columns.
+    for (int r = threadIdx.x; r < 128; r += blockDim.x) {
+      float bv = (b.layer < 0) ? comp[128 * W_HID + b.n0 + r] : flat[P.L.flat_b[b.layer] + b.n0 + r];
+      __half hi = __float2half_rn(bv);
+      float r1 = bv - __half2float(hi);
+      __half lo = __float2half_rn(r1);
+      __half lo2 = __float2half_rn(r1 - __half2float(lo));
+      for (int k = 0; k < 16; ++k) {
+        __half v = k == 0 ? hi : (k == 1 ? lo : (k == 2 ? lo2 : __float2half_rn(0.f)));
+        dst[((r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2) >> 1] = v;
+      }
+    }
+    return;
+  }
   for (int e = threadIdx.x; e < b.rows * 64; e += blockDim.x) {
     int r = e >> 6, kk = e & 63;
     float v = 0.f;
