@@ -86,13 +86,27 @@ def synthetic_rays(rank):
 
 
 def cpu_baseline(n_rays=2048, seconds_cap=40.0):
-    """The oracle's render_rays on the host cores (all threads torch uses)."""
+    """The oracle's render_rays on the host cores.  The thread count is probed (all cores, then
+    halving) on a small batch and the fastest setting is used for the timed sample - many-core hosts
+    are slower with every core on these GEMM sizes."""
     from oracle import nerf_oracle as orc
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    ncpu = os.cpu_count() or 1
     coarse, fine = orc.seeded_nets("object")
     rays = orc.blender_rays(64, 64)[:n_rays].contiguous()
+    probe = {}
     with torch.no_grad():
+        t = ncpu
+        while t >= 8 or t == ncpu:
+            torch.set_num_threads(t)
+            orc.render_rays(rays[:128], coarse, fine, white_bkgd=True)
+            t0 = time.perf_counter()
+            orc.render_rays(rays[:256], coarse, fine, white_bkgd=True)
+            probe[t] = 256 / (time.perf_counter() - t0)
+            if t <= 8:
+                break
+            t //= 2
+        threads = max(probe, key=probe.get)
+        torch.set_num_threads(threads)
         orc.render_rays(rays[:256], coarse, fine, white_bkgd=True)          # warm-up
         t0 = time.perf_counter()
         done = 0
@@ -102,7 +116,8 @@ def cpu_baseline(n_rays=2048, seconds_cap=40.0):
             if time.perf_counter() - t0 > seconds_cap:
                 break
         dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+    return {"value": done / dt, "unit": "rays/s", "cores": threads, "kind": "port", "host_cpus": ncpu,
+            "thread_probe_rays_per_s": {str(k): round(v, 1) for k, v in probe.items()},
             "sample": f"{done} rays of a 64x64 Blender view, 64+128 samples, oracle.render_rays, torch {torch.__version__} CPU"}
 
 

@@ -5,15 +5,15 @@
 // SSR/models/semantic_nerf.py:123-181, fused with the Embedder and run_network's
 // per-sample view-direction expansion) runs without touching HBM in between:
 //
-//   warp 0      weight producer : streams the pre-swizzled fp16 operand blocks of the packed
+//   warp 14     weight producer : streams the pre-swizzled fp16 operand blocks of the packed
 //                                 blob (pack.cu, MMA issue order) into a shared-memory ring with
 //                                 cp.async.bulk + mbarrier complete_tx (TMA bulk copies)
-//   warp 1      MMA issuer      : one thread issues tcgen05.mma (kind::f16, M=128, N=128/16..112,
+//   warp 15     MMA issuer      : one elected lane issues tcgen05.mma (kind::f16, M=128, N=128/16..112,
 //                                 K=16) with fp32 accumulators in TMEM; tcgen05.commit signals
 //                                 "accumulator half ready", "weight slot free", "A chunk free"
-//   warps 4-7   front end       : sample position (o + d z), range-reduced sin/cos positional
+//   warps 8-11  front end       : sample position (o + d z), range-reduced sin/cos positional
 //                                 encoding of the NEXT tile, written as fp16 UMMA operand tiles
-//   warps 8-15  epilogue        : tcgen05.ld accumulator -> +bias, ReLU (fp32) -> fp16 -> the next
+//   warps 0-7   epilogue        : tcgen05.ld accumulator -> +bias, ReLU (fp32) -> fp16 -> the next
 //                                 layer's A operand (SWIZZLE_128B K-major), in place; sigma head as
 //                                 an fp32 dot product on the un-rounded trunk output; sigmoid heads;
 //                                 packed raw rows to HBM
@@ -78,9 +78,12 @@ struct Params {
   int bias_mma;                   // 1: accumulators are initialised with the bias by an MMA (default)
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
   int* dbg;                       // [16] watchdog record (device)
+  long long* prof;                // optional [4][64] wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
+  int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
 };
 
 __device__ int g_dbg[16];
+__device__ long long g_prof[4 * 128];   // per role: [0,63) wait cycles per barrier, [63] total, [64,128) wait counts
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -169,31 +172,42 @@ struct Sync {
   uint32_t bar0;          // smem address of barrier 0
   uint64_t phase;         // one parity bit per barrier id
   int* dbg;
+  long long* prof;        // wait-cycle counters of this role (CTA 0, one thread per role) or nullptr
   bool dead;
   int tile;
   __device__ __forceinline__ uint32_t addr(int id) const { return bar0 + 8u * id; }
-  __device__ __forceinline__ void wait(int id) {
-    const uint32_t parity = (uint32_t)((phase >> id) & 1ull);
-    phase ^= (1ull << id);
-    if (dead) return;
-    if (mbar_try(addr(id), parity)) return;
+  __device__ __noinline__ void slow_wait(int id, uint32_t parity) {
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try(addr(id), parity)) {
       if ((++spins & 0x3ff) == 0) {
-        if (*(volatile int*)dbg != 0) { dead = true; return; }
+        if (*(volatile int*)dbg != 0) { dead = true; break; }
         if (clock64() - t0 > 3000000000LL) {
           if (atomicCAS(dbg, 0, 1) == 0) {
             dbg[1] = id; dbg[2] = threadIdx.x >> 5; dbg[3] = tile; dbg[4] = blockIdx.x; dbg[5] = (int)parity;
             __threadfence();
           }
           dead = true;
-          return;
+          break;
         }
       }
     }
+    if (prof) { prof[id] += clock64() - t0; prof[id + 64] += 1; }
+  }
+  __device__ __forceinline__ void wait(int id) {
+    const uint32_t parity = (uint32_t)((phase >> id) & 1ull);
+    phase ^= (1ull << id);
+    if (dead) return;
+    if (mbar_try(addr(id), parity)) return;
+    slow_wait(id, parity);
   }
 };
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // one K-major SWIZZLE_128B row address: 8-row atoms of 1024 B, 16-byte unit XOR (row & 7)
 __device__ __forceinline__ uint32_t swz(uint32_t chunk_base, int row, int unit) {
@@ -320,11 +334,12 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
 __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t smem_base, int cl, int rank) {
   int slot = 0;
   const uint16_t mask = (uint16_t)((1u << cl) - 1u);
+  const bool leader = elect_one();
   for (int it = 0; it < P.n_iter; ++it) {
     sy.tile = it;
     for (int b = 0; b < P.n_blocks; ++b) {
       sy.wait(B_WEMPTY + slot);           // every CTA of the cluster has consumed this slot
-      if (!sy.dead) {
+      if (leader && !sy.dead) {
         const uint32_t bytes = (uint32_t)P.block_bytes[b];
         const uint32_t dst = smem_base + SM_RING + slot * TC_SLOT_BYTES;
         mbar_expect_tx(sy.addr(B_WFULL + slot), bytes);
@@ -336,6 +351,7 @@ __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t sme
           bulk_g2s_mc(dst + rank * part, P.blocks + P.block_off[b] + rank * part, part, sy.addr(B_WFULL + slot), mask);
         }
       }
+      __syncwarp();
       slot = (slot + 1 == NS) ? 0 : slot + 1;
     }
   }
@@ -350,38 +366,52 @@ struct Issuer {
   int slot;
   int cl;
   int bias_mma;
-  // one operand block: A chunk (K = 16*ksteps) x ring slot -> accumulator columns [col, col+n)
-  __device__ __forceinline__ void block(uint32_t a_chunk, int ksteps, int n, uint32_t col, bool first) {
-    sy.wait(B_WFULL + slot);
+  int no_weights;
+  bool leader;
+  __device__ __forceinline__ void commit(int bar) {
+    if (leader) tc_commit(sy.addr(bar));
+    __syncwarp();
+  }
+  // one operand block: A chunk (K = 16*KSTEPS) x ring slot -> accumulator columns [col, col+n)
+  template <int KSTEPS>
+  __device__ __forceinline__ void block(uint32_t a_chunk, int n, uint32_t col, bool first) {
+    if (!no_weights) sy.wait(B_WFULL + slot);
     tc_fence_after();
     const uint64_t ad = make_desc(a_chunk);
     const uint64_t bd = make_desc(smem_base + SM_RING + slot * TC_SLOT_BYTES);
     const uint32_t id = make_idesc(n);
-#pragma unroll 4
-    for (int k = 0; k < ksteps; ++k)
-      tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k)
+        tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+    }
+    __syncwarp();
     release();
   }
   __device__ __forceinline__ void release() {
-    if (cl == 1) tc_commit(sy.addr(B_WEMPTY + slot));
-    else tc_commit_mc(sy.addr(B_WEMPTY + slot), (uint16_t)((1u << cl) - 1u));   // release the slot in every CTA
+    if (!no_weights && leader) {
+      if (cl == 1) tc_commit(sy.addr(B_WEMPTY + slot));
+      else tc_commit_mc(sy.addr(B_WEMPTY + slot), (uint16_t)((1u << cl) - 1u));   // release the slot in every CTA
+    }
+    __syncwarp();
     slot = (slot + 1 == NS) ? 0 : slot + 1;
   }
   // accumulator columns [col, col+128) := bias (one K=16 MMA of the constant "ones" tile with the
   // hi/lo/lo2 bias columns).  Returns true when the accumulator was initialised.
   __device__ __forceinline__ bool bias(uint32_t col) {
-    sy.wait(B_WFULL + slot);
+    if (!no_weights) sy.wait(B_WFULL + slot);
     tc_fence_after();
-    if (bias_mma)
+    if (bias_mma && leader)
       tc_mma(tmem + col, make_desc_flat(smem_base + SM_ONES, 128, 0),
              make_desc_flat(smem_base + SM_RING + slot * TC_SLOT_BYTES, 128, 256), make_idesc(128), 0u);
+    __syncwarp();
     release();
     return bias_mma != 0;
   }
 };
 
 __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl) {
-  Issuer I{sy, smem_base, tmem, 0, cl, P.bias_mma};
+  Issuer I{sy, smem_base, tmem, 0, cl, P.bias_mma, P.no_weights, elect_one()};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
   for (int it = 0; it < P.n_iter; ++it) {
     const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
@@ -393,8 +423,8 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
     tc_fence_after();
     for (int h = 0; h < 2; ++h) {
       const bool init = I.bias(h * 128);
-      I.block(PE, 4, 128, h * 128, !init);
-      tc_commit(sy.addr(B_ACC_FULL + h));
+      I.block<4>(PE, 128, h * 128, !init);
+      I.commit(B_ACC_FULL + h);
     }
     // ---- trunk layers 1..7 -----------------------------------------------------------------
     for (int l = 1; l < 8; ++l) {
@@ -402,17 +432,17 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
       for (int h = 0; h < 2; ++h) {
         bool first = !I.bias(acc + h * 128);
         if (l == 5) {                    // skip connection: [gamma(x), h] -> K = 64 + 256
-          I.block(PE, 4, 128, acc + h * 128, first);
+          I.block<4>(PE, 128, acc + h * 128, first);
           first = false;
-          if (h == 1) tc_commit(sy.addr(B_PE_FREE));
+          if (h == 1) I.commit(B_PE_FREE);
         }
         for (int c = 0; c < 4; ++c) {
           if (h == 0) { sy.wait(B_A_READY + c); tc_fence_after(); }
-          I.block(H + c * CHUNK, 4, 128, acc + h * 128, first);
+          I.block<4>(H + c * CHUNK, 128, acc + h * 128, first);
           first = false;
-          if (h == 1) tc_commit(sy.addr(B_A_FREE + c));
+          if (h == 1) I.commit(B_A_FREE + c);
         }
-        tc_commit(sy.addr(B_ACC_FULL + (l & 1) * 2 + h));
+        I.commit(B_ACC_FULL + (l & 1) * 2 + h);
       }
     }
     // ---- views' = relu(W' h + Wd gamma(d) + b')  -> accumulator 0, half 0 ----------------------
@@ -421,53 +451,53 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
       for (int c = 0; c < 4; ++c) {
         sy.wait(B_A_READY + c);
         tc_fence_after();
-        I.block(H + c * CHUNK, 4, 128, 0, c == 0 && !init);
+        I.block<4>(H + c * CHUNK, 128, 0, c == 0 && !init);
       }
     }
     sy.wait(B_DIR_READY);
     tc_fence_after();
-    I.block(DIR, 2, 128, 0, false);
-    tc_commit(sy.addr(B_DIR_FREE));
-    tc_commit(sy.addr(B_ACC_FULL + 0));
+    I.block<2>(DIR, 128, 0, false);
+    I.commit(B_DIR_FREE);
+    I.commit(B_ACC_FULL + 0);
     // ---- semantic hidden layer -> accumulator 0, half 1 ----------------------------------------
     if (P.C > 0) {
       const bool init = I.bias(128);
-      for (int c = 0; c < 4; ++c) I.block(H + c * CHUNK, 4, 128, 128, c == 0 && !init);
-      tc_commit(sy.addr(B_ACC_FULL + 1));
+      for (int c = 0; c < 4; ++c) I.block<4>(H + c * CHUNK, 128, 128, c == 0 && !init);
+      I.commit(B_ACC_FULL + 1);
     }
     // ---- albedo1 | shading1 -> accumulator 1 ----------------------------------------------------
     for (int h = 0; h < 2; ++h) {
       const bool init = I.bias(256 + h * 128);
       for (int c = 0; c < 4; ++c) {
-        I.block(H + c * CHUNK, 4, 128, 256 + h * 128, c == 0 && !init);
-        if (h == 1) tc_commit(sy.addr(B_A_FREE + c));
+        I.block<4>(H + c * CHUNK, 128, 256 + h * 128, c == 0 && !init);
+        if (h == 1) I.commit(B_A_FREE + c);
       }
-      tc_commit(sy.addr(B_ACC_FULL + 2 + h));
+      I.commit(B_ACC_FULL + 2 + h);
     }
     // ---- residual head on relu(views'): 16 x 128 -> accumulator 0 cols [0,16) -------------------
     for (int c = 0; c < 2; ++c) {
       sy.wait(B_V_READY + c);
       tc_fence_after();
-      I.block(V + c * CHUNK, 4, 16, 0, c == 0);
+      I.block<4>(V + c * CHUNK, 16, 0, c == 0);
     }
-    tc_commit(sy.addr(B_V_FREE));
+    I.commit(B_V_FREE);
     // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> cols [16,32) ---------------
     for (int c = 0; c < 4; ++c) {
       sy.wait(B_A_READY + c);
       tc_fence_after();
-      I.block(H + c * CHUNK, 4, 16, 16, c == 0);
-      tc_commit(sy.addr(B_A_FREE + c));
+      I.block<4>(H + c * CHUNK, 16, 16, c == 0);
+      I.commit(B_A_FREE + c);
     }
-    tc_commit(sy.addr(B_SMALL_FULL));
+    I.commit(B_SMALL_FULL);
     // ---- semantic logits on relu(sem1): C x 128 -> accumulator 1 cols [0, sem_rows) ---------------
     if (P.C > 0) {
       for (int c = 0; c < 2; ++c) {
         sy.wait(B_A_READY + c);
         tc_fence_after();
-        I.block(H + c * CHUNK, 4, P.sem_rows, 256, c == 0);
-        tc_commit(sy.addr(B_A_FREE + c));
+        I.block<4>(H + c * CHUNK, P.sem_rows, 256, c == 0);
+        I.commit(B_A_FREE + c);
       }
-      tc_commit(sy.addr(B_SEM2_FULL));
+      I.commit(B_SEM2_FULL);
     }
   }
 }
@@ -668,6 +698,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   Sync sy;
   sy.bar0 = smem_base + SM_BAR;
   sy.dbg = P.dbg;
+  sy.prof = nullptr;
   sy.dead = false;
   sy.tile = -1;
   sy.phase = 0;
@@ -686,7 +717,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     mbar_init(sy.addr(B_TAIL_DONE), 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 12) {
     // constant operands: alpha_linear row (fp32) and the "ones" tile of the bias MMAs:
     // 2 core matrices of 8 rows x 8 halves; K columns 0..2 are 1.0, the rest 0
     float* s_alpha = reinterpret_cast<float*>(smem + SM_ALPHA);
@@ -698,7 +729,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     }
     fence_async_smem();
   }
-  if (warp == 1) {
+  if (warp == 15) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -713,19 +744,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
                             (0xFull << B_A_FREE) | (1ull << B_V_FREE) | (1ull << B_TAIL_DONE);
   sy.phase = released;
 
-  if (warp == 0) {
-    if (lane == 0) producer(P, sy, smem_base, CL, rank);
-  } else if (warp == 1) {
-    if (lane == 0) issuer(P, sy, smem_base, tmem, CL);
-  } else if (warp >= 4 && warp < 8) {
-    front_end(P, sy, smem_base, (warp - 4) * 32 + lane);
-  } else if (warp >= 8) {
-    epilogue(P, sy, smem, smem_base, tmem, warp & 3, (warp - 8) >> 2, lane);
+  if (P.prof != nullptr && blockIdx.x == 0) {
+    const int role = (threadIdx.x == 448) ? 0 : (threadIdx.x == 480 ? 1 : (threadIdx.x == 256 ? 2 : (threadIdx.x == 0 ? 3 : -1)));
+    if (role >= 0) sy.prof = P.prof + role * 128;
   }
+  const long long t_start = clock64();
+  // warp roles.  The scheduler favours the highest warp id of each sub-partition, so the MMA issuer
+  // (15) and the weight producer (14) sit on top of their sub-partitions; both run converged on all
+  // 32 lanes (addresses and descriptors stay on the uniform datapath) and elect one lane to issue.
+  if (warp == 14) {
+    if (!P.no_weights) producer(P, sy, smem_base, CL, rank);
+  } else if (warp == 15) {
+    issuer(P, sy, smem_base, tmem, CL);
+  } else if (warp >= 8 && warp < 12) {
+    front_end(P, sy, smem_base, (warp - 8) * 32 + lane);
+  } else if (warp < 8) {
+    epilogue(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
+  }
+  if (sy.prof != nullptr) sy.prof[63] = clock64() - t_start;
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into this CTA
-  if (warp == 1) {
+  if (warp == 15) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
@@ -752,6 +792,16 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   P.sem_rows = (a.n_classes + 15) / 16 * 16;
   static const int bias_mma_env = getenv("INRF_TC_BIASMMA") ? atoi(getenv("INRF_TC_BIASMMA")) : 1;
   P.bias_mma = bias_mma_env ? 1 : 0;
+  static const bool prof_env = getenv("INRF_TC_PROF") != nullptr && getenv("INRF_TC_PROF")[0] == '1';
+  static const bool now_env = getenv("INRF_TC_NOWEIGHTS") != nullptr && getenv("INRF_TC_NOWEIGHTS")[0] == '1';
+  P.no_weights = now_env ? 1 : 0;
+  P.prof = nullptr;
+  if (prof_env) {
+    long long* pp = nullptr;
+    INRF_CUDA(cudaGetSymbolAddress((void**)&pp, tc::g_prof));
+    INRF_CUDA(cudaMemsetAsync(pp, 0, 4 * 128 * sizeof(long long), st));
+    P.prof = pp;
+  }
   int* dbg = nullptr;
   INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, tc::g_dbg));
   P.dbg = dbg;
@@ -782,6 +832,24 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   INRF_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+  if (prof_env) {
+    static const char* bar_names[] = {"WFULL0","WFULL1","WFULL2","WFULL3","WFULL4","WFULL5","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3","WEMPTY4","WEMPTY5",
+      "PE_READY","PE_FREE","DIR_READY","DIR_FREE","A_READY0","A_READY1","A_READY2","A_READY3","A_FREE0","A_FREE1","A_FREE2","A_FREE3",
+      "ACC_FULL0","ACC_FULL1","ACC_FULL2","ACC_FULL3","V_READY0","V_READY1","V_FREE","SMALL_FULL","SEM2_FULL","TAIL_DONE"};
+    static const char* roles[] = {"producer", "issuer", "frontend", "epilogue"};
+    long long h[4 * 128];
+    INRF_CUDA(cudaStreamSynchronize(st));
+    INRF_CUDA(cudaMemcpyFromSymbol(h, tc::g_prof, sizeof(h)));
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "TCPROF role=%s total_cycles=%lld n_iter=%d\n", roles[r], h[r * 128 + 63], P.n_iter);
+      long long w_full = 0, w_cnt = 0;
+      for (int b = 0; b < 34; ++b) {
+        if (h[r * 128 + 64 + b] == 0) continue;
+        fprintf(stderr, "TCPROF   %-10s waited %12lld cycles over %8lld waits\n", bar_names[b], h[r * 128 + b], h[r * 128 + 64 + b]);
+        (void)w_full; (void)w_cnt;
+      }
+    }
+  }
   if (checked) {      // debug mode: synchronise and surface watchdog records as errors
     int h[16];
     INRF_CUDA(cudaStreamSynchronize(st));

@@ -125,7 +125,9 @@ def test_ssr_renderer_golden(dev, golden_dir, precision):
             assert e < TOL, (k, lvl, e)
     assert rel_err(ev["z_std"], g["eval_z_std"]) < TOL
     assert ev["raw_coarse"].shape == (rays.shape[0], 64, 11 + C) and ev["raw_fine"].shape == (rays.shape[0], 192, 11 + C)
-    assert rel_err(ep["feat_map_fine"], g["ep_feat_map_fine"]) < TOL
+    # endpoint features are ReLU outputs (many exactly or nearly zero): error relative to the map's scale
+    feat = g["ep_feat_map_fine"]
+    assert rel_err(ep["feat_map_fine"], feat, floor=float(np.abs(feat).max())) < TOL
     assert ep["raw_fine"].shape[-1] == 11 + C + 128
 
 

@@ -105,8 +105,8 @@ def test_raw2outputs_golden_and_variants(dev, golden_dir):
     want = orc.composite(raw2, z2, rd2, noise, True, C, True)
     rec, w = ops.raw2outputs_rec(raw2.to(dev), z2.to(dev), rd2.to(dev), noise.to(dev), True, C, True)
     assert rel_err(w, want["weights"], floor=1e-2) < 1e-4        # weights live in [0,1]
-    assert rel_err(rec[:, 13:13 + C], want["sem"], floor=1e-2) < 2e-5
-    assert rel_err(rec[:, 13 + C:], want["feat"], floor=1e-2) < 2e-5
+    assert rel_err(rec[:, 13:13 + C], want["sem"], floor=1e-2) < 5e-5
+    assert rel_err(rec[:, 13 + C:], want["feat"], floor=1e-2) < 5e-5
     assert rel_err(rec[:, 0:3], want["rgb"], floor=1e-2) < 2e-5
     assert rel_err(rec[:, 9:12], want["residual"], floor=1e-2) < 2e-5
     tup = ssr.raw2outputs(raw2[..., :11 + C].to(dev), z2.to(dev), rd2.to(dev), 0, False, True, C, False)
