@@ -101,11 +101,18 @@ struct TcBlock {
   int32_t bytes;
 };
 constexpr int TC_MAX_BLOCKS = 128;
-constexpr int TC_SLOT_BYTES = 16384;
+constexpr int TC_SLOT_BYTES = 32768;   // one ring stage: a 256-row x 64-K operand tile
+constexpr int TC_MAX_FILLS = 64;
 
+// The blob is a sequence of 128-row (or narrower) sub-blocks; consecutive sub-blocks that the MMA
+// warp consumes as ONE operand tile (e.g. the two N halves of a 256-wide layer for one K chunk)
+// are adjacent and streamed as one "fill" of the shared-memory ring.
 struct TcProgram {
   int n_blocks;
   int bytes;
+  int n_fills;
+  int fill_off[TC_MAX_FILLS];
+  int fill_bytes[TC_MAX_FILLS];
   TcBlock blk[TC_MAX_BLOCKS];
 };
 int make_tc_program(int variant, int n_classes, TcProgram* prog);

@@ -79,6 +79,7 @@ struct Params {
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
   int* dbg;                       // [16] watchdog record (device)
   long long* prof;                // optional [4][64] wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
+  int exp_mode;                   // issue-order experiment (timing only, with no_weights): 1 interleave halves, 2 N=256
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
 };
 
@@ -388,6 +389,28 @@ struct Issuer {
     __syncwarp();
     release();
   }
+  // timing experiments (no_weights only): one K chunk into both accumulator halves
+  __device__ __forceinline__ void exp_chunk(uint32_t a_chunk, uint32_t col, bool first, int mode) {
+    tc_fence_after();
+    const uint64_t ad = make_desc(a_chunk);
+    const uint64_t bd = make_desc(smem_base + SM_RING + (slot & 3) * TC_SLOT_BYTES);
+    if (leader) {
+      if (mode == 2) {
+        const uint32_t id = make_idesc(256);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+      } else {
+        const uint32_t id = make_idesc(128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+          tc_mma(tmem + col + 128, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+        }
+      }
+    }
+    __syncwarp();
+    slot = (slot + 1 == NS) ? 0 : slot + 1;
+  }
   __device__ __forceinline__ void release() {
     if (!no_weights && leader) {
       if (cl == 1) tc_commit(sy.addr(B_WEMPTY + slot));
@@ -429,6 +452,17 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
     // ---- trunk layers 1..7 -----------------------------------------------------------------
     for (int l = 1; l < 8; ++l) {
       const uint32_t acc = (l & 1) * 256;
+      if (P.exp_mode != 0 && P.no_weights) {
+        if (l == 5) { I.exp_chunk(PE, acc, true, P.exp_mode); I.commit(B_PE_FREE); }
+        for (int c = 0; c < 4; ++c) {
+          sy.wait(B_A_READY + c);
+          I.exp_chunk(H + c * CHUNK, acc, l != 5 && c == 0, P.exp_mode);
+          I.commit(B_A_FREE + c);
+        }
+        I.commit(B_ACC_FULL + (l & 1) * 2 + 0);
+        I.commit(B_ACC_FULL + (l & 1) * 2 + 1);
+        continue;
+      }
       for (int h = 0; h < 2; ++h) {
         bool first = !I.bias(acc + h * 128);
         if (l == 5) {                    // skip connection: [gamma(x), h] -> K = 64 + 256
@@ -795,6 +829,8 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   static const bool prof_env = getenv("INRF_TC_PROF") != nullptr && getenv("INRF_TC_PROF")[0] == '1';
   static const bool now_env = getenv("INRF_TC_NOWEIGHTS") != nullptr && getenv("INRF_TC_NOWEIGHTS")[0] == '1';
   P.no_weights = now_env ? 1 : 0;
+  static const int exp_env = getenv("INRF_TC_EXP") ? atoi(getenv("INRF_TC_EXP")) : 0;
+  P.exp_mode = exp_env;
   P.prof = nullptr;
   if (prof_env) {
     long long* pp = nullptr;

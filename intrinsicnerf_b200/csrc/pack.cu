@@ -70,48 +70,52 @@ static void push(TcProgram* p, int layer, int rows, int n0, int k0, int kcols, i
   TcBlock& b = p->blk[p->n_blocks++];
   b.layer = (int16_t)layer; b.rows = (int16_t)rows; b.n0 = (int16_t)n0; b.k0 = (int16_t)k0;
   b.kcols = (int16_t)kcols; b.kind = (int16_t)kind; b.byte_off = p->bytes;
-  b.bytes = (kind == 3) ? 4096 : rows * 128;
-  p->bytes += (b.bytes + 1023) / 1024 * 1024;       // keep every block 1024-byte aligned in the blob
+  b.bytes = (kind == 3) ? rows * 32 : rows * 128;
+  p->bytes += b.bytes;
 }
 // bias of `layer` rows [n0, n0+128) as a K=16 operand (accumulator initialisation by MMA)
 static void push_bias(TcProgram* p, int layer, int n0) { push(p, layer, 128, n0, 0, 3, 3); }
+// everything pushed since `start_bytes` becomes one ring fill
+static void close_fill(TcProgram* p, int start_bytes) {
+  p->fill_off[p->n_fills] = start_bytes;
+  p->fill_bytes[p->n_fills] = p->bytes - start_bytes;
+  p->n_fills++;
+  p->bytes = (p->bytes + 1023) / 1024 * 1024;      // next fill starts 1024-byte aligned
+}
 
 int make_tc_program(int variant, int n_classes, TcProgram* p) {
-  p->n_blocks = 0; p->bytes = 0;
-  // trunk: per (layer, N half): bias block, then the K chunks
+  p->n_blocks = 0; p->bytes = 0; p->n_fills = 0;
+  const bool sem = n_classes > 0;
+  int f;
+#define FILL(stmts) do { f = p->bytes; stmts; close_fill(p, f); } while (0)
+  // trunk layers: N = 256 operand tiles (rows 0..127 | 128..255), one fill per K chunk
   for (int l = 0; l < 8; ++l) {
-    for (int h = 0; h < 2; ++h) {
-      push_bias(p, L_T0 + l, 128 * h);
-      if (l == 0) { push(p, L_T0, 128, 128 * h, 0, PE_PTS, 0); continue; }
-      if (l == 5) push(p, L_T5, 128, 128 * h, 0, PE_PTS, 0);
-      int base = (l == 5) ? PE_PTS : 0;
-      for (int c = 0; c < 4; ++c) push(p, L_T0 + l, 128, 128 * h, base + 64 * c, 64, 0);
-    }
+    FILL(push_bias(p, L_T0 + l, 0); push_bias(p, L_T0 + l, 128));
+    if (l == 0 || l == 5) FILL(push(p, L_T0 + l, 128, 0, 0, PE_PTS, 0); push(p, L_T0 + l, 128, 128, 0, PE_PTS, 0));
+    if (l == 0) continue;
+    const int base = (l == 5) ? PE_PTS : 0;
+    for (int c = 0; c < 4; ++c)
+      FILL(push(p, L_T0 + l, 128, 0, base + 64 * c, 64, 0); push(p, L_T0 + l, 128, 128, base + 64 * c, 64, 0));
   }
-  // views' (composed with feature_linear): K = 256 (h) + 27 (dir PE)
-  push_bias(p, -1, 0);
-  for (int c = 0; c < 4; ++c) push(p, -1, 128, 0, 64 * c, 64, 1);
-  push(p, L_VIEWS, 128, 0, W_HID, PE_DIR, 0);
-  // semantic hidden layer
-  if (n_classes > 0) {
-    push_bias(p, L_SEM1, 0);
-    for (int c = 0; c < 4; ++c) push(p, L_SEM1, 128, 0, 64 * c, 64, 0);
-  }
-  // albedo1 | shading1 as the two N halves of one 256-wide GEMM
-  push_bias(p, L_ALB1, 0);
-  for (int c = 0; c < 4; ++c) push(p, L_ALB1, 128, 0, 64 * c, 64, 0);
-  push_bias(p, L_SH1, 0);
-  for (int c = 0; c < 4; ++c) push(p, L_SH1, 128, 0, 64 * c, 64, 0);
-  // residual head on relu(views'):  16 x 128
-  for (int c = 0; c < 2; ++c) push(p, L_RES, 16, 0, 64 * c, 64, 0);
+  // albedo1 | shading1: one 256-wide GEMM on the trunk output
+  FILL(push_bias(p, L_ALB1, 0); push_bias(p, L_SH1, 0));
+  for (int c = 0; c < 4; ++c) FILL(push(p, L_ALB1, 128, 0, 64 * c, 64, 0); push(p, L_SH1, 128, 0, 64 * c, 64, 0));
+  // views' (composed with feature_linear) [| semantic hidden layer]: N = 128 [256], K = 256, then
+  // the 27 direction-encoding columns (K = 32) for the views' rows only
+  FILL(push_bias(p, -1, 0); if (sem) push_bias(p, L_SEM1, 0));
+  for (int c = 0; c < 4; ++c) FILL(push(p, -1, 128, 0, 64 * c, 64, 1); if (sem) push(p, L_SEM1, 128, 0, 64 * c, 64, 0));
+  FILL(push(p, L_VIEWS, 128, 0, W_HID, PE_DIR, 0));
+  // residual head on relu(views'):  16 x 128 (two K chunks in one fill)
+  FILL(for (int c = 0; c < 2; ++c) push(p, L_RES, 16, 0, 64 * c, 64, 0));
   // albedo2 (rows 0..2, K 0..127) + shading2 (row 3, K 128..255): block-diagonal 16 x 256
-  for (int c = 0; c < 4; ++c) push(p, L_ALB2, 16, 0, 64 * c, 64, 2);
+  FILL(for (int c = 0; c < 4; ++c) push(p, L_ALB2, 16, 0, 64 * c, 64, 2));
   // semantic logits on relu(sem1): ceil16(C) x 128
-  if (n_classes > 0) {
-    int rows = (n_classes + 15) / 16 * 16;
-    for (int c = 0; c < 2; ++c) push(p, L_SEM2, rows, 0, 64 * c, 64, 0);
+  if (sem) {
+    const int rows = (n_classes + 15) / 16 * 16;
+    FILL(for (int c = 0; c < 2; ++c) push(p, L_SEM2, rows, 0, 64 * c, 64, 0));
   }
-  if (p->n_blocks > TC_MAX_BLOCKS) { set_error("tc program too long"); return INRF_EUNSUPPORTED; }
+#undef FILL
+  if (p->n_blocks > TC_MAX_BLOCKS || p->n_fills > TC_MAX_FILLS) { set_error("tc program too long"); return INRF_EUNSUPPORTED; }
   return INRF_OK;
 }
 
