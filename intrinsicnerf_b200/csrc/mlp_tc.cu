@@ -5,22 +5,26 @@
 // SSR/models/semantic_nerf.py:123-181, fused with the Embedder and run_network's
 // per-sample view-direction expansion) runs without touching HBM in between:
 //
-//   warp 14     weight producer : streams the pre-swizzled fp16 operand blocks of the packed
-//                                 blob (pack.cu, MMA issue order) into a shared-memory ring with
-//                                 cp.async.bulk + mbarrier complete_tx (TMA bulk copies)
-//   warp 15     MMA issuer      : one elected lane issues tcgen05.mma (kind::f16, M=128, N=128/16..112,
-//                                 K=16) with fp32 accumulators in TMEM; tcgen05.commit signals
-//                                 "accumulator half ready", "weight slot free", "A chunk free"
+//   warp 14     weight producer : streams the pre-swizzled fp16 operand tiles of the packed blob
+//                                 (pack.cu, MMA issue order) into a 4 x 32 KB shared-memory ring with
+//                                 cp.async.bulk + mbarrier complete_tx (TMA bulk copies; optionally
+//                                 multicast across a 2-CTA cluster)
+//   warp 15     MMA issuer      : converged warp, one elected lane issues tcgen05.mma (kind::f16,
+//                                 M=128, N=256 for the 256-wide layers, K=16) with fp32 accumulators
+//                                 in TMEM; the bias enters as one extra K=16 MMA of a constant "ones"
+//                                 tile with hi/lo/lo2 bias columns (accumulator initialisation);
+//                                 tcgen05.commit signals "accumulator ready", "ring slot free",
+//                                 "A chunk free"
 //   warps 8-11  front end       : sample position (o + d z), range-reduced sin/cos positional
 //                                 encoding of the NEXT tile, written as fp16 UMMA operand tiles
-//   warps 0-7   epilogue        : tcgen05.ld accumulator -> +bias, ReLU (fp32) -> fp16 -> the next
-//                                 layer's A operand (SWIZZLE_128B K-major), in place; sigma head as
-//                                 an fp32 dot product on the un-rounded trunk output; sigmoid heads;
+//   warps 0-7   epilogue        : tcgen05.ld accumulator -> ReLU -> fp16 -> the next layer's A operand
+//                                 (SWIZZLE_128B K-major), in place, K chunk by K chunk so that the
+//                                 next layer's MMAs start as soon as chunk 0 exists; sigma head as an
+//                                 fp32 dot product on the un-rounded trunk output; sigmoid heads;
 //                                 packed raw rows to HBM
 //
-// The accumulator of layer l (TMEM columns (l&1)*256..) is drained by the epilogue in two N
-// halves while the tensor pipe already runs layer l's second half / layer l+1, so the tensor
-// core only waits for the first A chunk of each layer.
+// Why N=256 instructions: consecutive MMAs into the same accumulator are dependent; a 64-cycle
+// N=128 instruction cannot hide the accumulate latency (measured: 1.3x slower than N=256).
 //
 // Arithmetic: operands rounded to fp16 (RN, 11-bit significand), products and sums in fp32.
 // feature_linear has no activation, so views_linears.0 o feature_linear is composed into one
@@ -33,14 +37,14 @@ namespace tc {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 512;
-constexpr int NS = 6;                       // weight ring stages
+constexpr int NS = 4;                       // weight ring stages of TC_SLOT_BYTES (32 KB)
 constexpr int CHUNK = 16384;                // 128 rows x 64 fp16, SWIZZLE_128B
 // shared memory map (bytes)
 constexpr int SM_H = 0;                     // 4 chunks: hidden activations (A operand), in place
 constexpr int SM_PE = SM_H + 4 * CHUNK;     // gamma(x): 63 cols + zero
 constexpr int SM_DIR = SM_PE + CHUNK;       // gamma(d): 27 cols + zeros (only K=32 is multiplied)
-constexpr int SM_V = SM_DIR + CHUNK;        // 2 chunks: relu(views')
-constexpr int SM_RING = SM_V + 2 * CHUNK;
+constexpr int SM_V = SM_PE;                 // relu(views') (2 chunks) reuses the PE|DIR region at the tile tail
+constexpr int SM_RING = SM_DIR + CHUNK;
 constexpr int SM_SIG = SM_RING + NS * TC_SLOT_BYTES;   // [128][2] fp32 sigma partials
 constexpr int SM_ALPHA = SM_SIG + 1024;                // alpha_linear weight row, fp32 [256]
 constexpr int SM_ONES = SM_ALPHA + 1024;               // 8 x 16 fp16 "ones" A operand for the bias MMAs
@@ -54,32 +58,31 @@ constexpr int TCB_VIEWS = 2048, TCB_SEM1 = 2176, TCB_ALBSH = 2304, TCB_ALPHA_W =
 
 // barrier ids
 enum {
-  B_WFULL = 0,                 // [NS]
-  B_WEMPTY = B_WFULL + NS,     // [NS]
-  B_PE_READY = B_WEMPTY + NS, B_PE_FREE, B_DIR_READY, B_DIR_FREE,
-  B_A_READY,                   // [4]
-  B_A_FREE = B_A_READY + 4,    // [4]
-  B_ACC_FULL = B_A_FREE + 4,   // [4] = parity*2 + half
-  B_V_READY = B_ACC_FULL + 4,  // [2]
-  B_V_FREE = B_V_READY + 2,
+  B_WFULL = 0,                 // [NS] ring slot filled (tx bytes)
+  B_WEMPTY = B_WFULL + NS,     // [NS] ring slot consumed (tcgen05.commit)
+  B_F_READY = B_WEMPTY + NS,   // PE|DIR tiles of the next tile written (128 front-end threads)
+  B_F_FREE,                    // PE|DIR|V region no longer read by the tensor core
+  B_A_READY,                   // [4] H chunk c written by all 8 epilogue warps (256 threads)
+  B_A_FREE = B_A_READY + 4,    // [4] H chunk c no longer read by the tensor core
+  B_ACC_FULL = B_A_FREE + 4,   // [2] accumulator (TMEM columns parity*256 ..) complete
+  B_V_READY = B_ACC_FULL + 2,  // relu(views') written (256 threads)
   B_SMALL_FULL, B_SEM2_FULL, B_TAIL_DONE,
   B_COUNT
 };
-static_assert(B_COUNT <= 48, "barrier ids must fit the 64-bit phase mask and the 512 B area");
+static_assert(B_COUNT <= 40, "barrier area");
 
 struct Params {
   MlpArgs a;
-  const unsigned char* blocks;    // fp16 operand blocks
+  const unsigned char* blocks;    // fp16 operand blob
   const float* bias;              // fp32 bias table
-  int n_blocks;
-  int block_off[TC_MAX_BLOCKS];   // byte offsets
-  int block_bytes[TC_MAX_BLOCKS];
+  int n_fills;
+  int fill_off[TC_MAX_FILLS];     // byte offsets / sizes of the ring fills of one tile
+  int fill_bytes[TC_MAX_FILLS];
   int out_ch, C, sem_rows;
   int bias_mma;                   // 1: accumulators are initialised with the bias by an MMA (default)
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
   int* dbg;                       // [16] watchdog record (device)
-  long long* prof;                // optional [4][64] wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
-  int exp_mode;                   // issue-order experiment (timing only, with no_weights): 1 interleave halves, 2 N=256
+  long long* prof;                // optional wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
 };
 
@@ -246,16 +249,21 @@ __device__ __forceinline__ void pe_coord(float x, int n_freqs, float* s, float* 
   }
 }
 
-__device__ __forceinline__ void write_units(uint32_t chunk, int row, const float* v, int n_units) {
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    if (u < n_units)
-      st_shared_v4(swz(chunk, row, u), pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
-                   pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7]));
-  }
+__device__ __forceinline__ uint32_t relu_h2(uint32_t h2) {
+  __half2 v = *reinterpret_cast<__half2*>(&h2);
+  v = __hmax2(v, __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// swizzled byte offsets of the 8 16-byte units of this thread's row inside a chunk
+struct RowAddr {
+  uint32_t unit[8];
+};
+
 __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
+  RowAddr ra;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
   for (int it = 0; it < P.n_iter; ++it) {
     const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
     sy.tile = (int)tile;
@@ -283,6 +291,8 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
         for (int i = 0; i < 3; ++i) x[i] = __fdiv_rn(x[i], P.a.pe_scale);
       }
     }
+    // encode into packed halves (registers) while the previous tile still owns the PE|DIR region
+    uint32_t pw[32], dw[16];
     {
       float pe[64];
       if (pre_embedded) {
@@ -299,10 +309,8 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
         }
       }
       pe[63] = 0.f;
-      sy.wait(B_PE_FREE);
-      write_units(smem_base + SM_PE, row, pe, 8);
-      fence_async_smem();
-      mbar_arrive(sy.addr(B_PE_READY));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pw[i] = pack_h2(pe[2 * i], pe[2 * i + 1]);
     }
     {
       float de[32];
@@ -321,16 +329,21 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
       }
 #pragma unroll
       for (int i = 27; i < 32; ++i) de[i] = 0.f;
-      sy.wait(B_DIR_FREE);
-      write_units(smem_base + SM_DIR, row, de, 4);
-      fence_async_smem();
-      mbar_arrive(sy.addr(B_DIR_READY));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dw[i] = pack_h2(de[2 * i], de[2 * i + 1]);
     }
+    sy.wait(B_F_FREE);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) st_shared_v4(smem_base + SM_PE + ra.unit[u], pw[4 * u], pw[4 * u + 1], pw[4 * u + 2], pw[4 * u + 3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) st_shared_v4(smem_base + SM_DIR + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
+    fence_async_smem();
+    mbar_arrive(sy.addr(B_F_READY));
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// weight producer
+// weight producer (converged warp, elected lane issues the bulk copies)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t smem_base, int cl, int rank) {
   int slot = 0;
@@ -338,18 +351,18 @@ __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t sme
   const bool leader = elect_one();
   for (int it = 0; it < P.n_iter; ++it) {
     sy.tile = it;
-    for (int b = 0; b < P.n_blocks; ++b) {
+    for (int b = 0; b < P.n_fills; ++b) {
       sy.wait(B_WEMPTY + slot);           // every CTA of the cluster has consumed this slot
       if (leader && !sy.dead) {
-        const uint32_t bytes = (uint32_t)P.block_bytes[b];
+        const uint32_t bytes = (uint32_t)P.fill_bytes[b];
         const uint32_t dst = smem_base + SM_RING + slot * TC_SLOT_BYTES;
         mbar_expect_tx(sy.addr(B_WFULL + slot), bytes);
         if (cl == 1) {
-          bulk_g2s(dst, P.blocks + P.block_off[b], bytes, sy.addr(B_WFULL + slot));
+          bulk_g2s(dst, P.blocks + P.fill_off[b], bytes, sy.addr(B_WFULL + slot));
         } else {
-          // each CTA fetches 1/cl of the block from L2 and multicasts it into every CTA's slot
+          // each CTA fetches 1/cl of the tile from L2 and multicasts it into every CTA's slot
           const uint32_t part = bytes / (uint32_t)cl;
-          bulk_g2s_mc(dst + rank * part, P.blocks + P.block_off[b] + rank * part, part, sy.addr(B_WFULL + slot), mask);
+          bulk_g2s_mc(dst + rank * part, P.blocks + P.fill_off[b] + rank * part, part, sy.addr(B_WFULL + slot), mask);
         }
       }
       __syncwarp();
@@ -359,7 +372,8 @@ __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t sme
 }
 
 // ------------------------------------------------------------------------------------------
-// MMA issuer (one thread)
+// MMA issuer: converged warp (descriptor arithmetic stays on the uniform datapath), one elected
+// lane issues tcgen05.mma / tcgen05.commit
 // ------------------------------------------------------------------------------------------
 struct Issuer {
   Sync& sy;
@@ -369,17 +383,29 @@ struct Issuer {
   int bias_mma;
   int no_weights;
   bool leader;
+  __device__ __forceinline__ uint32_t slot_addr() const { return smem_base + SM_RING + slot * TC_SLOT_BYTES; }
   __device__ __forceinline__ void commit(int bar) {
     if (leader) tc_commit(sy.addr(bar));
     __syncwarp();
   }
-  // one operand block: A chunk (K = 16*KSTEPS) x ring slot -> accumulator columns [col, col+n)
-  template <int KSTEPS>
-  __device__ __forceinline__ void block(uint32_t a_chunk, int n, uint32_t col, bool first) {
+  __device__ __forceinline__ void acquire() {        // next ring fill has landed
     if (!no_weights) sy.wait(B_WFULL + slot);
     tc_fence_after();
+  }
+  __device__ __forceinline__ void release() {        // MMAs reading the slot are done -> refill
+    if (!no_weights && leader) {
+      if (cl == 1) tc_commit(sy.addr(B_WEMPTY + slot));
+      else tc_commit_mc(sy.addr(B_WEMPTY + slot), (uint16_t)((1u << cl) - 1u));
+    }
+    __syncwarp();
+    slot = (slot + 1 == NS) ? 0 : slot + 1;
+  }
+  // K = 16*KSTEPS of A chunk `a_chunk` times the operand tile at byte offset `b_off` of the current
+  // slot -> accumulator columns [col, col+n)
+  template <int KSTEPS>
+  __device__ __forceinline__ void mma(uint32_t a_chunk, uint32_t b_off, int n, uint32_t col, bool first) {
     const uint64_t ad = make_desc(a_chunk);
-    const uint64_t bd = make_desc(smem_base + SM_RING + slot * TC_SLOT_BYTES);
+    const uint64_t bd = make_desc(slot_addr() + b_off);
     const uint32_t id = make_idesc(n);
     if (leader) {
 #pragma unroll
@@ -387,46 +413,20 @@ struct Issuer {
         tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
     }
     __syncwarp();
+  }
+  // whole fill = one operand tile
+  template <int KSTEPS>
+  __device__ __forceinline__ void fill_mma(uint32_t a_chunk, int n, uint32_t col, bool first) {
+    acquire();
+    mma<KSTEPS>(a_chunk, 0, n, col, first);
     release();
   }
-  // timing experiments (no_weights only): one K chunk into both accumulator halves
-  __device__ __forceinline__ void exp_chunk(uint32_t a_chunk, uint32_t col, bool first, int mode) {
-    tc_fence_after();
-    const uint64_t ad = make_desc(a_chunk);
-    const uint64_t bd = make_desc(smem_base + SM_RING + (slot & 3) * TC_SLOT_BYTES);
-    if (leader) {
-      if (mode == 2) {
-        const uint32_t id = make_idesc(256);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
-      } else {
-        const uint32_t id = make_idesc(128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
-          tc_mma(tmem + col + 128, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
-        }
-      }
-    }
-    __syncwarp();
-    slot = (slot + 1 == NS) ? 0 : slot + 1;
-  }
-  __device__ __forceinline__ void release() {
-    if (!no_weights && leader) {
-      if (cl == 1) tc_commit(sy.addr(B_WEMPTY + slot));
-      else tc_commit_mc(sy.addr(B_WEMPTY + slot), (uint16_t)((1u << cl) - 1u));   // release the slot in every CTA
-    }
-    __syncwarp();
-    slot = (slot + 1 == NS) ? 0 : slot + 1;
-  }
-  // accumulator columns [col, col+128) := bias (one K=16 MMA of the constant "ones" tile with the
-  // hi/lo/lo2 bias columns).  Returns true when the accumulator was initialised.
-  __device__ __forceinline__ bool bias(uint32_t col) {
-    if (!no_weights) sy.wait(B_WFULL + slot);
-    tc_fence_after();
+  // accumulator columns [col, col+n) := bias: one K=16 MMA of the constant "ones" tile with the
+  // hi/lo/lo2 bias columns of the fill.  Returns true when the accumulator was initialised.
+  __device__ __forceinline__ bool bias(int n, uint32_t col) {
+    acquire();
     if (bias_mma && leader)
-      tc_mma(tmem + col, make_desc_flat(smem_base + SM_ONES, 128, 0),
-             make_desc_flat(smem_base + SM_RING + slot * TC_SLOT_BYTES, 128, 256), make_idesc(128), 0u);
+      tc_mma(tmem + col, make_desc_flat(smem_base + SM_ONES, 128, 0), make_desc_flat(slot_addr(), 128, 256), make_idesc(n), 0u);
     __syncwarp();
     release();
     return bias_mma != 0;
@@ -436,189 +436,176 @@ struct Issuer {
 __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl) {
   Issuer I{sy, smem_base, tmem, 0, cl, P.bias_mma, P.no_weights, elect_one()};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
+  const bool sem = P.C > 0;
+  const int nv = sem ? 256 : 128;       // views' [| sem1] width
   for (int it = 0; it < P.n_iter; ++it) {
-    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
-    sy.tile = (int)tile;
+    sy.tile = it;
     sy.wait(B_TAIL_DONE);               // previous tile's accumulators drained
+    sy.wait(B_F_READY);                 // gamma(x), gamma(d) of this tile
     tc_fence_after();
-    // ---- trunk layer 0: K = 64 (gamma(x)) ------------------------------------------------
-    sy.wait(B_PE_READY);
-    tc_fence_after();
-    for (int h = 0; h < 2; ++h) {
-      const bool init = I.bias(h * 128);
-      I.block<4>(PE, 128, h * 128, !init);
-      I.commit(B_ACC_FULL + h);
+    // ---- trunk layer 0: K = 64 (gamma(x)) -> accumulator 0 ---------------------------------------
+    {
+      const bool init = I.bias(256, 0);
+      I.fill_mma<4>(PE, 256, 0, !init);
+      I.commit(B_ACC_FULL + 0);
     }
-    // ---- trunk layers 1..7 -----------------------------------------------------------------
+    // ---- trunk layers 1..7 ------------------------------------------------------------------------
     for (int l = 1; l < 8; ++l) {
       const uint32_t acc = (l & 1) * 256;
-      if (P.exp_mode != 0 && P.no_weights) {
-        if (l == 5) { I.exp_chunk(PE, acc, true, P.exp_mode); I.commit(B_PE_FREE); }
-        for (int c = 0; c < 4; ++c) {
-          sy.wait(B_A_READY + c);
-          I.exp_chunk(H + c * CHUNK, acc, l != 5 && c == 0, P.exp_mode);
-          I.commit(B_A_FREE + c);
-        }
-        I.commit(B_ACC_FULL + (l & 1) * 2 + 0);
-        I.commit(B_ACC_FULL + (l & 1) * 2 + 1);
-        continue;
+      bool first = !I.bias(256, acc);
+      if (l == 5) {                      // skip connection: [gamma(x), h] -> K = 64 + 256
+        I.fill_mma<4>(PE, 256, acc, first);
+        first = false;
       }
-      for (int h = 0; h < 2; ++h) {
-        bool first = !I.bias(acc + h * 128);
-        if (l == 5) {                    // skip connection: [gamma(x), h] -> K = 64 + 256
-          I.block<4>(PE, 128, acc + h * 128, first);
-          first = false;
-          if (h == 1) I.commit(B_PE_FREE);
-        }
-        for (int c = 0; c < 4; ++c) {
-          if (h == 0) { sy.wait(B_A_READY + c); tc_fence_after(); }
-          I.block<4>(H + c * CHUNK, 128, acc + h * 128, first);
-          first = false;
-          if (h == 1) I.commit(B_A_FREE + c);
-        }
-        I.commit(B_ACC_FULL + (l & 1) * 2 + h);
-      }
-    }
-    // ---- views' = relu(W' h + Wd gamma(d) + b')  -> accumulator 0, half 0 ----------------------
-    {
-      const bool init = I.bias(0);
       for (int c = 0; c < 4; ++c) {
         sy.wait(B_A_READY + c);
-        tc_fence_after();
-        I.block<4>(H + c * CHUNK, 128, 0, c == 0 && !init);
+        I.fill_mma<4>(H + c * CHUNK, 256, acc, first);
+        first = false;
+        I.commit(B_A_FREE + c);
       }
+      I.commit(B_ACC_FULL + (l & 1));
     }
-    sy.wait(B_DIR_READY);
-    tc_fence_after();
-    I.block<2>(DIR, 128, 0, false);
-    I.commit(B_DIR_FREE);
-    I.commit(B_ACC_FULL + 0);
-    // ---- semantic hidden layer -> accumulator 0, half 1 ----------------------------------------
-    if (P.C > 0) {
-      const bool init = I.bias(128);
-      for (int c = 0; c < 4; ++c) I.block<4>(H + c * CHUNK, 128, 128, c == 0 && !init);
+    // ---- albedo1 | shading1 on the trunk output -> accumulator 0 ------------------------------------
+    {
+      bool first = !I.bias(256, 0);
+      for (int c = 0; c < 4; ++c) {
+        sy.wait(B_A_READY + c);          // all four waits also prove layer 7's accumulator (1) is drained
+        I.fill_mma<4>(H + c * CHUNK, 256, 0, first);
+        first = false;
+      }
+      I.commit(B_ACC_FULL + 0);
+    }
+    // ---- views' [| sem1] -> accumulator 1 -----------------------------------------------------------
+    {
+      bool first = !I.bias(nv, 256);
+      for (int c = 0; c < 4; ++c) {
+        I.fill_mma<4>(H + c * CHUNK, nv, 256, first);
+        first = false;
+        I.commit(B_A_FREE + c);          // last reader of the trunk output chunk c
+      }
+      I.fill_mma<2>(DIR, 128, 256, false);
       I.commit(B_ACC_FULL + 1);
     }
-    // ---- albedo1 | shading1 -> accumulator 1 ----------------------------------------------------
-    for (int h = 0; h < 2; ++h) {
-      const bool init = I.bias(256 + h * 128);
-      for (int c = 0; c < 4; ++c) {
-        I.block<4>(H + c * CHUNK, 128, 256 + h * 128, c == 0 && !init);
-        if (h == 1) I.commit(B_A_FREE + c);
-      }
-      I.commit(B_ACC_FULL + 2 + h);
-    }
-    // ---- residual head on relu(views'): 16 x 128 -> accumulator 0 cols [0,16) -------------------
-    for (int c = 0; c < 2; ++c) {
-      sy.wait(B_V_READY + c);
-      tc_fence_after();
-      I.block<4>(V + c * CHUNK, 16, 0, c == 0);
-    }
-    I.commit(B_V_FREE);
-    // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> cols [16,32) ---------------
+    // ---- residual head on relu(views'): 16 x 128 -> accumulator 1 cols [0,16) ------------------------
+    sy.wait(B_V_READY);
+    I.acquire();
+    I.mma<4>(V, 0, 16, 256, true);
+    I.mma<4>(V + CHUNK, 2048, 16, 256, false);
+    I.release();
+    I.commit(B_F_FREE);                  // PE | DIR | V region may be rewritten by the front end
+    // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> accumulator 1 cols [16,32) ------
+    I.acquire();
     for (int c = 0; c < 4; ++c) {
       sy.wait(B_A_READY + c);
       tc_fence_after();
-      I.block<4>(H + c * CHUNK, 16, 16, c == 0);
+      I.mma<4>(H + c * CHUNK, 2048 * c, 16, 256 + 16, c == 0);
       I.commit(B_A_FREE + c);
     }
+    I.release();
     I.commit(B_SMALL_FULL);
-    // ---- semantic logits on relu(sem1): C x 128 -> accumulator 1 cols [0, sem_rows) ---------------
-    if (P.C > 0) {
+    // ---- semantic logits on relu(sem1): C x 128 -> accumulator 0 cols [0, sem_rows) -------------------
+    if (sem) {
+      I.acquire();
       for (int c = 0; c < 2; ++c) {
         sy.wait(B_A_READY + c);
         tc_fence_after();
-        I.block<4>(H + c * CHUNK, P.sem_rows, 256, c == 0);
+        I.mma<4>(H + c * CHUNK, (uint32_t)(P.sem_rows * 128 * c), P.sem_rows, 0, c == 0);
         I.commit(B_A_FREE + c);
       }
+      I.release();
       I.commit(B_SEM2_FULL);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// epilogue warps
+// epilogue warps.  Warp (q, jj): TMEM lanes 32q..32q+31 (one row per thread); of every 64-column
+// K chunk it owns columns jj*32..jj*32+31, so all 8 warps finish chunk 0 first, then 1, 2, 3.
 // ------------------------------------------------------------------------------------------
-// 64 accumulator columns of this thread's row -> ReLU -> fp16 -> 8 swizzled 16-byte stores into
-// the destination A chunk.  With the bias already in the accumulator (bias MMA) the ReLU runs on
-// packed halves (relu(round(x)) == round(relu(x))), 1 cvt + 1 max per two columns.
-struct RowAddr {
-  uint32_t unit[8];   // byte offset of 16-byte unit u of this thread's row inside a chunk (swizzled)
-};
-
-__device__ __forceinline__ uint32_t relu_h2(uint32_t h2) {
-  __half2 v = *reinterpret_cast<__half2*>(&h2);
-  v = __hmax2(v, __float2half2_rn(0.f));
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
+// 32 accumulator columns -> (+bias) -> ReLU -> fp16 -> 4 swizzled 16-byte stores
 template <bool ADD_BIAS>
-__device__ __forceinline__ void epi_half(uint32_t taddr, const float* __restrict__ bias, uint32_t dst_chunk,
-                                         const RowAddr& ra, Sync& sy, int free_bar, const float* alpha_w_smem,
-                                         float* sigma_acc, float* gout) {
-  uint32_t v[64];
-  tmem_ld32(taddr, v);
-  tmem_ld32(taddr + 32, v + 32);
-  tmem_ld_wait();
+__device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __restrict__ bias, uint32_t dst_chunk,
+                                            const RowAddr& ra, int unit0, const float* alpha_w_smem, float* sigma_acc,
+                                            float* gout) {
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
   if (ADD_BIAS) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(bias) + i);
-      v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + t.x);
-      v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + t.y);
-      v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + t.z);
-      v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + t.w);
+      f[4 * i] += t.x; f[4 * i + 1] += t.y; f[4 * i + 2] += t.z; f[4 * i + 3] += t.w;
     }
   }
   if (alpha_w_smem != nullptr) {              // sigma head: fp32 dot on the un-rounded ReLU output
     float s = *sigma_acc;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const float4 t = *reinterpret_cast<const float4*>(alpha_w_smem + 4 * i);
-      s = fmaf(fmaxf(__uint_as_float(v[4 * i]), 0.f), t.x, s);
-      s = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), t.y, s);
-      s = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), t.z, s);
-      s = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), t.w, s);
+      s = fmaf(fmaxf(f[4 * i], 0.f), t.x, s);
+      s = fmaf(fmaxf(f[4 * i + 1], 0.f), t.y, s);
+      s = fmaf(fmaxf(f[4 * i + 2], 0.f), t.z, s);
+      s = fmaf(fmaxf(f[4 * i + 3], 0.f), t.w, s);
     }
     *sigma_acc = s;
   }
   if (gout != nullptr) {                      // endpoint feature rows (fp32, post-ReLU)
 #pragma unroll
-    for (int i = 0; i < 64; ++i) gout[i] = fmaxf(__uint_as_float(v[i]), 0.f);
+    for (int i = 0; i < 32; ++i) gout[i] = fmaxf(f[i], 0.f);
   }
-  if (free_bar >= 0) sy.wait(free_bar);
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < 4; ++u) {
     uint32_t pk[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      pk[i] = relu_h2(pack_h2(__uint_as_float(v[8 * u + 2 * i]), __uint_as_float(v[8 * u + 2 * i + 1])));
-    st_shared_v4(dst_chunk + ra.unit[u], pk[0], pk[1], pk[2], pk[3]);
+    for (int i = 0; i < 4; ++i) pk[i] = relu_h2(pack_h2(f[8 * u + 2 * i], f[8 * u + 2 * i + 1]));
+    st_shared_v4(dst_chunk + ra.unit[unit0 + u], pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
-__device__ __forceinline__ void epi_dispatch(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst_chunk,
-                                             const RowAddr& ra, Sync& sy, int free_bar, const float* alpha_w_smem,
-                                             float* sigma_acc, float* gout) {
-  if (add_bias) epi_half<true>(taddr, bias, dst_chunk, ra, sy, free_bar, alpha_w_smem, sigma_acc, gout);
-  else epi_half<false>(taddr, bias, dst_chunk, ra, sy, free_bar, alpha_w_smem, sigma_acc, gout);
+// A 256-column accumulator -> 4 H chunks, two chunks per TMEM load batch.
+// taddr: this thread's lane + accumulator base column; bias: 256 floats (fallback path only).
+__device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst0, int n_chunks,
+                                          const RowAddr& ra, int jj, Sync& sy, int free_bar0, int ready_bar0,
+                                          const float* alpha_smem, float* sigma_acc, float* gout0) {
+#pragma unroll 1
+  for (int cp = 0; cp < n_chunks; cp += 2) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(taddr + cp * 64 + jj * 32, v0);
+    tmem_ld32(taddr + (cp + 1) * 64 + jj * 32, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int c = cp + half;
+      const int col = c * 64 + jj * 32;
+      const uint32_t* v = half == 0 ? v0 : v1;
+      if (free_bar0 >= 0) sy.wait(free_bar0 + c);
+      float* g = gout0 ? gout0 + col : nullptr;
+      const float* aw = alpha_smem ? alpha_smem + col : nullptr;
+      if (add_bias) epi_store32<true>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
+      else epi_store32<false>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
+      fence_async_smem();
+      tc_fence_before();
+      if (ready_bar0 >= 0) mbar_arrive(sy.addr(ready_bar0 + c));
+    }
+  }
 }
 
 __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* smem, uint32_t smem_base, uint32_t tmem,
-                                         int q, int j, int lane) {
+                                         int q, int jj, int lane) {
   const int row = q * 32 + lane;
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
   float* s_sig = reinterpret_cast<float*>(smem + SM_SIG);
   const float* s_alpha = reinterpret_cast<const float*>(smem + SM_ALPHA);
   const uint32_t H = smem_base + SM_H, V = smem_base + SM_V;
   const bool add_bias = P.bias_mma == 0;
+  const bool sem = P.C > 0;
   RowAddr ra;
 #pragma unroll
   for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
   for (int it = 0; it < P.n_iter; ++it) {
-    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
+    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: stores are masked
     sy.tile = (int)tile;
     const int64_t m = tile * TILE_M + row;
     const bool valid = m < P.a.M;
@@ -626,62 +613,35 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
     float sig = 0.f;
     for (int l = 0; l < 8; ++l) {
-      for (int h = 0; h < 2; ++h) {
-        sy.wait(B_ACC_FULL + (l & 1) * 2 + h);
-        tc_fence_after();
-        const int c = 2 * h + j;                       // destination chunk = my 64 accumulator columns
-        const int col = h * 128 + j * 64;
-        epi_dispatch(add_bias, lane_addr + (l & 1) * 256 + col, P.bias + l * 256 + col, H + c * CHUNK, ra, sy,
-                     B_A_FREE + c, l == 7 ? s_alpha + col : nullptr, &sig, nullptr);
-        fence_async_smem();
-        tc_fence_before();
-        mbar_arrive(sy.addr(B_A_READY + c));
-      }
+      sy.wait(B_ACC_FULL + (l & 1));
+      tc_fence_after();
+      epi_layer(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, sy, B_A_FREE, B_A_READY,
+                l == 7 ? s_alpha : nullptr, &sig, nullptr);
     }
-    s_sig[row * 2 + j] = sig;                          // fixed-order sum later: deterministic sigma
-    // ---- relu(views') -> V chunk j (and the endpoint feature rows) --------------------------------
+    s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
+    // ---- relu(albedo1 | shading1) -> H (in place over the trunk output, chunk by chunk as the
+    //      views' MMAs release it) ------------------------------------------------------------------
     sy.wait(B_ACC_FULL + 0);
     tc_fence_after();
-    {
-      const int col = j * 64;
-      float* g = (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C + col : nullptr;
-      epi_dispatch(add_bias, lane_addr + col, P.bias + TCB_VIEWS + col, V + j * CHUNK, ra, sy, B_V_FREE, nullptr, nullptr, g);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    mbar_arrive(sy.addr(B_V_READY + j));
-    // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ------------------------------
-    for (int h = 0; h < 2; ++h) {
-      sy.wait(B_ACC_FULL + 2 + h);
-      tc_fence_after();
-      const int c = 2 * h + j;
-      const int col = h * 128 + j * 64;
-      epi_dispatch(add_bias, lane_addr + 256 + col, P.bias + TCB_ALBSH + col, H + c * CHUNK, ra, sy, B_A_FREE + c,
-                   nullptr, nullptr, nullptr);
-      fence_async_smem();
-      tc_fence_before();
-      mbar_arrive(sy.addr(B_A_READY + c));
-    }
-    // ---- relu(sem1) -> H chunk j (after the albedo2/shading2 MMAs released it) ------------------------
-    if (P.C > 0) {
-      sy.wait(B_ACC_FULL + 1);
-      tc_fence_after();
-      const int col = j * 64;
-      epi_dispatch(add_bias, lane_addr + 128 + col, P.bias + TCB_SEM1 + col, H + j * CHUNK, ra, sy, B_A_FREE + j,
-                   nullptr, nullptr, nullptr);
-      fence_async_smem();
-      tc_fence_before();
-      mbar_arrive(sy.addr(B_A_READY + j));
-    }
+    epi_layer(add_bias, lane_addr + 0, P.bias + TCB_ALBSH, H, 4, ra, jj, sy, B_A_FREE, B_A_READY, nullptr, nullptr, nullptr);
+    // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 1) -------------
+    sy.wait(B_ACC_FULL + 1);
+    tc_fence_after();
+    epi_layer(add_bias, lane_addr + 256, P.bias + TCB_VIEWS, V, 2, ra, jj, sy, -1, -1, nullptr, nullptr,
+              (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C : nullptr);
+    mbar_arrive(sy.addr(B_V_READY));
+    // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
+    if (sem)
+      epi_layer(add_bias, lane_addr + 256 + 128, P.bias + TCB_SEM1, H, 2, ra, jj, sy, B_A_FREE, B_A_READY, nullptr, nullptr, nullptr);
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
-    if (P.C > 0) sy.wait(B_SEM2_FULL);
+    if (sem) sy.wait(B_SEM2_FULL);
     tc_fence_after();
     __syncwarp();
     asm volatile("bar.sync 1, 256;" ::: "memory");     // both sigma partials of every row are in smem
-    if (j == 0) {
+    if (jj == 0) {
       uint32_t v[32];
-      tmem_ld32(lane_addr + 0, v);
+      tmem_ld32(lane_addr + 256, v);
       tmem_ld_wait();
       if (valid) {
         float res[3], alb[3], sh;
@@ -700,10 +660,10 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 #pragma unroll
         for (int i = 0; i < 3; ++i) grow[8 + i] = res[i];
       }
-    } else if (P.C > 0) {
+    } else if (sem) {
       for (int c0 = 0; c0 < P.C; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(lane_addr + 256 + c0, v);
+        tmem_ld32(lane_addr + c0, v);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -742,11 +702,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), CL); }
-    mbar_init(sy.addr(B_PE_READY), 128); mbar_init(sy.addr(B_PE_FREE), 1);
-    mbar_init(sy.addr(B_DIR_READY), 128); mbar_init(sy.addr(B_DIR_FREE), 1);
-    for (int c = 0; c < 4; ++c) { mbar_init(sy.addr(B_A_READY + c), 128); mbar_init(sy.addr(B_A_FREE + c), 1); mbar_init(sy.addr(B_ACC_FULL + c), 1); }
-    for (int c = 0; c < 2; ++c) mbar_init(sy.addr(B_V_READY + c), 128);
-    mbar_init(sy.addr(B_V_FREE), 1);
+    mbar_init(sy.addr(B_F_READY), 128); mbar_init(sy.addr(B_F_FREE), 1);
+    for (int c = 0; c < 4; ++c) { mbar_init(sy.addr(B_A_READY + c), 256); mbar_init(sy.addr(B_A_FREE + c), 1); }
+    mbar_init(sy.addr(B_ACC_FULL + 0), 1); mbar_init(sy.addr(B_ACC_FULL + 1), 1);
+    mbar_init(sy.addr(B_V_READY), 256);
     mbar_init(sy.addr(B_SMALL_FULL), 1); mbar_init(sy.addr(B_SEM2_FULL), 1);
     mbar_init(sy.addr(B_TAIL_DONE), 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -774,8 +733,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   const uint32_t tmem = *tmem_slot;
 
   // "free"-type barriers start released: the first wait must pass on a fresh barrier
-  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_PE_FREE) | (1ull << B_DIR_FREE) |
-                            (0xFull << B_A_FREE) | (1ull << B_V_FREE) | (1ull << B_TAIL_DONE);
+  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (0xFull << B_A_FREE) | (1ull << B_TAIL_DONE);
   sy.phase = released;
 
   if (P.prof != nullptr && blockIdx.x == 0) {
@@ -819,8 +777,12 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   const unsigned char* blob = static_cast<const unsigned char*>(a.packed);
   P.blocks = blob + L.tc_blocks;
   P.bias = reinterpret_cast<const float*>(blob + L.tc_bias);
-  P.n_blocks = prog.n_blocks;
-  for (int i = 0; i < prog.n_blocks; ++i) { P.block_off[i] = prog.blk[i].byte_off; P.block_bytes[i] = prog.blk[i].bytes; }
+  P.n_fills = prog.n_fills;
+  for (int i = 0; i < prog.n_fills; ++i) {
+    P.fill_off[i] = prog.fill_off[i];
+    P.fill_bytes[i] = prog.fill_bytes[i];
+    if (prog.fill_bytes[i] > TC_SLOT_BYTES || (prog.fill_bytes[i] & 31)) { set_error("internal: ring fill %d has %d bytes", i, prog.fill_bytes[i]); return INRF_EINVAL; }
+  }
   P.out_ch = raw_channels(a.n_classes, a.endpoint);
   P.C = a.n_classes;
   P.sem_rows = (a.n_classes + 15) / 16 * 16;
@@ -829,8 +791,6 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   static const bool prof_env = getenv("INRF_TC_PROF") != nullptr && getenv("INRF_TC_PROF")[0] == '1';
   static const bool now_env = getenv("INRF_TC_NOWEIGHTS") != nullptr && getenv("INRF_TC_NOWEIGHTS")[0] == '1';
   P.no_weights = now_env ? 1 : 0;
-  static const int exp_env = getenv("INRF_TC_EXP") ? atoi(getenv("INRF_TC_EXP")) : 0;
-  P.exp_mode = exp_env;
   P.prof = nullptr;
   if (prof_env) {
     long long* pp = nullptr;
@@ -846,14 +806,14 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   int dev = 0, sms = 148;
   INRF_CUDA(cudaGetDevice(&dev));
   INRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static const int cl_env = getenv("INRF_TC_CLUSTER") ? atoi(getenv("INRF_TC_CLUSTER")) : 2;
+  static const int cl_env = getenv("INRF_TC_CLUSTER") ? atoi(getenv("INRF_TC_CLUSTER")) : 1;
   const int64_t tiles = (a.M + tc::TILE_M - 1) / tc::TILE_M;
-  int cl = (cl_env == 4) ? 4 : (cl_env == 1 ? 1 : 2);
+  int cl = (cl_env == 2) ? 2 : 1;
   if (tiles < cl) cl = 1;
   int grid = (int)(tiles < sms ? tiles : sms);
   grid = grid / cl * cl;                       // whole clusters only
   P.n_iter = (int)((tiles + grid - 1) / grid);
-  void (*kern)(tc::Params) = cl == 4 ? tc::k_mlp_tc<4> : (cl == 2 ? tc::k_mlp_tc<2> : tc::k_mlp_tc<1>);
+  void (*kern)(tc::Params) = cl == 2 ? tc::k_mlp_tc<2> : tc::k_mlp_tc<1>;
   INRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -869,20 +829,18 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   cfg.numAttrs = 1;
   INRF_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   if (prof_env) {
-    static const char* bar_names[] = {"WFULL0","WFULL1","WFULL2","WFULL3","WFULL4","WFULL5","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3","WEMPTY4","WEMPTY5",
-      "PE_READY","PE_FREE","DIR_READY","DIR_FREE","A_READY0","A_READY1","A_READY2","A_READY3","A_FREE0","A_FREE1","A_FREE2","A_FREE3",
-      "ACC_FULL0","ACC_FULL1","ACC_FULL2","ACC_FULL3","V_READY0","V_READY1","V_FREE","SMALL_FULL","SEM2_FULL","TAIL_DONE"};
+    static const char* bar_names[] = {"WFULL0","WFULL1","WFULL2","WFULL3","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3","F_READY","F_FREE",
+      "A_READY0","A_READY1","A_READY2","A_READY3","A_FREE0","A_FREE1","A_FREE2","A_FREE3","ACC_FULL0","ACC_FULL1","V_READY",
+      "SMALL_FULL","SEM2_FULL","TAIL_DONE"};
     static const char* roles[] = {"producer", "issuer", "frontend", "epilogue"};
     long long h[4 * 128];
     INRF_CUDA(cudaStreamSynchronize(st));
     INRF_CUDA(cudaMemcpyFromSymbol(h, tc::g_prof, sizeof(h)));
     for (int r = 0; r < 4; ++r) {
       fprintf(stderr, "TCPROF role=%s total_cycles=%lld n_iter=%d\n", roles[r], h[r * 128 + 63], P.n_iter);
-      long long w_full = 0, w_cnt = 0;
-      for (int b = 0; b < 34; ++b) {
+      for (int b = 0; b < tc::B_COUNT; ++b) {
         if (h[r * 128 + 64 + b] == 0) continue;
-        fprintf(stderr, "TCPROF   %-10s waited %12lld cycles over %8lld waits\n", bar_names[b], h[r * 128 + b], h[r * 128 + 64 + b]);
-        (void)w_full; (void)w_cnt;
+        fprintf(stderr, "TCPROF   %-10s waited %12lld cycles over %8lld slow waits\n", bar_names[b], h[r * 128 + b], h[r * 128 + 64 + b]);
       }
     }
   }
