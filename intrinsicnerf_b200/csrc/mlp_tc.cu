@@ -63,8 +63,10 @@ enum {
   B_F_READY = B_WEMPTY + NS,   // PE|DIR tiles of the next tile written (128 front-end threads)
   B_F_FREE,                    // PE|DIR|V region no longer read by the tensor core
   B_A_READY,                   // [4] H chunk c written by all 8 epilogue warps (256 threads)
-  B_A_FREE = B_A_READY + 4,    // [4] H chunk c no longer read by the tensor core
-  B_ACC_FULL = B_A_FREE + 4,   // [2] accumulator (TMEM columns parity*256 ..) complete
+  B_H_FREE = B_A_READY + 4,    // tail only: the tensor core finished reading H (before it is overwritten
+                               // by relu(albedo1|shading1) / relu(sem1)); in the trunk "accumulator
+                               // complete" already implies that every read of H by that layer is done
+  B_ACC_FULL,                  // [2] accumulator (TMEM columns parity*256 ..) complete
   B_V_READY = B_ACC_FULL + 2,  // relu(views') written (256 threads)
   B_SMALL_FULL, B_SEM2_FULL, B_TAIL_DONE,
   B_COUNT
@@ -83,11 +85,13 @@ struct Params {
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
   int* dbg;                       // [16] watchdog record (device)
   long long* prof;                // optional wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
+  long long* trace;               // optional event timestamps (tile iteration 5 of CTA 0)
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
 };
 
 __device__ int g_dbg[16];
-__device__ long long g_prof[4 * 128];   // per role: [0,63) wait cycles per barrier, [63] total, [64,128) wait counts
+__device__ long long g_prof[4 * 128];
+__device__ long long g_trace[512];      // event timestamps of one tile of CTA 0 (INRF_TC_PROF=1)   // per role: [0,63) wait cycles per barrier, [63] total, [64,128) wait counts
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -172,7 +176,36 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
 // barrier bookkeeping with a watchdog: a stuck wait records who/where, raises a global abort
 // flag and lets every role run to the end (garbage out, but no hung GPU and no lost context)
 // ------------------------------------------------------------------------------------------
-struct Sync {
+// out-of-line spin with watchdog; returns true when the wait was abandoned (dead)
+__device__ __noinline__ bool slow_wait_impl(uint32_t bar_addr, uint32_t parity, int id, int tile, int* dbg, long long* prof) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  bool dead = false;
+  while (!mbar_try(bar_addr, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*(volatile int*)dbg != 0) { dead = true; break; }
+      if (clock64() - t0 > 3000000000LL) {
+        if (atomicCAS(dbg, 0, 1) == 0) {
+          dbg[1] = id; dbg[2] = threadIdx.x >> 5; dbg[3] = tile; dbg[4] = blockIdx.x; dbg[5] = (int)parity;
+          __threadfence();
+        }
+        dead = true;
+        break;
+      }
+    }
+  }
+  if (prof) { prof[id] += clock64() - t0; prof[id + 64] += 1; }
+  return dead;
+}
+
+__device__ __forceinline__ uint32_t mbar_test(uint32_t addr, uint32_t parity) {   // non-blocking probe
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok;
+}
+
+struct Sync {             // lives in registers (never escapes by address)
   uint32_t bar0;          // smem address of barrier 0
   uint64_t phase;         // one parity bit per barrier id
   int* dbg;
@@ -180,32 +213,28 @@ struct Sync {
   bool dead;
   int tile;
   __device__ __forceinline__ uint32_t addr(int id) const { return bar0 + 8u * id; }
-  __device__ __noinline__ void slow_wait(int id, uint32_t parity) {
-    const long long t0 = clock64();
-    uint32_t spins = 0;
-    while (!mbar_try(addr(id), parity)) {
-      if ((++spins & 0x3ff) == 0) {
-        if (*(volatile int*)dbg != 0) { dead = true; break; }
-        if (clock64() - t0 > 3000000000LL) {
-          if (atomicCAS(dbg, 0, 1) == 0) {
-            dbg[1] = id; dbg[2] = threadIdx.x >> 5; dbg[3] = tile; dbg[4] = blockIdx.x; dbg[5] = (int)parity;
-            __threadfence();
-          }
-          dead = true;
-          break;
-        }
-      }
-    }
-    if (prof) { prof[id] += clock64() - t0; prof[id + 64] += 1; }
-  }
-  __device__ __forceinline__ void wait(int id) {
+  __device__ __forceinline__ uint32_t take_parity(int id) {       // consume the next phase of barrier id
     const uint32_t parity = (uint32_t)((phase >> id) & 1ull);
     phase ^= (1ull << id);
+    return parity;
+  }
+  __device__ __forceinline__ void slow(int id, uint32_t parity) {
+    if (!dead) dead = slow_wait_impl(addr(id), parity, id, tile, dbg, prof);
+  }
+  __device__ __forceinline__ void wait(int id) {
+    const uint32_t parity = take_parity(id);
     if (dead) return;
     if (mbar_try(addr(id), parity)) return;
-    slow_wait(id, parity);
+    slow(id, parity);
   }
 };
+
+// One arrival per warp: every lane has fenced its own shared-memory writes, the warp converges and
+// lane 0 arrives (a 32-lane arrive on one mbarrier word serialises like a same-address atomic).
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -338,7 +367,7 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
 #pragma unroll
     for (int u = 0; u < 4; ++u) st_shared_v4(smem_base + SM_DIR + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     fence_async_smem();
-    mbar_arrive(sy.addr(B_F_READY));
+    warp_arrive(sy.addr(B_F_READY), row & 31);
   }
 }
 
@@ -383,13 +412,30 @@ struct Issuer {
   int bias_mma;
   int no_weights;
   bool leader;
+  // probe-ahead state: the barriers of the NEXT fill are tested (non-blocking) before the MMAs of
+  // the current fill are issued, so the mbarrier round trip overlaps the issue of tcgen05.mma
+  uint32_t pw_ok, pa_ok, pw_par, pa_par;
+  int pa_bar;             // activation barrier of the probed fill or -1
   __device__ __forceinline__ uint32_t slot_addr() const { return smem_base + SM_RING + slot * TC_SLOT_BYTES; }
   __device__ __forceinline__ void commit(int bar) {
     if (leader) tc_commit(sy.addr(bar));
     __syncwarp();
   }
-  __device__ __forceinline__ void acquire() {        // next ring fill has landed
-    if (!no_weights) sy.wait(B_WFULL + slot);
+  // start probing the fill that will be consumed next (ring slot `slot`), optionally with an activation barrier
+  __device__ __forceinline__ void probe(int act_bar) {
+    pa_bar = act_bar;
+    pw_par = sy.take_parity(B_WFULL + slot);
+    pw_ok = no_weights ? 1u : mbar_test(sy.addr(B_WFULL + slot), pw_par);
+    pa_ok = 1u;
+    if (act_bar >= 0) {
+      pa_par = sy.take_parity(act_bar);
+      pa_ok = mbar_test(sy.addr(act_bar), pa_par);
+    }
+  }
+  // the probed fill is usable (falls back to blocking waits when the probe said "not yet")
+  __device__ __forceinline__ void acquire() {
+    if (!pw_ok) sy.slow(B_WFULL + slot, pw_par);
+    if (!pa_ok) sy.slow(pa_bar, pa_par);
     tc_fence_after();
   }
   __device__ __forceinline__ void release() {        // MMAs reading the slot are done -> refill
@@ -398,14 +444,13 @@ struct Issuer {
       else tc_commit_mc(sy.addr(B_WEMPTY + slot), (uint16_t)((1u << cl) - 1u));
     }
     __syncwarp();
-    slot = (slot + 1 == NS) ? 0 : slot + 1;
   }
-  // K = 16*KSTEPS of A chunk `a_chunk` times the operand tile at byte offset `b_off` of the current
-  // slot -> accumulator columns [col, col+n)
+  __device__ __forceinline__ void advance() { slot = (slot + 1 == NS) ? 0 : slot + 1; }
+  // K = 16*KSTEPS of A chunk `a_chunk` times the operand tile at byte offset `b_off` of slot `sl`
   template <int KSTEPS>
-  __device__ __forceinline__ void mma(uint32_t a_chunk, uint32_t b_off, int n, uint32_t col, bool first) {
+  __device__ __forceinline__ void mma(uint32_t a_chunk, uint32_t b_addr, int n, uint32_t col, bool first) {
     const uint64_t ad = make_desc(a_chunk);
-    const uint64_t bd = make_desc(slot_addr() + b_off);
+    const uint64_t bd = make_desc(b_addr);
     const uint32_t id = make_idesc(n);
     if (leader) {
 #pragma unroll
@@ -414,105 +459,124 @@ struct Issuer {
     }
     __syncwarp();
   }
-  // whole fill = one operand tile
+  // whole fill = one operand tile.  `next_act`: activation barrier of the FOLLOWING fill (-1 none,
+  // -2: do not probe ahead - the caller probes after doing something else)
   template <int KSTEPS>
-  __device__ __forceinline__ void fill_mma(uint32_t a_chunk, int n, uint32_t col, bool first) {
+  __device__ __forceinline__ void fill_mma(uint32_t a_chunk, int n, uint32_t col, bool first, int next_act) {
     acquire();
-    mma<KSTEPS>(a_chunk, 0, n, col, first);
+    mma<KSTEPS>(a_chunk, slot_addr(), n, col, first);    // MMAs first: their issue is on the critical path
     release();
+    advance();
+    if (next_act != -2) probe(next_act);                  // the probe's round trip overlaps MMA execution
   }
-  // accumulator columns [col, col+n) := bias: one K=16 MMA of the constant "ones" tile with the
-  // hi/lo/lo2 bias columns of the fill.  Returns true when the accumulator was initialised.
-  __device__ __forceinline__ bool bias(int n, uint32_t col) {
+  // accumulator columns [col, col+n) := bias (one K=16 MMA of the constant "ones" tile)
+  __device__ __forceinline__ bool bias(int n, uint32_t col, int next_act) {
     acquire();
     if (bias_mma && leader)
       tc_mma(tmem + col, make_desc_flat(smem_base + SM_ONES, 128, 0), make_desc_flat(slot_addr(), 128, 256), make_idesc(n), 0u);
     __syncwarp();
     release();
+    advance();
+    if (next_act != -2) probe(next_act);
     return bias_mma != 0;
   }
 };
 
 __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl) {
-  Issuer I{sy, smem_base, tmem, 0, cl, P.bias_mma, P.no_weights, elect_one()};
+  Issuer I{sy, smem_base, tmem, 0, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
   const bool sem = P.C > 0;
   const int nv = sem ? 256 : 128;       // views' [| sem1] width
+  I.probe(-1);                          // first fill of the first tile (layer-0 bias)
   for (int it = 0; it < P.n_iter; ++it) {
     sy.tile = it;
+    if (sy.prof && it == 5) P.trace[60] = clock64();                        // tile start (issuer)
+    if (sy.prof && it == 6) P.trace[61] = clock64();                        // next tile start
     sy.wait(B_TAIL_DONE);               // previous tile's accumulators drained
     sy.wait(B_F_READY);                 // gamma(x), gamma(d) of this tile
-    tc_fence_after();
     // ---- trunk layer 0: K = 64 (gamma(x)) -> accumulator 0 ---------------------------------------
     {
-      const bool init = I.bias(256, 0);
-      I.fill_mma<4>(PE, 256, 0, !init);
+      const bool init = I.bias(256, 0, -1);
+      I.fill_mma<4>(PE, 256, 0, !init, -1);
       I.commit(B_ACC_FULL + 0);
     }
     // ---- trunk layers 1..7 ------------------------------------------------------------------------
     for (int l = 1; l < 8; ++l) {
       const uint32_t acc = (l & 1) * 256;
-      bool first = !I.bias(256, acc);
+      bool first = !I.bias(256, acc, l == 5 ? -1 : B_A_READY + 0);
       if (l == 5) {                      // skip connection: [gamma(x), h] -> K = 64 + 256
-        I.fill_mma<4>(PE, 256, acc, first);
+        I.fill_mma<4>(PE, 256, acc, first, B_A_READY + 0);
         first = false;
       }
       for (int c = 0; c < 4; ++c) {
-        sy.wait(B_A_READY + c);
-        I.fill_mma<4>(H + c * CHUNK, 256, acc, first);
+        I.fill_mma<4>(H + c * CHUNK, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
         first = false;
-        I.commit(B_A_FREE + c);
+        if (sy.prof && it == 5) P.trace[l * 4 + c] = clock64();             // chunk c of layer l issued
       }
       I.commit(B_ACC_FULL + (l & 1));
     }
-    // ---- albedo1 | shading1 on the trunk output -> accumulator 0 ------------------------------------
+    // ---- views' [| sem1] on the trunk output -> accumulator 0 (drained since layer 6) ---------------
     {
-      bool first = !I.bias(256, 0);
-      for (int c = 0; c < 4; ++c) {
-        sy.wait(B_A_READY + c);          // all four waits also prove layer 7's accumulator (1) is drained
-        I.fill_mma<4>(H + c * CHUNK, 256, 0, first);
+      bool first = !I.bias(nv, 0, B_A_READY + 0);
+      for (int c = 0; c < 4; ++c) {       // all four waits also prove layer 7's accumulator (1) is drained
+        I.fill_mma<4>(H + c * CHUNK, nv, 0, first, c < 3 ? B_A_READY + c + 1 : -1);
         first = false;
       }
+      I.fill_mma<2>(DIR, 128, 0, false, -1);
       I.commit(B_ACC_FULL + 0);
+      if (sy.prof && it == 5) P.trace[40] = clock64();                      // views' issued
     }
-    // ---- views' [| sem1] -> accumulator 1 -----------------------------------------------------------
+    // ---- albedo1 | shading1 on the trunk output -> accumulator 1 ------------------------------------
     {
-      bool first = !I.bias(nv, 256);
+      bool first = !I.bias(256, 256, -1);
       for (int c = 0; c < 4; ++c) {
-        I.fill_mma<4>(H + c * CHUNK, nv, 256, first);
+        I.fill_mma<4>(H + c * CHUNK, 256, 256, first, -1);
         first = false;
-        I.commit(B_A_FREE + c);          // last reader of the trunk output chunk c
       }
-      I.fill_mma<2>(DIR, 128, 256, false);
+      I.commit(B_H_FREE);                // last reader of the trunk output: relu(albedo1|shading1) may land in H
       I.commit(B_ACC_FULL + 1);
     }
-    // ---- residual head on relu(views'): 16 x 128 -> accumulator 1 cols [0,16) ------------------------
+    // ---- residual head on relu(views'): 16 x 128 -> accumulator 0 cols [0,16) ------------------------
     sy.wait(B_V_READY);
-    I.acquire();
-    I.mma<4>(V, 0, 16, 256, true);
-    I.mma<4>(V + CHUNK, 2048, 16, 256, false);
-    I.release();
-    I.commit(B_F_FREE);                  // PE | DIR | V region may be rewritten by the front end
-    // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> accumulator 1 cols [16,32) ------
-    I.acquire();
-    for (int c = 0; c < 4; ++c) {
-      sy.wait(B_A_READY + c);
-      tc_fence_after();
-      I.mma<4>(H + c * CHUNK, 2048 * c, 16, 256 + 16, c == 0);
-      I.commit(B_A_FREE + c);
+    {
+      I.acquire();
+      const uint32_t b_addr = I.slot_addr();
+      I.mma<4>(V, b_addr, 16, 0, true);
+      I.mma<4>(V + CHUNK, b_addr + 2048, 16, 0, false);
+      I.release();
+      I.advance();
+      I.probe(-1);
     }
-    I.release();
+    I.commit(B_F_FREE);                  // PE | DIR | V region may be rewritten by the front end
+    if (sy.prof && it == 5) P.trace[41] = clock64();                        // residual issued
+    // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> accumulator 0 cols [16,32) ------
+    {
+      I.acquire();
+      const uint32_t b_addr = I.slot_addr();
+      for (int c = 0; c < 4; ++c) {
+        sy.wait(B_A_READY + c);
+        tc_fence_after();
+        I.mma<4>(H + c * CHUNK, b_addr + 2048 * c, 16, 16, c == 0);
+      }
+      I.release();
+      I.advance();
+      I.probe(-1);
+    }
+    if (sem) I.commit(B_H_FREE);         // relu(sem1) may overwrite H chunks 0,1
     I.commit(B_SMALL_FULL);
-    // ---- semantic logits on relu(sem1): C x 128 -> accumulator 0 cols [0, sem_rows) -------------------
+    if (sy.prof && it == 5) P.trace[42] = clock64();                        // small heads issued
+    // ---- semantic logits on relu(sem1): C x 128 -> accumulator 1 cols [0, sem_rows) -------------------
     if (sem) {
       I.acquire();
+      const uint32_t b_addr = I.slot_addr();
       for (int c = 0; c < 2; ++c) {
         sy.wait(B_A_READY + c);
         tc_fence_after();
-        I.mma<4>(H + c * CHUNK, (uint32_t)(P.sem_rows * 128 * c), P.sem_rows, 0, c == 0);
-        I.commit(B_A_FREE + c);
+        I.mma<4>(H + c * CHUNK, b_addr + (uint32_t)(P.sem_rows * 128 * c), P.sem_rows, 256, c == 0);
       }
       I.release();
+      I.advance();
+      I.probe(-1);
       I.commit(B_SEM2_FULL);
     }
   }
@@ -562,30 +626,49 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
   }
 }
 
+struct EpiProf {
+  long long cyc[6];     // 0 acc_full wait, 1 tmem ld+wait, 2 math+stores, 3 proxy fence, 4 arrive, 5 other waits
+  bool on;
+  long long* trace;     // where to record chunk completion times of the current layer (or nullptr)
+  __device__ __forceinline__ long long tic() const { return on ? clock64() : 0; }
+  __device__ __forceinline__ void toc(int c, long long t0) { if (on) cyc[c] += clock64() - t0; }
+};
+
 // A 256-column accumulator -> 4 H chunks, two chunks per TMEM load batch.
 // taddr: this thread's lane + accumulator base column; bias: 256 floats (fallback path only).
 __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst0, int n_chunks,
-                                          const RowAddr& ra, int jj, Sync& sy, int free_bar0, int ready_bar0,
-                                          const float* alpha_smem, float* sigma_acc, float* gout0) {
+                                          const RowAddr& ra, int jj, int lane, Sync& sy, int free_bar0, int ready_bar0,
+                                          const float* alpha_smem, float* sigma_acc, float* gout0, EpiProf& ep) {
 #pragma unroll 1
   for (int cp = 0; cp < n_chunks; cp += 2) {
     uint32_t v0[32], v1[32];
+    long long t0 = ep.tic();
     tmem_ld32(taddr + cp * 64 + jj * 32, v0);
     tmem_ld32(taddr + (cp + 1) * 64 + jj * 32, v1);
     tmem_ld_wait();
+    ep.toc(1, t0);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int c = cp + half;
       const int col = c * 64 + jj * 32;
       const uint32_t* v = half == 0 ? v0 : v1;
-      if (free_bar0 >= 0) sy.wait(free_bar0 + c);
+      t0 = ep.tic();
+      if (free_bar0 >= 0 && c == 0) sy.wait(free_bar0);     // one "H free" barrier for the whole layer
+      ep.toc(5, t0);
+      t0 = ep.tic();
       float* g = gout0 ? gout0 + col : nullptr;
       const float* aw = alpha_smem ? alpha_smem + col : nullptr;
       if (add_bias) epi_store32<true>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
       else epi_store32<false>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
+      ep.toc(2, t0);
+      t0 = ep.tic();
       fence_async_smem();
       tc_fence_before();
-      if (ready_bar0 >= 0) mbar_arrive(sy.addr(ready_bar0 + c));
+      ep.toc(3, t0);
+      t0 = ep.tic();
+      if (ready_bar0 >= 0) warp_arrive(sy.addr(ready_bar0 + c), lane);
+      ep.toc(4, t0);
+      if (ep.trace) ep.trace[c] = clock64();
     }
   }
 }
@@ -604,6 +687,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
   RowAddr ra;
 #pragma unroll
   for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
+  EpiProf ep{{0, 0, 0, 0, 0, 0}, sy.prof != nullptr, nullptr};
   for (int it = 0; it < P.n_iter; ++it) {
     const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: stores are masked
     sy.tile = (int)tile;
@@ -613,26 +697,25 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
     float sig = 0.f;
     for (int l = 0; l < 8; ++l) {
-      sy.wait(B_ACC_FULL + (l & 1));
-      tc_fence_after();
-      epi_layer(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, sy, B_A_FREE, B_A_READY,
-                l == 7 ? s_alpha : nullptr, &sig, nullptr);
+      { const long long t0 = ep.tic(); sy.wait(B_ACC_FULL + (l & 1)); tc_fence_after(); ep.toc(0, t0); }
+      if (ep.on && it == 5) { P.trace[100 + l] = clock64(); ep.trace = P.trace + 110 + l * 4; } else ep.trace = nullptr;
+      epi_layer(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY,
+                l == 7 ? s_alpha : nullptr, &sig, nullptr, ep);
     }
+    ep.trace = nullptr;
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
-    // ---- relu(albedo1 | shading1) -> H (in place over the trunk output, chunk by chunk as the
-    //      views' MMAs release it) ------------------------------------------------------------------
-    sy.wait(B_ACC_FULL + 0);
-    tc_fence_after();
-    epi_layer(add_bias, lane_addr + 0, P.bias + TCB_ALBSH, H, 4, ra, jj, sy, B_A_FREE, B_A_READY, nullptr, nullptr, nullptr);
-    // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 1) -------------
-    sy.wait(B_ACC_FULL + 1);
-    tc_fence_after();
-    epi_layer(add_bias, lane_addr + 256, P.bias + TCB_VIEWS, V, 2, ra, jj, sy, -1, -1, nullptr, nullptr,
-              (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C : nullptr);
-    mbar_arrive(sy.addr(B_V_READY));
+    // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
+    //      the tensor core works on albedo1|shading1 ---------------------------------------------------
+    { const long long t0 = ep.tic(); sy.wait(B_ACC_FULL + 0); tc_fence_after(); ep.toc(0, t0); }
+    epi_layer(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
+              (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C : nullptr, ep);
+    warp_arrive(sy.addr(B_V_READY), lane);
+    // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ---------------------------------
+    { const long long t0 = ep.tic(); sy.wait(B_ACC_FULL + 1); tc_fence_after(); ep.toc(0, t0); }
+    epi_layer(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, ep);
     // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
     if (sem)
-      epi_layer(add_bias, lane_addr + 256 + 128, P.bias + TCB_SEM1, H, 2, ra, jj, sy, B_A_FREE, B_A_READY, nullptr, nullptr, nullptr);
+      epi_layer(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, ep);
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
     if (sem) sy.wait(B_SEM2_FULL);
@@ -641,7 +724,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     asm volatile("bar.sync 1, 256;" ::: "memory");     // both sigma partials of every row are in smem
     if (jj == 0) {
       uint32_t v[32];
-      tmem_ld32(lane_addr + 256, v);
+      tmem_ld32(lane_addr + 0, v);
       tmem_ld_wait();
       if (valid) {
         float res[3], alb[3], sh;
@@ -663,7 +746,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     } else if (sem) {
       for (int c0 = 0; c0 < P.C; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(lane_addr + c0, v);
+        tmem_ld32(lane_addr + 256 + c0, v);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -674,8 +757,10 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     }
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");     // s_sig may be rewritten by the next tile
-    mbar_arrive(sy.addr(B_TAIL_DONE));
+    warp_arrive(sy.addr(B_TAIL_DONE), lane);
+    if (ep.on && it == 5) P.trace[150] = clock64();                         // tail done (epilogue warp 0)
   }
+  if (sy.prof) for (int i = 0; i < 6; ++i) sy.prof[40 + i] = ep.cyc[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -702,12 +787,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), CL); }
-    mbar_init(sy.addr(B_F_READY), 128); mbar_init(sy.addr(B_F_FREE), 1);
-    for (int c = 0; c < 4; ++c) { mbar_init(sy.addr(B_A_READY + c), 256); mbar_init(sy.addr(B_A_FREE + c), 1); }
+    mbar_init(sy.addr(B_F_READY), 4); mbar_init(sy.addr(B_F_FREE), 1);
+    for (int c = 0; c < 4; ++c) mbar_init(sy.addr(B_A_READY + c), 8);
+    mbar_init(sy.addr(B_H_FREE), 1);
     mbar_init(sy.addr(B_ACC_FULL + 0), 1); mbar_init(sy.addr(B_ACC_FULL + 1), 1);
-    mbar_init(sy.addr(B_V_READY), 256);
+    mbar_init(sy.addr(B_V_READY), 8);
     mbar_init(sy.addr(B_SMALL_FULL), 1); mbar_init(sy.addr(B_SEM2_FULL), 1);
-    mbar_init(sy.addr(B_TAIL_DONE), 256);
+    mbar_init(sy.addr(B_TAIL_DONE), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
@@ -733,7 +819,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   const uint32_t tmem = *tmem_slot;
 
   // "free"-type barriers start released: the first wait must pass on a fresh barrier
-  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (0xFull << B_A_FREE) | (1ull << B_TAIL_DONE);
+  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (1ull << B_TAIL_DONE);
   sy.phase = released;
 
   if (P.prof != nullptr && blockIdx.x == 0) {
@@ -792,11 +878,16 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   static const bool now_env = getenv("INRF_TC_NOWEIGHTS") != nullptr && getenv("INRF_TC_NOWEIGHTS")[0] == '1';
   P.no_weights = now_env ? 1 : 0;
   P.prof = nullptr;
+  P.trace = nullptr;
   if (prof_env) {
     long long* pp = nullptr;
     INRF_CUDA(cudaGetSymbolAddress((void**)&pp, tc::g_prof));
     INRF_CUDA(cudaMemsetAsync(pp, 0, 4 * 128 * sizeof(long long), st));
     P.prof = pp;
+    long long* tt = nullptr;
+    INRF_CUDA(cudaGetSymbolAddress((void**)&tt, tc::g_trace));
+    INRF_CUDA(cudaMemsetAsync(tt, 0, 512 * sizeof(long long), st));
+    P.trace = tt;
   }
   int* dbg = nullptr;
   INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, tc::g_dbg));
@@ -806,9 +897,9 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   int dev = 0, sms = 148;
   INRF_CUDA(cudaGetDevice(&dev));
   INRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static const int cl_env = getenv("INRF_TC_CLUSTER") ? atoi(getenv("INRF_TC_CLUSTER")) : 1;
+  static const int cl_env = getenv("INRF_TC_CLUSTER") ? atoi(getenv("INRF_TC_CLUSTER")) : 2;
   const int64_t tiles = (a.M + tc::TILE_M - 1) / tc::TILE_M;
-  int cl = (cl_env == 2) ? 2 : 1;
+  int cl = (cl_env == 1) ? 1 : 2;     // default: 2-CTA clusters share every weight fetch (multicast)
   if (tiles < cl) cl = 1;
   int grid = (int)(tiles < sms ? tiles : sms);
   grid = grid / cl * cl;                       // whole clusters only
@@ -830,14 +921,32 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   INRF_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   if (prof_env) {
     static const char* bar_names[] = {"WFULL0","WFULL1","WFULL2","WFULL3","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3","F_READY","F_FREE",
-      "A_READY0","A_READY1","A_READY2","A_READY3","A_FREE0","A_FREE1","A_FREE2","A_FREE3","ACC_FULL0","ACC_FULL1","V_READY",
+      "A_READY0","A_READY1","A_READY2","A_READY3","H_FREE","ACC_FULL0","ACC_FULL1","V_READY",
       "SMALL_FULL","SEM2_FULL","TAIL_DONE"};
     static const char* roles[] = {"producer", "issuer", "frontend", "epilogue"};
     long long h[4 * 128];
     INRF_CUDA(cudaStreamSynchronize(st));
     INRF_CUDA(cudaMemcpyFromSymbol(h, tc::g_prof, sizeof(h)));
+    if (P.n_iter > 6) {
+      long long t[512];
+      INRF_CUDA(cudaMemcpyFromSymbol(t, tc::g_trace, sizeof(t)));
+      const long long t0 = t[60];
+      fprintf(stderr, "TCTRACE tile start 0, next tile start %lld\n", t[61] - t0);
+      for (int l = 1; l < 8; ++l)
+        fprintf(stderr, "TCTRACE L%d issued chunks at %6lld %6lld %6lld %6lld | acc_full seen %6lld | epilogue chunks done %6lld %6lld %6lld %6lld\n", l,
+                t[l * 4] - t0, t[l * 4 + 1] - t0, t[l * 4 + 2] - t0, t[l * 4 + 3] - t0, t[100 + l] - t0,
+                t[110 + l * 4] - t0, t[110 + l * 4 + 1] - t0, t[110 + l * 4 + 2] - t0, t[110 + l * 4 + 3] - t0);
+      fprintf(stderr, "TCTRACE L0 acc_full seen %lld, epilogue chunks %lld %lld %lld %lld\n", t[100] - t0, t[110] - t0, t[111] - t0, t[112] - t0, t[113] - t0);
+      fprintf(stderr, "TCTRACE views' issued %lld | residual issued %lld | small heads issued %lld | tail done %lld\n", t[40] - t0, t[41] - t0, t[42] - t0, t[150] - t0);
+    }
     for (int r = 0; r < 4; ++r) {
       fprintf(stderr, "TCPROF role=%s total_cycles=%lld n_iter=%d\n", roles[r], h[r * 128 + 63], P.n_iter);
+      if (r == 3) fprintf(stderr, "TCPROF   epilogue (warp 0) cycles/tile: acc_full waits %lld | tmem ld+wait %lld | math+stores %lld | proxy fence %lld | arrive %lld | h_free waits %lld\n",
+                          h[r * 128 + 40] / P.n_iter, h[r * 128 + 41] / P.n_iter, h[r * 128 + 42] / P.n_iter, h[r * 128 + 43] / P.n_iter,
+                          h[r * 128 + 44] / P.n_iter, h[r * 128 + 45] / P.n_iter);
+      if (r == 1) fprintf(stderr, "TCPROF   issuer cycles/tile: fill waits %lld | mma issue %lld | commits %lld | activation waits %lld | first-chunk waits %lld | tile boundary %lld\n",
+                          h[r * 128 + 40] / P.n_iter, h[r * 128 + 41] / P.n_iter, h[r * 128 + 42] / P.n_iter, h[r * 128 + 43] / P.n_iter,
+                          h[r * 128 + 44] / P.n_iter, h[r * 128 + 45] / P.n_iter);
       for (int b = 0; b < tc::B_COUNT; ++b) {
         if (h[r * 128 + 64 + b] == 0) continue;
         fprintf(stderr, "TCPROF   %-10s waited %12lld cycles over %8lld slow waits\n", bar_names[b], h[r * 128 + b], h[r * 128 + 64 + b]);

@@ -97,14 +97,14 @@ int make_tc_program(int variant, int n_classes, TcProgram* p) {
     for (int c = 0; c < 4; ++c)
       FILL(push(p, L_T0 + l, 128, 0, base + 64 * c, 64, 0); push(p, L_T0 + l, 128, 128, base + 64 * c, 64, 0));
   }
-  // albedo1 | shading1: one 256-wide GEMM on the trunk output
-  FILL(push_bias(p, L_ALB1, 0); push_bias(p, L_SH1, 0));
-  for (int c = 0; c < 4; ++c) FILL(push(p, L_ALB1, 128, 0, 64 * c, 64, 0); push(p, L_SH1, 128, 0, 64 * c, 64, 0));
   // views' (composed with feature_linear) [| semantic hidden layer]: N = 128 [256], K = 256, then
   // the 27 direction-encoding columns (K = 32) for the views' rows only
   FILL(push_bias(p, -1, 0); if (sem) push_bias(p, L_SEM1, 0));
   for (int c = 0; c < 4; ++c) FILL(push(p, -1, 128, 0, 64 * c, 64, 1); if (sem) push(p, L_SEM1, 128, 0, 64 * c, 64, 0));
   FILL(push(p, L_VIEWS, 128, 0, W_HID, PE_DIR, 0));
+  // albedo1 | shading1: one 256-wide GEMM on the trunk output
+  FILL(push_bias(p, L_ALB1, 0); push_bias(p, L_SH1, 0));
+  for (int c = 0; c < 4; ++c) FILL(push(p, L_ALB1, 128, 0, 64 * c, 64, 0); push(p, L_SH1, 128, 0, 64 * c, 64, 0));
   // residual head on relu(views'):  16 x 128 (two K chunks in one fill)
   FILL(for (int c = 0; c < 2; ++c) push(p, L_RES, 16, 0, 64 * c, 64, 0));
   // albedo2 (rows 0..2, K 0..127) + shading2 (row 3, K 128..255): block-diagonal 16 x 256

@@ -125,9 +125,11 @@ def test_ssr_renderer_golden(dev, golden_dir, precision):
             assert e < TOL, (k, lvl, e)
     assert rel_err(ev["z_std"], g["eval_z_std"]) < TOL
     assert ev["raw_coarse"].shape == (rays.shape[0], 64, 11 + C) and ev["raw_fine"].shape == (rays.shape[0], 192, 11 + C)
-    # endpoint features are ReLU outputs (many exactly or nearly zero): error relative to the map's scale
+    # endpoint features are raw ReLU hidden activations (many exactly or nearly zero), not rendered
+    # quantities: their error is taken relative to the map's scale; fp16-operand rounding of a
+    # 256-term dot product leaves ~2e-4 of that scale on the tensor-core path
     feat = g["ep_feat_map_fine"]
-    assert rel_err(ep["feat_map_fine"], feat, floor=float(np.abs(feat).max())) < TOL
+    assert rel_err(ep["feat_map_fine"], feat, floor=float(np.abs(feat).max())) < (TOL if precision == "fp32" else 1e-3)
     assert ep["raw_fine"].shape[-1] == 11 + C + 128
 
 

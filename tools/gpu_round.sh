@@ -12,4 +12,5 @@ unset INRF_TC_CHECK
 if grep -q "TC_DEBUG PASS" gpurun_out/tc_debug.log; then
   timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 fi
+bash tools/gpu_profile.sh > gpurun_out/profile.log 2>&1
 tail -n 4 gpurun_out/tc_debug.log; tail -n 15 gpurun_out/pytest_stages.log; tail -n 30 gpurun_out/pytest_render.log; cat gpurun_out/bench.json 2>/dev/null; tail -5 gpurun_out/bench.err 2>/dev/null
