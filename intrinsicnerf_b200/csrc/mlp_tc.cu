@@ -85,13 +85,11 @@ struct Params {
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
   int* dbg;                       // [16] watchdog record (device)
   long long* prof;                // optional wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
-  long long* trace;               // optional event timestamps (tile iteration 5 of CTA 0)
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
 };
 
 __device__ int g_dbg[16];
 __device__ long long g_prof[4 * 128];
-__device__ long long g_trace[512];      // event timestamps of one tile of CTA 0 (INRF_TC_PROF=1)   // per role: [0,63) wait cycles per barrier, [63] total, [64,128) wait counts
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -490,8 +488,6 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
   I.probe(-1);                          // first fill of the first tile (layer-0 bias)
   for (int it = 0; it < P.n_iter; ++it) {
     sy.tile = it;
-    if (sy.prof && it == 5) P.trace[60] = clock64();                        // tile start (issuer)
-    if (sy.prof && it == 6) P.trace[61] = clock64();                        // next tile start
     sy.wait(B_TAIL_DONE);               // previous tile's accumulators drained
     sy.wait(B_F_READY);                 // gamma(x), gamma(d) of this tile
     // ---- trunk layer 0: K = 64 (gamma(x)) -> accumulator 0 ---------------------------------------
@@ -511,7 +507,6 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
       for (int c = 0; c < 4; ++c) {
         I.fill_mma<4>(H + c * CHUNK, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
         first = false;
-        if (sy.prof && it == 5) P.trace[l * 4 + c] = clock64();             // chunk c of layer l issued
       }
       I.commit(B_ACC_FULL + (l & 1));
     }
@@ -524,7 +519,6 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
       }
       I.fill_mma<2>(DIR, 128, 0, false, -1);
       I.commit(B_ACC_FULL + 0);
-      if (sy.prof && it == 5) P.trace[40] = clock64();                      // views' issued
     }
     // ---- albedo1 | shading1 on the trunk output -> accumulator 1 ------------------------------------
     {
@@ -548,7 +542,6 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
       I.probe(-1);
     }
     I.commit(B_F_FREE);                  // PE | DIR | V region may be rewritten by the front end
-    if (sy.prof && it == 5) P.trace[41] = clock64();                        // residual issued
     // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> accumulator 0 cols [16,32) ------
     {
       I.acquire();
@@ -564,7 +557,6 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
     }
     if (sem) I.commit(B_H_FREE);         // relu(sem1) may overwrite H chunks 0,1
     I.commit(B_SMALL_FULL);
-    if (sy.prof && it == 5) P.trace[42] = clock64();                        // small heads issued
     // ---- semantic logits on relu(sem1): C x 128 -> accumulator 1 cols [0, sem_rows) -------------------
     if (sem) {
       I.acquire();
@@ -587,7 +579,7 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
 // K chunk it owns columns jj*32..jj*32+31, so all 8 warps finish chunk 0 first, then 1, 2, 3.
 // ------------------------------------------------------------------------------------------
 // 32 accumulator columns -> (+bias) -> ReLU -> fp16 -> 4 swizzled 16-byte stores
-template <bool ADD_BIAS>
+template <bool ADD_BIAS, bool SIGMA, bool GOUT>
 __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __restrict__ bias, uint32_t dst_chunk,
                                             const RowAddr& ra, int unit0, const float* alpha_w_smem, float* sigma_acc,
                                             float* gout) {
@@ -601,7 +593,7 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
       f[4 * i] += t.x; f[4 * i + 1] += t.y; f[4 * i + 2] += t.z; f[4 * i + 3] += t.w;
     }
   }
-  if (alpha_w_smem != nullptr) {              // sigma head: fp32 dot on the un-rounded ReLU output
+  if (SIGMA) {                                // sigma head: fp32 dot on the un-rounded ReLU output
     float s = *sigma_acc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -613,7 +605,7 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
     }
     *sigma_acc = s;
   }
-  if (gout != nullptr) {                      // endpoint feature rows (fp32, post-ReLU)
+  if (GOUT && gout != nullptr) {              // endpoint feature rows (fp32, post-ReLU)
 #pragma unroll
     for (int i = 0; i < 32; ++i) gout[i] = fmaxf(f[i], 0.f);
   }
@@ -626,49 +618,32 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
   }
 }
 
-struct EpiProf {
-  long long cyc[6];     // 0 acc_full wait, 1 tmem ld+wait, 2 math+stores, 3 proxy fence, 4 arrive, 5 other waits
-  bool on;
-  long long* trace;     // where to record chunk completion times of the current layer (or nullptr)
-  __device__ __forceinline__ long long tic() const { return on ? clock64() : 0; }
-  __device__ __forceinline__ void toc(int c, long long t0) { if (on) cyc[c] += clock64() - t0; }
-};
-
 // A 256-column accumulator -> 4 H chunks, two chunks per TMEM load batch.
 // taddr: this thread's lane + accumulator base column; bias: 256 floats (fallback path only).
+// MODE 0: plain layer, 1: also accumulate the sigma head (trunk layer 7), 2: also emit fp32 rows (endpoint)
+template <int MODE>
 __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst0, int n_chunks,
                                           const RowAddr& ra, int jj, int lane, Sync& sy, int free_bar0, int ready_bar0,
-                                          const float* alpha_smem, float* sigma_acc, float* gout0, EpiProf& ep) {
+                                          const float* alpha_smem, float* sigma_acc, float* gout0) {
 #pragma unroll 1
   for (int cp = 0; cp < n_chunks; cp += 2) {
     uint32_t v0[32], v1[32];
-    long long t0 = ep.tic();
     tmem_ld32(taddr + cp * 64 + jj * 32, v0);
     tmem_ld32(taddr + (cp + 1) * 64 + jj * 32, v1);
     tmem_ld_wait();
-    ep.toc(1, t0);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int c = cp + half;
       const int col = c * 64 + jj * 32;
       const uint32_t* v = half == 0 ? v0 : v1;
-      t0 = ep.tic();
       if (free_bar0 >= 0 && c == 0) sy.wait(free_bar0);     // one "H free" barrier for the whole layer
-      ep.toc(5, t0);
-      t0 = ep.tic();
-      float* g = gout0 ? gout0 + col : nullptr;
-      const float* aw = alpha_smem ? alpha_smem + col : nullptr;
-      if (add_bias) epi_store32<true>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
-      else epi_store32<false>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
-      ep.toc(2, t0);
-      t0 = ep.tic();
+      float* g = (MODE == 2 && gout0) ? gout0 + col : nullptr;
+      const float* aw = (MODE == 1) ? alpha_smem + col : nullptr;
+      if (add_bias) epi_store32<true, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
+      else epi_store32<false, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
       fence_async_smem();
       tc_fence_before();
-      ep.toc(3, t0);
-      t0 = ep.tic();
       if (ready_bar0 >= 0) warp_arrive(sy.addr(ready_bar0 + c), lane);
-      ep.toc(4, t0);
-      if (ep.trace) ep.trace[c] = clock64();
     }
   }
 }
@@ -687,7 +662,6 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
   RowAddr ra;
 #pragma unroll
   for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
-  EpiProf ep{{0, 0, 0, 0, 0, 0}, sy.prof != nullptr, nullptr};
   for (int it = 0; it < P.n_iter; ++it) {
     const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: stores are masked
     sy.tile = (int)tile;
@@ -697,25 +671,29 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
     float sig = 0.f;
     for (int l = 0; l < 8; ++l) {
-      { const long long t0 = ep.tic(); sy.wait(B_ACC_FULL + (l & 1)); tc_fence_after(); ep.toc(0, t0); }
-      if (ep.on && it == 5) { P.trace[100 + l] = clock64(); ep.trace = P.trace + 110 + l * 4; } else ep.trace = nullptr;
-      epi_layer(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY,
-                l == 7 ? s_alpha : nullptr, &sig, nullptr, ep);
+      sy.wait(B_ACC_FULL + (l & 1));
+      tc_fence_after();
+      if (l == 7) epi_layer<1>(add_bias, lane_addr + 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr);
+      else epi_layer<0>(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr);
     }
-    ep.trace = nullptr;
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
     //      the tensor core works on albedo1|shading1 ---------------------------------------------------
-    { const long long t0 = ep.tic(); sy.wait(B_ACC_FULL + 0); tc_fence_after(); ep.toc(0, t0); }
-    epi_layer(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
-              (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C : nullptr, ep);
+    sy.wait(B_ACC_FULL + 0);
+      tc_fence_after();
+    if (P.a.endpoint)
+      epi_layer<2>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
+                   valid ? grow + INRF_RAW_BASE + P.C : nullptr);
+    else
+      epi_layer<0>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr);
     warp_arrive(sy.addr(B_V_READY), lane);
     // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ---------------------------------
-    { const long long t0 = ep.tic(); sy.wait(B_ACC_FULL + 1); tc_fence_after(); ep.toc(0, t0); }
-    epi_layer(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, ep);
+    sy.wait(B_ACC_FULL + 1);
+      tc_fence_after();
+    epi_layer<0>(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr);
     // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
     if (sem)
-      epi_layer(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, ep);
+      epi_layer<0>(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr);
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
     if (sem) sy.wait(B_SEM2_FULL);
@@ -758,9 +736,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");     // s_sig may be rewritten by the next tile
     warp_arrive(sy.addr(B_TAIL_DONE), lane);
-    if (ep.on && it == 5) P.trace[150] = clock64();                         // tail done (epilogue warp 0)
   }
-  if (sy.prof) for (int i = 0; i < 6; ++i) sy.prof[40 + i] = ep.cyc[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -878,16 +854,11 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   static const bool now_env = getenv("INRF_TC_NOWEIGHTS") != nullptr && getenv("INRF_TC_NOWEIGHTS")[0] == '1';
   P.no_weights = now_env ? 1 : 0;
   P.prof = nullptr;
-  P.trace = nullptr;
   if (prof_env) {
     long long* pp = nullptr;
     INRF_CUDA(cudaGetSymbolAddress((void**)&pp, tc::g_prof));
     INRF_CUDA(cudaMemsetAsync(pp, 0, 4 * 128 * sizeof(long long), st));
     P.prof = pp;
-    long long* tt = nullptr;
-    INRF_CUDA(cudaGetSymbolAddress((void**)&tt, tc::g_trace));
-    INRF_CUDA(cudaMemsetAsync(tt, 0, 512 * sizeof(long long), st));
-    P.trace = tt;
   }
   int* dbg = nullptr;
   INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, tc::g_dbg));
@@ -927,26 +898,8 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
     long long h[4 * 128];
     INRF_CUDA(cudaStreamSynchronize(st));
     INRF_CUDA(cudaMemcpyFromSymbol(h, tc::g_prof, sizeof(h)));
-    if (P.n_iter > 6) {
-      long long t[512];
-      INRF_CUDA(cudaMemcpyFromSymbol(t, tc::g_trace, sizeof(t)));
-      const long long t0 = t[60];
-      fprintf(stderr, "TCTRACE tile start 0, next tile start %lld\n", t[61] - t0);
-      for (int l = 1; l < 8; ++l)
-        fprintf(stderr, "TCTRACE L%d issued chunks at %6lld %6lld %6lld %6lld | acc_full seen %6lld | epilogue chunks done %6lld %6lld %6lld %6lld\n", l,
-                t[l * 4] - t0, t[l * 4 + 1] - t0, t[l * 4 + 2] - t0, t[l * 4 + 3] - t0, t[100 + l] - t0,
-                t[110 + l * 4] - t0, t[110 + l * 4 + 1] - t0, t[110 + l * 4 + 2] - t0, t[110 + l * 4 + 3] - t0);
-      fprintf(stderr, "TCTRACE L0 acc_full seen %lld, epilogue chunks %lld %lld %lld %lld\n", t[100] - t0, t[110] - t0, t[111] - t0, t[112] - t0, t[113] - t0);
-      fprintf(stderr, "TCTRACE views' issued %lld | residual issued %lld | small heads issued %lld | tail done %lld\n", t[40] - t0, t[41] - t0, t[42] - t0, t[150] - t0);
-    }
     for (int r = 0; r < 4; ++r) {
       fprintf(stderr, "TCPROF role=%s total_cycles=%lld n_iter=%d\n", roles[r], h[r * 128 + 63], P.n_iter);
-      if (r == 3) fprintf(stderr, "TCPROF   epilogue (warp 0) cycles/tile: acc_full waits %lld | tmem ld+wait %lld | math+stores %lld | proxy fence %lld | arrive %lld | h_free waits %lld\n",
-                          h[r * 128 + 40] / P.n_iter, h[r * 128 + 41] / P.n_iter, h[r * 128 + 42] / P.n_iter, h[r * 128 + 43] / P.n_iter,
-                          h[r * 128 + 44] / P.n_iter, h[r * 128 + 45] / P.n_iter);
-      if (r == 1) fprintf(stderr, "TCPROF   issuer cycles/tile: fill waits %lld | mma issue %lld | commits %lld | activation waits %lld | first-chunk waits %lld | tile boundary %lld\n",
-                          h[r * 128 + 40] / P.n_iter, h[r * 128 + 41] / P.n_iter, h[r * 128 + 42] / P.n_iter, h[r * 128 + 43] / P.n_iter,
-                          h[r * 128 + 44] / P.n_iter, h[r * 128 + 45] / P.n_iter);
       for (int b = 0; b < tc::B_COUNT; ++b) {
         if (h[r * 128 + 64 + b] == 0) continue;
         fprintf(stderr, "TCPROF   %-10s waited %12lld cycles over %8lld slow waits\n", bar_names[b], h[r * 128 + b], h[r * 128 + 64 + b]);
