@@ -141,6 +141,13 @@ int inrf_merge_sorted(const float* z_a, const float* z_b, int64_t N, int Sa, int
 int inrf_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S,
                   int lindisp, float* z, void* stream);
 
+/* Pinhole ray generation + packing of render() for a full image (run_nerf_helpers.py:359-368
+ * get_rays, run_nerf.py:100-128 with use_viewdirs=True, ndc=False): pixel (i=column, j=row) ->
+ * dir = ((i-cx)/fx, -(j-cy)/fy, -1), d = R dir, o = t, viewdir = d/|d|.
+ * c2w[12] is the row-major 3x4 camera-to-world matrix (HOST pointer), rays[H*W,11] device.      */
+int inrf_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w_host,
+                  float near, float far, float* rays, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Fused renderer: render_rays (run_nerf.py:415-528) / SSRTrainer.volumetric_rendering
  * (SSR/training/trainer.py:717-808) for one chunk of rays.

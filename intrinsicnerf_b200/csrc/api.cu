@@ -12,6 +12,7 @@ int launch_sample_pdf(const float* bins, const float* weights, int ld_w, const f
                       const float* u_det, int64_t N, int B, int n_samples, float* samples, int64_t* inds, float* cdf_out, cudaStream_t st);
 int launch_merge_sorted(const float* za, const float* zb, int64_t N, int Sa, int Sb, float* zout, float* zstd, cudaStream_t st);
 int launch_zmid(const float* z, int64_t N, int S, float* zmid, cudaStream_t st);
+int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, float nearv, float farv, float* rays, cudaStream_t st);
 
 static int run_mlp(const MlpArgs& a, int precision, cudaStream_t st) {
   if (precision == INRF_PREC_FP32) return launch_mlp_fp32(a, st);
@@ -149,6 +150,13 @@ int inrf_merge_sorted(const float* z_a, const float* z_b, int64_t N, int Sa, int
 int inrf_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S, int lindisp, float* z, void* stream) {
   INRF_CHECK_ARG(N >= 0 && S > 0 && (N == 0 || (rays && t_vals && z)), "null pointer / bad size");
   return launch_coarse_z(rays, t_vals, t_rand, N, S, lindisp, z, (cudaStream_t)stream);
+}
+
+int inrf_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w_host, float near, float far,
+                  float* rays, void* stream) {
+  INRF_CHECK_ARG(H > 0 && W > 0 && c2w_host && rays, "null pointer / bad size");
+  INRF_CHECK_ARG(fx != 0.f && fy != 0.f, "zero focal length");
+  return launch_get_rays(H, W, fx, fy, cx, cy, c2w_host, near, far, rays, (cudaStream_t)stream);
 }
 
 int64_t inrf_render_workspace_bytes(const InrfRenderCfg* cfg, int64_t N) {

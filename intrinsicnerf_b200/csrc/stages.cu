@@ -306,6 +306,28 @@ __global__ void k_zmid(const float* __restrict__ z, int64_t N, int S, float* __r
   }
 }
 
+// get_rays + render()'s ray packing for a full image (run_nerf_helpers.py:359-368, run_nerf.py:100-128)
+struct Cam { float fx, fy, cx, cy, m[12], nearv, farv; };
+__global__ void k_get_rays(int H, int W, Cam c, float* __restrict__ rays) {
+  const int64_t total = (int64_t)H * W;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(p / W), i = (int)(p - (int64_t)j * W);
+    const float dx = __fdiv_rn(__fsub_rn((float)i, c.cx), c.fx);
+    const float dy = -__fdiv_rn(__fsub_rn((float)j, c.cy), c.fy);
+    const float dz = -1.f;
+    float d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)      // torch.sum(dirs[..., None, :] * c2w[:3, :3], -1): ((x*m0 + y*m1) + z*m2)
+      d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.m[4 * r]), __fmul_rn(dy, c.m[4 * r + 1])), __fmul_rn(dz, c.m[4 * r + 2]));
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    float* o = rays + p * 11;
+    o[0] = c.m[3]; o[1] = c.m[7]; o[2] = c.m[11];
+    o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
+    o[6] = c.nearv; o[7] = c.farv;
+    o[8] = __fdiv_rn(d[0], nrm); o[9] = __fdiv_rn(d[1], nrm); o[10] = __fdiv_rn(d[2], nrm);
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
@@ -314,6 +336,16 @@ static inline int grid_for(int64_t total, int block, int cap = 148 * 16) {
   if (g < 1) g = 1;
   if (g > cap) g = cap;
   return (int)g;
+}
+
+int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, float nearv, float farv,
+                    float* rays, cudaStream_t st) {
+  Cam c;
+  c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy; c.nearv = nearv; c.farv = farv;
+  for (int i = 0; i < 12; ++i) c.m[i] = c2w[i];
+  k_get_rays<<<grid_for((int64_t)H * W, 256), 256, 0, st>>>(H, W, c, rays);
+  INRF_LAUNCH_CHECK();
+  return INRF_OK;
 }
 
 int launch_zmid(const float* z, int64_t N, int S, float* zmid, cudaStream_t st) {

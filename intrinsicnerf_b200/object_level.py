@@ -223,6 +223,17 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
     """-> [rgb_map, disp_map, acc_map, albedo_map, shading_map, residual_map, extras_dict]."""
+    if c2w is not None and use_viewdirs and not ndc and c2w_staticcam is None and not torch.is_tensor(near) \
+            and not torch.is_tensor(far):
+        # full-image fast path: rays are generated and packed on the device by one kernel
+        net = kwargs.get("network_fn")
+        dev = next(net.parameters()).device if isinstance(net, torch.nn.Module) else torch.device("cuda")
+        packed = ops.get_rays_packed(H, W, K, c2w, near, far, dev)
+        all_ret = batchify_rays(packed, chunk, **kwargs)
+        for k in all_ret:
+            all_ret[k] = torch.reshape(all_ret[k], [H, W] + list(all_ret[k].shape[1:]))
+        main = ["rgb_map", "disp_map", "acc_map", "albedo_map", "shading_map", "residual_map"]
+        return [all_ret[k] for k in main] + [{k: v for k, v in all_ret.items() if k not in main}]
     if c2w is not None:
         rays_o, rays_d = get_rays(H, W, K, c2w)
     else:

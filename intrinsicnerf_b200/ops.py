@@ -181,6 +181,17 @@ def coarse_z(rays, n_samples, lindisp=False, t_rand=None):
     return z
 
 
+def get_rays_packed(H, W, K, c2w, near, far, device):
+    """Full-image ray records [H*W, 11] (get_rays + render()'s packing, use_viewdirs=True, ndc=False)."""
+    m = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].contiguous()
+    arr = (C.c_float * 12)(*[float(v) for v in m.reshape(-1).tolist()])
+    rays = torch.empty(H * W, 11, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(_lib.lib().inrf_get_rays(int(H), int(W), float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), arr,
+                                       float(near), float(far), _ptr(rays), _stream()))
+    return rays
+
+
 class _Workspace:
     """Grow-only scratch buffer per device (the library allocates nothing itself)."""
     bufs = {}

@@ -153,3 +153,39 @@ def test_merge_sorted_exact(dev):
     from intrinsicnerf_b200._lib import InrfError
     with pytest.raises(InrfError):
         ops.merge_sorted(torch.zeros(2, 1000, device=dev), torch.zeros(2, 100, device=dev))
+
+
+def test_get_rays_bitexact(dev):
+    """inrf_get_rays == get_rays + render()'s packing (run_nerf_helpers.py:359-368, run_nerf.py:100-128)."""
+    from intrinsicnerf_b200 import ops
+    for (H, W, theta) in ((7, 5, -180.0), (33, 40, 57.0)):
+        K = orc.blender_intrinsics(H, W)
+        c2w = orc.pose_spherical(theta, -30.0, 4.0)[:3, :4]
+        want = orc.blender_rays(H, W, theta=theta)
+        got = ops.get_rays_packed(H, W, K, c2w, 2.0, 6.0, dev).cpu()
+        assert got.shape == want.shape
+        assert torch.equal(got[:, :8], want[:, :8])
+        assert (got[:, 8:] - want[:, 8:]).abs().max() <= 6e-8          # viewdir = d/|d|: norm summation order
+
+
+def test_full_frame_properties(dev):
+    """Size-independent properties at BASELINE's full size (800x800, 64+128): merged depths are
+    sorted and inside [near, far], accumulated opacity in [0,1], compositing weights sum to acc,
+    chunking does not change a single bit, NaNs only where acc == 0."""
+    from intrinsicnerf_b200 import ops
+    from tests.util import build_nets, rec_get
+    coarse, fine, _, _ = build_nets("object")
+    K = orc.blender_intrinsics(800, 800)
+    rays = ops.get_rays_packed(800, 800, K, orc.pose_spherical(30.0, -30.0, 4.0)[:3, :4], 2.0, 6.0, dev)
+    assert rays.shape == (640000, 11)
+    a = ops.render_chunk(rays[:200000], coarse.packed(), fine.packed(), white_bkgd=True, want_z=True, want_weights=True)
+    z = a["z_fine"]
+    assert bool((z[:, 1:] >= z[:, :-1]).all()) and float(z.min()) >= 2.0 - 1e-5 and float(z.max()) <= 6.0 + 1e-5
+    acc = rec_get(a["rec_fine"], "acc")
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
+    assert float((a["weights_fine"].sum(-1) - acc).abs().max()) < 1e-5
+    disp = rec_get(a["rec_fine"], "disp")
+    assert bool((torch.isnan(disp) == (acc == 0)).all())
+    b = ops.render_chunk(rays[:200000][77777:123457], coarse.packed(), fine.packed(), white_bkgd=True)
+    assert torch.equal(b["rec_fine"], a["rec_fine"][77777:123457])     # bit-identical under re-chunking
+    assert torch.equal(b["rec_coarse"], a["rec_coarse"][77777:123457])
