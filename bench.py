@@ -78,11 +78,21 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
-def synthetic_rays(rank):
-    """[H*W, 11] rays of a Blender-style view (pose_spherical(theta_rank, -30, 4), near 2, far 6)."""
-    from oracle import nerf_oracle as orc                       # ray generator only (host side input synthesis)
-    theta = -180.0 + 360.0 * (rank % 100) / 100.0
-    return orc.blender_rays(H, W, theta=theta)
+def synthetic_rays(rank, device):
+    """[H*W, 11] rays of a Blender-style view: pose_spherical(theta_rank, -30, 4) (load_blender.py:29-34),
+    camera_angle_x of the 'chair' scene, near 2, far 6 - generated on the device by inrf_get_rays."""
+    from intrinsicnerf_b200 import ops
+    theta = math.radians(-180.0 + 360.0 * (rank % 100) / 100.0)
+    phi = math.radians(-30.0)
+    ct, st, cp, sp = math.cos(theta), math.sin(theta), math.cos(phi), math.sin(phi)
+    trans = torch.tensor([[1., 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 4.0], [0, 0, 0, 1]])
+    rphi = torch.tensor([[1., 0, 0, 0], [0, cp, -sp, 0], [0, sp, cp, 0], [0, 0, 0, 1]])
+    rth = torch.tensor([[ct, 0, -st, 0], [0, 1., 0, 0], [st, 0, ct, 0], [0, 0, 0, 1]])
+    flip = torch.tensor([[-1., 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])
+    c2w = (flip @ rth @ rphi @ trans)[:3, :4]
+    f = 0.5 * W / math.tan(0.5 * 0.6911112070083618)
+    K = [[f, 0.0, 0.5 * W], [0.0, f, 0.5 * H], [0.0, 0.0, 1.0]]
+    return ops.get_rays_packed(H, W, K, c2w, 2.0, 6.0, device)
 
 
 def cpu_baseline(n_rays=2048, seconds_cap=40.0):
@@ -180,8 +190,8 @@ def main():
     embeddirs_fn, _ = ol.get_embedder(4, 0)
     kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=ol._FusedQuery(embed_fn, embeddirs_fn, 65536),
               N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=0., white_bkgd=True, raw_noise_std=0.)
-    rays_host = synthetic_rays(rank).pin_memory()
-    rays_dev = rays_host.to(dev)
+    rays_dev = synthetic_rays(rank, dev)
+    rays_host = rays_dev.cpu().pin_memory()
     n_rays = rays_dev.shape[0]
     pc, pf = coarse.packed(), fine.packed()
     chunks = [(i, min(i + args.chunk, n_rays)) for i in range(0, n_rays, args.chunk)]

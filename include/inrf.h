@@ -115,6 +115,15 @@ int inrf_raw2outputs(const float* raw, const float* z, const float* rays_d, int 
                      const float* noise, int64_t N, int S, int n_classes, int endpoint_feat,
                      int white_bkgd, float* rec, float* weights, void* stream);
 
+/* Backward of raw2outputs: given the forward inputs and dL/d(rec) [N, rec_ch] (and optionally
+ * dL/d(weights) [N,S]), writes dL/d(raw) [N,S,ch].  z, rays_d and noise receive no gradient (the
+ * reference never differentiates them: z_samples is detached, run_nerf.py:501).  S <= 256.
+ * The disparity output contributes through d(1/max(1e-10, depth/acc)).                           */
+int inrf_raw2outputs_bwd(const float* raw, const float* z, const float* rays_d, int ld_rays_d,
+                         const float* noise, int64_t N, int S, int n_classes, int endpoint_feat,
+                         int white_bkgd, const float* grad_rec, const float* grad_weights,
+                         float* grad_raw, void* stream);
+
 /* sample_pdf (run_nerf_helpers.py:402-445; SSR/models/rays.py:176-220).
  * bins[N,B], weights given with row stride ld_w and B-1 used entries per row
  * (pass weights_coarse+1 with ld_w=S to express weights[...,1:-1]).

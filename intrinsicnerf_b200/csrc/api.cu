@@ -8,6 +8,9 @@ int launch_embed(const float* x, int64_t M, int L, float scale, float* out, cuda
 int launch_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S, int lindisp, float* z, cudaStream_t st);
 int launch_raw2outputs(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise, int64_t N,
                        int S, int n_classes, int endpoint, int white_bkgd, float* rec, float* weights, cudaStream_t st);
+int launch_raw2outputs_bwd(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise, int64_t N,
+                           int S, int n_classes, int endpoint, int white_bkgd, const float* grec, const float* gweights,
+                           float* graw, cudaStream_t st);
 int launch_sample_pdf(const float* bins, const float* weights, int ld_w, const float* cdf_in, const float* u,
                       const float* u_det, int64_t N, int B, int n_samples, float* samples, int64_t* inds, float* cdf_out, cudaStream_t st);
 int launch_merge_sorted(const float* za, const float* zb, int64_t N, int Sa, int Sb, float* zout, float* zstd, cudaStream_t st);
@@ -125,6 +128,16 @@ int inrf_raw2outputs(const float* raw, const float* z, const float* rays_d, int 
   INRF_CHECK_SUPPORTED(n_classes >= 0 && n_classes <= MAX_CLASSES, "n_classes out of range");
   return launch_raw2outputs(raw, z, rays_d, ld_rays_d, noise, N, S, n_classes, endpoint_feat ? 1 : 0, white_bkgd,
                             rec, weights, (cudaStream_t)stream);
+}
+
+int inrf_raw2outputs_bwd(const float* raw, const float* z, const float* rays_d, int ld_rays_d, const float* noise,
+                         int64_t N, int S, int n_classes, int endpoint_feat, int white_bkgd, const float* grad_rec,
+                         const float* grad_weights, float* grad_raw, void* stream) {
+  INRF_CHECK_ARG(N >= 0 && S > 0 && (N == 0 || (raw && z && rays_d && grad_rec && grad_raw)), "null pointer / bad size");
+  INRF_CHECK_ARG(ld_rays_d >= 3, "ld_rays_d < 3");
+  INRF_CHECK_SUPPORTED(n_classes >= 0 && n_classes <= MAX_CLASSES, "n_classes out of range");
+  return launch_raw2outputs_bwd(raw, z, rays_d, ld_rays_d, noise, N, S, n_classes, endpoint_feat ? 1 : 0, white_bkgd,
+                                grad_rec, grad_weights, grad_raw, (cudaStream_t)stream);
 }
 
 int inrf_sample_pdf(const float* bins, const float* weights, int ld_w, const float* u, const float* u_det, int64_t N,

@@ -170,6 +170,105 @@ k_raw2outputs(const float* __restrict__ raw, const float* __restrict__ z, const 
   }
 }
 
+// ---------------------------------------------------------------------------------
+// backward of raw2outputs: one warp per ray, lane l owns samples l, l+32, ... (<= 8 groups).
+//   w_i = a_i T_i,  T_i = prod_{j<i} om_j,  om_j = 1 - a_j + 1e-10,  a = 1 - exp(-relu(s+n) d)
+//   dL/da_i = Gw_i T_i - (sum_{j>i} Gw_j w_j) / om_i,   da/ds = d (1-a) [s+n > 0]
+// ---------------------------------------------------------------------------------
+constexpr int BWD_MAXG = 8;
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_raw2outputs_bwd(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int ld_d,
+                  const float* __restrict__ noise, int64_t N, int S, int ch, int n_sem, int n_extra, int white_bkgd,
+                  const float* __restrict__ grec, int rec_ch, const float* __restrict__ gweights, float* __restrict__ graw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * (int64_t)WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (ray >= N) return;
+  const float* rw = raw + ray * (int64_t)S * ch;
+  float* gr = graw + ray * (int64_t)S * ch;
+  const float* zr = z + ray * (int64_t)S;
+  const float* g = grec + ray * rec_ch;
+  const float dx = rays_d[ray * ld_d + 0], dy = rays_d[ray * ld_d + 1], dz = rays_d[ray * ld_d + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const int G = (S + 31) / 32;
+  float al[BWD_MAXG], T[BWD_MAXG], dist[BWD_MAXG], pos[BWD_MAXG];
+  float carry = 1.f, acc = 0.f, depth = 0.f;
+#pragma unroll
+  for (int gi = 0; gi < BWD_MAXG; ++gi) {
+    al[gi] = 0.f; T[gi] = 0.f; dist[gi] = 0.f; pos[gi] = 0.f;
+    if (gi < G) {
+      const int s = gi * 32 + lane;
+      float one_minus = 1.f, a = 0.f;
+      if (s < S) {
+        float d = (s + 1 < S) ? (zr[s + 1] - zr[s]) : 1e10f;
+        d *= dnorm;
+        float sig = rw[(int64_t)s * ch + 3] + (noise ? noise[ray * S + s] : 0.f);
+        a = 1.f - expf(-fmaxf(sig, 0.f) * d);
+        one_minus = 1.f - a + 1e-10f;
+        dist[gi] = d;
+        pos[gi] = sig > 0.f ? 1.f : 0.f;
+      }
+      float p = one_minus;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { float q = __shfl_up_sync(FULL, p, o); if (lane >= o) p *= q; }
+      float excl = __shfl_up_sync(FULL, p, 1);
+      if (lane == 0) excl = 1.f;
+      al[gi] = a;
+      T[gi] = carry * excl;
+      carry *= __shfl_sync(FULL, p, 31);
+      if (s < S) { float w = a * T[gi]; acc += w; depth += w * zr[s]; }
+    }
+  }
+  acc = warp_sum(acc);
+  depth = warp_sum(depth);
+  // upstream gradients of the per-ray record
+  const float g_disp = g[3], g_acc = g[4], g_depth = g[12];
+  const float ratio = depth / acc;
+  const float m = fmaxf(1e-10f, ratio);
+  const float g_ratio = (ratio > 1e-10f) ? (-g_disp / (m * m)) : 0.f;   // NaN ratio (acc == 0): no gradient
+  float bg = 0.f;
+  if (white_bkgd) {
+    bg = g[0] + g[1] + g[2] + g[5] + g[6] + g[7] + g[8];
+    for (int e = 0; e < n_sem; ++e) bg += g[INRF_REC_BASE + e];
+  }
+  // reverse sweep: suffix sum of Gw_j w_j
+  float suffix = 0.f;
+#pragma unroll
+  for (int gi = BWD_MAXG - 1; gi >= 0; --gi) {
+    if (gi < G) {
+      const int s = gi * 32 + lane;
+      float gw = 0.f, w = 0.f;
+      if (s < S) {
+        const float* c = rw + (int64_t)s * ch;
+        w = al[gi] * T[gi];
+        gw = g[0] * c[0] + g[1] * c[1] + g[2] * c[2] + g[5] * c[4] + g[6] * c[5] + g[7] * c[6] + g[8] * c[7] +
+             g[9] * c[8] + g[10] * c[9] + g[11] * c[10] + g_depth * zr[s] + g_acc - bg;
+        for (int e = 0; e < n_extra; ++e) gw += g[INRF_REC_BASE + e] * c[INRF_RAW_BASE + e];
+        if (acc != 0.f) gw += g_ratio * (zr[s] - ratio) / acc;
+        if (gweights) gw += gweights[ray * S + s];
+        // colour-like channels: dL/dc = g w
+        float* o = gr + (int64_t)s * ch;
+        o[0] = g[0] * w; o[1] = g[1] * w; o[2] = g[2] * w;
+        o[4] = g[5] * w; o[5] = g[6] * w; o[6] = g[7] * w; o[7] = g[8] * w;
+        o[8] = g[9] * w; o[9] = g[10] * w; o[10] = g[11] * w;
+        for (int e = 0; e < n_extra; ++e) o[INRF_RAW_BASE + e] = g[INRF_REC_BASE + e] * w;
+      }
+      // inclusive suffix scan of gw*w inside the group (lanes above me), plus the groups after
+      float v = gw * w;
+      float incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { float q = __shfl_down_sync(FULL, incl, o); if (lane + o < 32) incl += q; }
+      const float after = suffix + (incl - v);          // sum over samples strictly after s
+      suffix += __shfl_sync(FULL, incl, 0);
+      if (s < S) {
+        const float om = 1.f - al[gi] + 1e-10f;
+        const float dLda = gw * T[gi] - after / om;
+        gr[(int64_t)s * ch + 3] = dLda * dist[gi] * (1.f - al[gi]) * pos[gi];
+      }
+    }
+  }
+}
+
 // semantic white-background fix-up kept separate so the main kernel stays simple
 __global__ void k_add_bg_sem(float* __restrict__ rec, int64_t N, int rec_ch, int n_sem) {
   int64_t total = N * n_sem;
@@ -382,6 +481,19 @@ int launch_raw2outputs(const float* raw, const float* z, const float* rays_d, in
     k_add_bg_sem<<<grid_for(N * n_classes, 256), 256, 0, st>>>(rec, N, rc, n_classes);
     INRF_LAUNCH_CHECK();
   }
+  return INRF_OK;
+}
+
+int launch_raw2outputs_bwd(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise, int64_t N,
+                           int S, int n_classes, int endpoint, int white_bkgd, const float* grec, const float* gweights,
+                           float* graw, cudaStream_t st) {
+  if (N == 0) return INRF_OK;
+  if (S > BWD_MAXG * 32) { set_error("raw2outputs_bwd: %d samples per ray > %d", S, BWD_MAXG * 32); return INRF_EUNSUPPORTED; }
+  int ch = raw_channels(n_classes, endpoint), rc = rec_channels(n_classes, endpoint);
+  int64_t blocks = (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  k_raw2outputs_bwd<<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, st>>>(raw, z, rays_d, ld_d, noise, N, S, ch, n_classes,
+                                                                   ch - INRF_RAW_BASE, white_bkgd, grec, rc, gweights, graw);
+  INRF_LAUNCH_CHECK();
   return INRF_OK;
 }
 

@@ -87,7 +87,7 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=F
             noise = torch.Tensor(np.random.rand(*list(raw[..., 3].shape))).to(raw.device) * raw_noise_std
         else:
             noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std
-    rec, w = ops.raw2outputs_rec(raw[..., :11], z_vals, rays_d, noise, white_bkgd)
+    rec, w = ops.composite(raw[..., :11], z_vals, rays_d, noise, white_bkgd)
     g = lambda k: _split_rec(rec, k)  # noqa: E731
     return g("rgb"), g("disp"), g("acc"), w, g("depth"), g("albedo"), g("shading"), g("residual")
 
@@ -154,15 +154,15 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand)
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         raw = network_query_fn(pts, viewdirs, network_fn)
-        rec, weights = ops.raw2outputs_rec(raw[..., :11], z_vals, rays_d, draw_noise(N, N_samples), white_bkgd)
+        rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, draw_noise(N, N_samples), white_bkgd)
         rec0 = rec
         if N_importance > 0:
             z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
-            z_samples = ops.sample_pdf(z_mid, weights[..., 1:-1], N_importance, u)[0]
+            z_samples = ops.sample_pdf(z_mid, weights[..., 1:-1].detach(), N_importance, u)[0]   # detached (run_nerf.py:501)
             z_vals, z_std = ops.merge_sorted(z_vals, z_samples)
             pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
             raw = network_query_fn(pts, viewdirs, network_fn if network_fine is None else network_fine)
-            rec, weights = ops.raw2outputs_rec(raw[..., :11], z_vals, rays_d, draw_noise(N, St), white_bkgd)
+            rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, draw_noise(N, St), white_bkgd)
         for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
             ret[k + "_map"] = _split_rec(rec, k)
         if retraw:

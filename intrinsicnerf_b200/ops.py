@@ -132,6 +132,48 @@ def raw2outputs_rec(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes
     return rec, weights
 
 
+def raw2outputs_bwd(raw, z_vals, rays_d, noise, grad_rec, grad_weights, white_bkgd=False, n_classes=0, endpoint=False):
+    raw, z_vals, rays_d, grad_rec = _f32(raw, "raw"), _f32(z_vals, "z_vals"), _f32(rays_d, "rays_d"), _f32(grad_rec, "grad_rec")
+    N, S, ch = raw.shape
+    noise = None if noise is None else _f32(noise, "noise")
+    grad_weights = None if grad_weights is None else _f32(grad_weights, "grad_weights")
+    grad_raw = torch.empty_like(raw)
+    with torch.cuda.device(raw.device):
+        check(_lib.lib().inrf_raw2outputs_bwd(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S, n_classes,
+                                              int(endpoint), int(bool(white_bkgd)), _ptr(grad_rec), _ptr(grad_weights),
+                                              _ptr(grad_raw), _stream()))
+    return grad_raw
+
+
+class CompositeFn(torch.autograd.Function):
+    """raw2outputs with a CUDA backward for `raw` (z_vals, rays_d and the noise are constants in the
+    reference: z_samples is detached, run_nerf.py:501).  Lets a foreign PyTorch network train
+    through the compositing kernel."""
+
+    @staticmethod
+    def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint):
+        rec, w = raw2outputs_rec(raw.detach(), z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True)
+        ctx.save_for_backward(raw.detach(), z_vals, rays_d, noise if noise is not None else torch.empty(0))
+        ctx.cfg = (bool(white_bkgd), int(n_classes), bool(endpoint), noise is not None)
+        return rec, w
+
+    @staticmethod
+    def backward(ctx, g_rec, g_w):
+        raw, z_vals, rays_d, noise = ctx.saved_tensors
+        wb, C, ep, has_noise = ctx.cfg
+        g_rec = torch.zeros(raw.shape[0], REC_BASE + C + (128 if ep else 0), device=raw.device) if g_rec is None else g_rec
+        g = raw2outputs_bwd(raw, z_vals, rays_d, noise if has_noise else None, g_rec.contiguous(),
+                            None if g_w is None else g_w.contiguous(), wb, C, ep)
+        return g, None, None, None, None, None, None
+
+
+def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, endpoint=False):
+    """rec, weights = raw2outputs; differentiable w.r.t. raw when autograd is recording."""
+    if torch.is_grad_enabled() and raw.requires_grad:
+        return CompositeFn.apply(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint)
+    return raw2outputs_rec(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True)
+
+
 def sample_pdf(bins, weights, n_samples, u=None, want_inds=False, want_cdf=False):
     bins, weights = _f32(bins, "bins"), _f32(weights, "weights")
     N, B = bins.shape

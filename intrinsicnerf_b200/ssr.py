@@ -59,7 +59,7 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, enable_s
         raw = torch.cat([raw[..., :11 + C], raw[..., -128:]], -1)
     elif not endpoint_feat and ch != 11 + C:
         raw = raw[..., :11 + C]
-    rec, w = ops.raw2outputs_rec(raw, z_vals, rays_d, noise, white_bkgd, C, endpoint_feat)
+    rec, w = ops.composite(raw, z_vals, rays_d, noise, white_bkgd, C, endpoint_feat)
     g = lambda k: _split_rec(rec, k)  # noqa: E731
     sem = rec[:, 13:13 + C] if C > 0 else torch.tensor(0)
     feat = rec[:, 13 + C:13 + C + 128] if endpoint_feat else torch.tensor(0)

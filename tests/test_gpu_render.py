@@ -179,3 +179,40 @@ def test_oracle_end_to_end_medium(dev, obj_nets):
             assert rel_err(rec_get(o["rec_fine"], k), want["fine"][k]) < TOL, (prec, k)
             assert rel_err(rec_get(o["rec_coarse"], k), want["coarse"][k]) < TOL, (prec, k)
         assert rel_err(o["z_std"], want["z_std"]) < TOL
+
+
+def test_training_step_through_stage_kernels_with_foreign_network(dev):
+    """Training path available in round 1: a foreign PyTorch network (here the oracle's functional
+    MLP on the GPU) trains through our sampling / compositing kernels - forward by the CUDA stages,
+    backward by k_raw2outputs_bwd - and the parameter gradients equal full PyTorch autograd through
+    the CPU oracle.  (The fused tensor-core path is forward-only and says so.)"""
+    from intrinsicnerf_b200 import object_level as ol
+    torch.manual_seed(20220414)
+    pc = orc.make_opaque(orc.init_params("object"))
+    pf = orc.make_opaque(orc.init_params("object"))
+    rays = orc.blender_rays(6, 6)[::3].contiguous()                   # 12 rays
+    target = torch.rand(rays.shape[0], 3, generator=torch.Generator().manual_seed(1))
+
+    def loss_of(res_rgb, res_rgb0, res_alb):
+        return ((res_rgb - target) ** 2).mean() + ((res_rgb0 - target) ** 2).mean() + 0.1 * res_alb.mean()
+
+    # reference gradients: full autograd through the oracle on the CPU
+    cc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    cf = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    r = orc.render_rays(rays, cc, cf, white_bkgd=True)
+    loss_of(r["fine"]["rgb"], r["coarse"]["rgb"], r["fine"]["albedo"]).backward()
+
+    gc = {k: v.clone().to(dev).requires_grad_(True) for k, v in pc.items()}
+    gf = {k: v.clone().to(dev).requires_grad_(True) for k, v in pf.items()}
+
+    def query(pts, viewdirs, params):                                  # foreign network_query_fn
+        return orc.query_field(pts, viewdirs, params)
+    out = ol.render_rays(rays.to(dev), gc, query, N_samples=64, N_importance=128, network_fine=gf, perturb=0.,
+                         white_bkgd=True, raw_noise_std=0.)
+    tgt = target.to(dev)
+    loss = ((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean() + 0.1 * out["albedo_map"].mean()
+    loss.backward()
+    for name in ("pts_linears.0.weight", "pts_linears.7.weight", "alpha_linear.weight", "albedo_linear2.weight", "shading_linear.bias"):
+        for ref, got in ((cc, gc), (cf, gf)):
+            a, b = ref[name].grad, got[name].grad.cpu()
+            assert float((a - b).abs().max()) < 2e-3 * float(a.abs().max()) + 1e-9, name

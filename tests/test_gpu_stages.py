@@ -165,7 +165,7 @@ def test_get_rays_bitexact(dev):
         got = ops.get_rays_packed(H, W, K, c2w, 2.0, 6.0, dev).cpu()
         assert got.shape == want.shape
         assert torch.equal(got[:, :8], want[:, :8])
-        assert (got[:, 8:] - want[:, 8:]).abs().max() <= 6e-8          # viewdir = d/|d|: norm summation order
+        assert (got[:, 8:] - want[:, 8:]).abs().max() <= 2e-7          # viewdir = d/|d|: 1 ulp (norm summation order)
 
 
 def test_full_frame_properties(dev):
@@ -189,3 +189,38 @@ def test_full_frame_properties(dev):
     b = ops.render_chunk(rays[:200000][77777:123457], coarse.packed(), fine.packed(), white_bkgd=True)
     assert torch.equal(b["rec_fine"], a["rec_fine"][77777:123457])     # bit-identical under re-chunking
     assert torch.equal(b["rec_coarse"], a["rec_coarse"][77777:123457])
+
+
+@pytest.mark.parametrize("white,C,endpoint,with_noise", [(True, 0, False, False), (False, 28, True, True), (True, 5, False, True)])
+def test_raw2outputs_backward_matches_autograd(dev, white, C, endpoint, with_noise):
+    """CUDA backward of the compositing stage vs PyTorch autograd through the oracle (fp64 reference)."""
+    from intrinsicnerf_b200 import ops
+    gen = torch.Generator().manual_seed(12)
+    N, S = 7, 192
+    ch = 11 + C + (128 if endpoint else 0)
+    raw = torch.randn(N, S, ch, generator=gen)
+    raw[..., 3] = raw[..., 3] * 2.0 + 0.5
+    z = torch.sort(torch.rand(N, S, generator=gen) * 4 + 2, dim=-1)[0]
+    rd = torch.randn(N, 3, generator=gen)
+    noise = torch.randn(N, S, generator=gen) if with_noise else None
+    rc = 13 + C + (128 if endpoint else 0)
+    g_rec = torch.randn(N, rc, generator=gen)
+    g_w = torch.randn(N, S, generator=gen) * 0.1
+    # reference gradient in double precision
+    r64 = raw.double().requires_grad_(True)
+    o = orc.composite(r64, z.double(), rd.double(), None if noise is None else noise.double(), white, C, endpoint)
+    parts = [o["rgb"], o["disp"][:, None], o["acc"][:, None], o["albedo"], o["shading"][:, None], o["residual"], o["depth"][:, None]]
+    if C > 0:
+        parts.append(o["sem"])
+    if endpoint:
+        parts.append(o["feat"])
+    rec64 = torch.cat(parts, -1)
+    loss = (rec64 * g_rec.double()).sum() + (o["weights"] * g_w.double()).sum()
+    loss.backward()
+    want = r64.grad.float()
+    rg = raw.to(dev).requires_grad_(True)
+    rec, w = ops.composite(rg, z.to(dev), rd.to(dev), None if noise is None else noise.to(dev), white, C, endpoint)
+    ((rec * g_rec.to(dev)).sum() + (w * g_w.to(dev)).sum()).backward()
+    got = rg.grad.cpu()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) < 2e-4 * scale, float((got - want).abs().max()) / scale

@@ -4,7 +4,7 @@ import os
 import sys
 
 os.environ.setdefault("INRF_TC_CHECK", "1")
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

@@ -3,7 +3,7 @@ Env: INRF_TC_CLUSTER, INRF_TC_BIASMMA select the variant (read once per process)
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("INRF_TC_CHECK", "0")
 import torch  # noqa: E402
