@@ -106,6 +106,23 @@ int inrf_mlp_fwd_rays(const void* packed, int variant, int n_classes, int endpoi
                       float pe_scalar_factor, const float* rays, const float* z, int64_t N, int S,
                       float* raw, int precision, void* stream);
 
+/* Training forward / backward of the field network (fp32 CUDA cores).
+ * Exactly one addressing mode is given: (pts, viewdirs) per sample row, or (rays, z, S), or emb
+ * (already embedded rows); the others are NULL.  The forward additionally writes the activation
+ * stash [M, inrf_stash_floats_per_row()] that the backward consumes.  The backward ACCUMULATES
+ * dL/d(parameters) into grad_flat (canonical flat order of inrf_flat_param_count; the caller zeroes
+ * it) given dL/d(raw) [M, out_ch].  Sample positions get no gradient (z_samples is detached in the
+ * reference, run_nerf.py:501).  This is what makes `loss.backward()` of run_nerf.py:1018 /
+ * trainer.py:990 work on the NeRF / Semantic_NeRF modules.                                        */
+int64_t inrf_stash_floats_per_row(void);
+int inrf_mlp_fwd_train(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
+                       const float* pts, const float* viewdirs, const float* rays, const float* z, int S,
+                       const float* emb, int64_t M, float* raw, float* stash, void* stream);
+int inrf_mlp_bwd(const float* flat_params, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
+                 const float* pts, const float* viewdirs, const float* rays, const float* z, int S,
+                 const float* emb, int64_t M, const float* raw, const float* stash, const float* grad_raw,
+                 float* grad_flat, void* stream);
+
 /* raw2outputs (run_nerf.py:359-412; model_utils.py:39-116).
  * raw[N,S,ch], z[N,S], rays_d given as rays_d[N,ld] with row stride ld floats (ld=3 for a
  * packed [N,3] tensor, 11 to address columns 3:6 of a ray record - pass rays+3).

@@ -109,6 +109,49 @@ int inrf_mlp_fwd_embedded(const void* packed, int variant, int n_classes, int en
   return run_mlp(a, precision, (cudaStream_t)stream);
 }
 
+int64_t inrf_stash_floats_per_row(void) { return STASH_LD; }
+
+static int fill_addressing(MlpArgs& a, const float* pts, const float* viewdirs, const float* rays, const float* z, int S,
+                           const float* emb) {
+  const int modes = (pts != nullptr) + (rays != nullptr) + (emb != nullptr);
+  if (modes != 1) { set_error("exactly one of (pts,viewdirs) / (rays,z) / emb must be given"); return INRF_EINVAL; }
+  if (pts && !viewdirs) { set_error("viewdirs missing"); return INRF_EINVAL; }
+  if (rays && (!z || S <= 0)) { set_error("z / S missing"); return INRF_EINVAL; }
+  a.pts = pts; a.viewdirs = viewdirs; a.rays = rays; a.z = z; a.S = rays ? S : 1; a.emb = emb;
+  return INRF_OK;
+}
+
+int inrf_mlp_fwd_train(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
+                       const float* pts, const float* viewdirs, const float* rays, const float* z, int S, const float* emb,
+                       int64_t M, float* raw, float* stash, void* stream) {
+  INRF_CHECK_ARG(M >= 0 && packed && (M == 0 || (raw && stash)), "null pointer / negative size");
+  INRF_CHECK_ARG(pe_scalar_factor > 0.f, "pe_scalar_factor must be positive");
+  INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
+  if (M == 0) return INRF_OK;
+  MlpArgs a{};
+  int rc = fill_addressing(a, pts, viewdirs, rays, z, S, emb);
+  if (rc) return rc;
+  a.packed = packed; a.variant = variant; a.n_classes = n_classes; a.endpoint = endpoint_feat ? 1 : 0;
+  a.pe_scale = pe_scalar_factor; a.M = M; a.raw = raw; a.stash = stash;
+  return launch_mlp_fp32(a, (cudaStream_t)stream);
+}
+
+int inrf_mlp_bwd(const float* flat_params, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
+                 const float* pts, const float* viewdirs, const float* rays, const float* z, int S, const float* emb,
+                 int64_t M, const float* raw, const float* stash, const float* grad_raw, float* grad_flat, void* stream) {
+  INRF_CHECK_ARG(M >= 0 && flat_params && grad_flat && (M == 0 || (raw && stash && grad_raw)), "null pointer / negative size");
+  INRF_CHECK_ARG(pe_scalar_factor > 0.f, "pe_scalar_factor must be positive");
+  INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
+  if (M == 0) return INRF_OK;
+  MlpBwdArgs b{};
+  int rc = fill_addressing(b.f, pts, viewdirs, rays, z, S, emb);
+  if (rc) return rc;
+  b.f.variant = variant; b.f.n_classes = n_classes; b.f.endpoint = endpoint_feat ? 1 : 0; b.f.pe_scale = pe_scalar_factor;
+  b.f.M = M; b.f.raw = const_cast<float*>(raw);
+  b.flat = flat_params; b.stash = stash; b.grad_raw = grad_raw; b.grad_flat = grad_flat;
+  return launch_mlp_bwd_fp32(b, (cudaStream_t)stream);
+}
+
 int inrf_mlp_fwd_rays(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
                       const float* rays, const float* z, int64_t N, int S, float* raw, int precision, void* stream) {
   INRF_CHECK_ARG(N >= 0 && S > 0 && packed && (N == 0 || (rays && z && raw)), "null pointer / bad size");

@@ -135,8 +135,21 @@ struct MlpArgs {
   int S;
   int64_t M;                 // total rows (N*S in ray mode)
   float* raw;                // [M,out_ch]
+  float* stash;              // optional [M, STASH_LD] fp32 activations for the backward pass (fp32 path only)
 };
+// training stash (fp32, per sample row): post-ReLU outputs of the 8 trunk layers, the feature vector,
+// relu(albedo1|shading1), relu(views) and relu(sem1)
+constexpr int ST_H = 0, ST_FEAT = 2048, ST_AS = 2304, ST_V = 2560, ST_SEM1 = 2688, STASH_LD = 2816;
+
 int launch_mlp_fp32(const MlpArgs& a, cudaStream_t st);
+struct MlpBwdArgs {
+  const float* flat;         // canonical flat parameters (fp32, nn.Linear layout)
+  MlpArgs f;                 // forward addressing (pts/viewdirs | rays,z | emb), M, variant, ...; f.raw = forward output
+  const float* stash;        // [M, STASH_LD] written by the training forward
+  const float* grad_raw;     // [M, out_ch]
+  float* grad_flat;          // [flat_count], accumulated into (+=)
+};
+int launch_mlp_bwd_fp32(const MlpBwdArgs& a, cudaStream_t st);
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t st);
 
 }  // namespace inrf

@@ -99,6 +99,16 @@ __device__ __forceinline__ float head_dot(const float* in_row, const float* __re
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// copy a [64 x width] activation tile to the training stash (rows beyond M are skipped)
+__device__ __forceinline__ void stash_tile(float* stash, int64_t row0, int64_t M, const float* tile, int ld, int col0,
+                                           int width, int stash_col) {
+  if (stash == nullptr) return;
+  for (int i = threadIdx.x; i < FT_ROWS * width; i += FT_THREADS) {
+    const int r = i / width, c = i - r * width;
+    if (row0 + r < M) stash[(row0 + r) * STASH_LD + stash_col + c] = tile[r * ld + col0 + c];
+  }
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 1) k_mlp_fp32(const __grid_constant__ Fp32Params P) {
   extern __shared__ __align__(16) float smem[];
   float* s_pe = smem;                          // [64][64]  (col 63 = 0)
@@ -178,6 +188,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_mlp_fp32(const __grid_constan
     pc[0] = {s_pe, LD_PE, PE_PTS};
     dense<8, true>(pc, 1, WT(L_T0), BI(L_T0), s_a, LD_H, 0);
     __syncthreads();
+    stash_tile(P.a.stash, row0, P.a.M, s_a, LD_H, 0, W_HID, ST_H);
     float* cur = s_a;
     float* nxt = s_b;
     for (int l = 1; l < 8; ++l) {
@@ -190,6 +201,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_mlp_fp32(const __grid_constan
         dense<8, true>(pc, 1, WT(L_T0 + l), BI(L_T0 + l), nxt, LD_H, 0);
       }
       __syncthreads();
+      stash_tile(P.a.stash, row0, P.a.M, nxt, LD_H, 0, W_HID, ST_H + l * W_HID);
       float* t = cur; cur = nxt; nxt = t;
     }
     // cur = h (trunk output), nxt = scratch
@@ -202,6 +214,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_mlp_fp32(const __grid_constan
       if (lane == 0) s_out[(8 * w + r) * 12 + 0] = sg + __ldg(BI(L_ALPHA));
     }
     __syncthreads();
+    stash_tile(P.a.stash, row0, P.a.M, nxt, LD_H, 0, W_HID, ST_AS);
     for (int r = 0; r < 8; ++r) {
       const float* row = nxt + (8 * w + r) * LD_H;
       for (int n = 0; n < 3; ++n) {
@@ -216,6 +229,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_mlp_fp32(const __grid_constan
     if (C > 0) {
       dense<4, true>(pc, 1, WT(L_SEM1), BI(L_SEM1), nxt, LD_H, 0);
       __syncthreads();
+      stash_tile(P.a.stash, row0, P.a.M, nxt, LD_H, 0, 128, ST_SEM1);
       for (int r = 0; r < 8; ++r) {
         int64_t m = row0 + 8 * w + r;
         const float* row = nxt + (8 * w + r) * LD_H;
@@ -229,10 +243,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_mlp_fp32(const __grid_constan
     // ---- feature -> views -> residual ----------------------------------------------------------
     dense<8, false>(pc, 1, WT(L_FEAT), BI(L_FEAT), nxt, LD_H, 0);
     __syncthreads();
+    stash_tile(P.a.stash, row0, P.a.M, nxt, LD_H, 0, W_HID, ST_FEAT);
     pc[0] = {nxt, LD_H, W_HID};
     pc[1] = {s_dir, LD_DIR, PE_DIR};
     dense<4, true>(pc, 2, WT(L_VIEWS), BI(L_VIEWS), cur, LD_H, 0);   // h is dead now
     __syncthreads();
+    stash_tile(P.a.stash, row0, P.a.M, cur, LD_H, 0, 128, ST_V);
     for (int r = 0; r < 8; ++r) {
       const float* row = cur + (8 * w + r) * LD_H;
       for (int n = 0; n < 3; ++n) {

@@ -83,12 +83,34 @@ class _FieldNet(nn.Module):
             self._packed_key = key
         return self._packed_blob
 
-    def _no_grad_guard(self, *tensors):
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
-                                        and any(True for _ in tensors)):
-            raise NotImplementedError(
-                "intrinsicnerf_b200 round 1 implements the forward path only: wrap the call in torch.no_grad() "
-                "(the backward kernels are the next row of the scope table, DESIGN.md)")
+    def needs_grad(self):
+        """True when the call must be recorded by autograd (training): the fp32 training kernels are
+        used (forward with activation stash + backward); otherwise the tensor-core inference path."""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def flat_params_diff(self):
+        """Canonical flat parameter vector as a differentiable function of the module parameters."""
+        parts = []
+        for lin in self._ordered_layers():
+            parts.append(lin.weight.reshape(-1))
+            parts.append(lin.bias.reshape(-1))
+        return torch.cat(parts).float()
+
+    def evaluate(self, mode, a, b=None, endpoint=False, pe_scalar_factor=1.0):
+        """raw rows for (pts, viewdirs) | (rays, z) | embedded rows; differentiable w.r.t. the parameters
+        in training mode."""
+        C = self.n_classes
+        if self.needs_grad():
+            if not next(self.parameters()).is_cuda:
+                raise RuntimeError("intrinsicnerf_b200 networks run on CUDA only: call .cuda() first (no CPU fallback)")
+            return ops.MlpFn.apply(self.flat_params_diff(), self.variant, C, bool(endpoint), float(pe_scalar_factor), mode, a, b)
+        if mode == "pts":
+            return ops.mlp_forward(self.packed(), self.variant, C, a, b, endpoint, pe_scalar_factor)
+        if mode == "rays":
+            out = ops.mlp_forward_rays(self.packed(), self.variant, C, a, b, endpoint, pe_scalar_factor)
+            return out.reshape(-1, out.shape[-1])
+        out = ops.mlp_forward_embedded(self.packed(), self.variant, C, a, endpoint)
+        return out.reshape(-1, out.shape[-1])
 
 
 class NeRF(_FieldNet):
@@ -118,8 +140,8 @@ class NeRF(_FieldNet):
 
     def forward(self, x):
         """x: [..., 90] embedded rows (gamma(x) | gamma(d)) -> [..., 11]."""
-        self._no_grad_guard(x)
-        return ops.mlp_forward_embedded(self.packed(), self.variant, 0, x, False)
+        out = self.evaluate("emb", x)
+        return out.reshape(*x.shape[:-1], out.shape[-1])
 
 
 class Semantic_NeRF(_FieldNet):
@@ -159,5 +181,5 @@ class Semantic_NeRF(_FieldNet):
         return layers
 
     def forward(self, x, show_endpoint=False):
-        self._no_grad_guard(x)
-        return ops.mlp_forward_embedded(self.packed(), self.variant, self.n_classes, x, bool(show_endpoint))
+        out = self.evaluate("emb", x, endpoint=bool(show_endpoint))
+        return out.reshape(*x.shape[:-1], out.shape[-1])

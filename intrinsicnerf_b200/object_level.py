@@ -64,10 +64,8 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     network are one kernel launch; otherwise embed -> fn like the reference."""
     if isinstance(fn, NeRF) and isinstance(embed_fn, Embedder) and isinstance(embeddirs_fn, Embedder) \
             and viewdirs is not None and embed_fn.n_freqs == 10 and embeddirs_fn.n_freqs == 4:
-        fn._no_grad_guard(inputs)
         dirs = viewdirs[:, None].expand(inputs.shape)
-        out = ops.mlp_forward(fn.packed(), fn.variant, 0, inputs.reshape(-1, 3), dirs.reshape(-1, 3),
-                              False, embed_fn.scalar_factor)
+        out = fn.evaluate("pts", inputs.reshape(-1, 3), dirs.reshape(-1, 3), False, embed_fn.scalar_factor)
         return out.reshape(list(inputs.shape[:-1]) + [out.shape[-1]])
     flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
     embedded = embed_fn(flat)
@@ -129,9 +127,10 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     u = draw_uniform(N, N_importance) if (N_importance > 0 and perturb != 0.) else None
 
     fused = isinstance(network_query_fn, _FusedQuery) and network_query_fn.fusable_with(network_fn, network_fine)
+    if fused and (network_fn.needs_grad() or (network_fine is not None and network_fine.needs_grad())):
+        fused = False          # training: stage kernels + differentiable MLP / compositing (MlpFn, CompositeFn)
     ret = {}
     if fused:
-        network_fn._no_grad_guard(ray_batch)
         fine = network_fine if network_fine is not None else network_fn
         o = ops.render_chunk(ray_batch, network_fn.packed(), fine.packed() if N_importance > 0 else None,
                              variant=network_fn.variant, n_samples=N_samples, n_importance=N_importance,

@@ -145,6 +145,62 @@ def raw2outputs_bwd(raw, z_vals, rays_d, noise, grad_rec, grad_weights, white_bk
     return grad_raw
 
 
+class MlpFn(torch.autograd.Function):
+    """Differentiable field-network evaluation (training path, fp32 CUDA cores).
+
+    forward : inrf_mlp_fwd_train (k_mlp_fp32 writing the activation stash)
+    backward: inrf_mlp_bwd       (k_mlp_bwd_fp32) -> dL/d(flat parameters)
+    The flat parameter vector is built with torch.cat from the module's parameters, so autograd
+    scatters the flat gradient back to every nn.Parameter.  Inputs (points / rays / depths) get no
+    gradient - the reference never differentiates them (z_samples is detached, run_nerf.py:501)."""
+
+    @staticmethod
+    def forward(ctx, flat, variant, n_classes, endpoint, pe_scalar_factor, mode, a, b):
+        flat_c = _f32(flat.detach(), "flat_params")
+        packed = pack_weights(flat_c, variant, n_classes)
+        L = _lib.lib()
+        ch = RAW_BASE + n_classes + (128 if endpoint else 0)
+        pts = vd = rays = z = emb = None
+        S = 1
+        if mode == "pts":
+            pts, vd = _f32(a, "pts").reshape(-1, 3), _f32(b, "viewdirs").reshape(-1, 3)
+            M = pts.shape[0]
+        elif mode == "rays":
+            rays, z = _f32(a, "rays"), _f32(b, "z")
+            S = z.shape[1]
+            M = z.numel()
+        else:
+            emb = _f32(a, "embedded").reshape(-1, 90)
+            M = emb.shape[0]
+        dev = flat_c.device
+        raw = torch.empty(M, ch, dtype=torch.float32, device=dev)
+        stash = torch.empty(M, int(L.inrf_stash_floats_per_row()), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(L.inrf_mlp_fwd_train(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor), _ptr(pts), _ptr(vd),
+                                       _ptr(rays), _ptr(z), S, _ptr(emb), M, _ptr(raw), _ptr(stash), _stream()))
+        ctx.save_for_backward(flat_c, raw, stash, *[t for t in (pts, vd, rays, z, emb) if t is not None])
+        ctx.cfg = (variant, n_classes, bool(endpoint), float(pe_scalar_factor), mode, S, M)
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        variant, n_classes, endpoint, pe, mode, S, M = ctx.cfg
+        flat_c, raw, stash, *addr = ctx.saved_tensors
+        pts = vd = rays = z = emb = None
+        if mode == "pts":
+            pts, vd = addr
+        elif mode == "rays":
+            rays, z = addr
+        else:
+            (emb,) = addr
+        g_raw = _f32(g_raw, "grad_raw").reshape(M, -1)
+        g_flat = torch.zeros_like(flat_c)
+        with torch.cuda.device(flat_c.device):
+            check(_lib.lib().inrf_mlp_bwd(_ptr(flat_c), variant, n_classes, int(endpoint), pe, _ptr(pts), _ptr(vd), _ptr(rays),
+                                          _ptr(z), S, _ptr(emb), M, _ptr(raw), _ptr(stash), _ptr(g_raw), _ptr(g_flat), _stream()))
+        return g_flat, None, None, None, None, None, None, None
+
+
 class CompositeFn(torch.autograd.Function):
     """raw2outputs with a CUDA backward for `raw` (z_vals, rays_d and the noise are constants in the
     reference: z_samples is detached, run_nerf.py:501).  Lets a foreign PyTorch network train

@@ -24,10 +24,8 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
     endpoint = bool(getattr(fn, "_inrf_endpoint", False))
     if isinstance(net, Semantic_NeRF) and isinstance(embed_fn, Embedder) and isinstance(embeddirs_fn, Embedder) \
             and viewdirs is not None and embed_fn.n_freqs == 10 and embeddirs_fn.n_freqs == 4:
-        net._no_grad_guard(inputs)
         dirs = viewdirs[:, None].expand(inputs.shape)
-        out = ops.mlp_forward(net.packed(), net.variant, net.n_classes, inputs.reshape(-1, 3), dirs.reshape(-1, 3),
-                              endpoint, embed_fn.scalar_factor)
+        out = net.evaluate("pts", inputs.reshape(-1, 3), dirs.reshape(-1, 3), endpoint, embed_fn.scalar_factor)
         return out.reshape(list(inputs.shape[:-1]) + [out.shape[-1]])
     flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
     embedded = embed_fn(flat)
@@ -104,7 +102,8 @@ class SSRRenderer:
                 and isinstance(self.embed_fn, Embedder) and isinstance(self.embeddirs_fn, Embedder)):
             raise NotImplementedError("SSRRenderer needs intrinsicnerf_b200 Semantic_NeRF networks and embedders "
                                       "(build them with create_ssr); there is no fallback path")
-        coarse._no_grad_guard(ray_batch)
+        if coarse.needs_grad() or (fine is not None and fine.needs_grad()):
+            return self._volumetric_rendering_train(ray_batch, t_rand, u, noise_c, noise_f, C)
         o = ops.render_chunk(ray_batch, coarse.packed(), (fine or coarse).packed() if Sf > 0 else None,
                              variant=coarse.variant, n_classes=C, n_samples=Sc, n_importance=Sf, lindisp=False,
                              white_bkgd=self.white_bkgd, endpoint=bool(self.endpoint_feat) and Sf > 0,
@@ -128,6 +127,39 @@ class SSRRenderer:
         for k in ret:
             if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
                 print(f"! [Numerical Error] {k} contains nan or inf.")
+        return ret
+
+    def _volumetric_rendering_train(self, ray_batch, t_rand, u, noise_c, noise_f, C):
+        """Training step (trainer.py:717-808 under autograd): the stage kernels composed in PyTorch with the
+        differentiable field network (ops.MlpFn) and compositing (ops.CompositeFn)."""
+        Sc, Sf = self.N_samples, self.N_importance
+        rays_o, rays_d, viewdirs = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, 8:11]
+        z = ops.coarse_z(ray_batch, Sc, False, t_rand)
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
+        raw_c = run_network(pts, viewdirs, self.ssr_net_coarse, self.embed_fn, self.embeddirs_fn)
+        rec_c, w_c = ops.composite(raw_c, z, rays_d, noise_c, self.white_bkgd, C, False)
+        ret = {"raw_coarse": raw_c}
+        names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual")
+        for k in names:
+            ret[k + "_coarse"] = _split_rec(rec_c, k)
+        if C > 0:
+            ret["sem_logits_coarse"] = rec_c[:, 13:13 + C]
+        if Sf > 0:
+            z_mid = .5 * (z[:, 1:] + z[:, :-1])
+            z_samples = ops.sample_pdf(z_mid, w_c[:, 1:-1].detach(), Sf, u)[0]
+            z_f, z_std = ops.merge_sorted(z, z_samples)
+            pts = rays_o[:, None, :] + rays_d[:, None, :] * z_f[:, :, None]
+            ep = bool(self.endpoint_feat)
+            raw_f = run_network(pts, viewdirs, with_endpoint(self.ssr_net_fine, ep), self.embed_fn, self.embeddirs_fn)
+            rec_f, _ = ops.composite(raw_f, z_f, rays_d, noise_f, self.white_bkgd, C, ep)
+            for k in names:
+                ret[k + "_fine"] = _split_rec(rec_f, k)
+            if C > 0:
+                ret["sem_logits_fine"] = rec_f[:, 13:13 + C]
+            ret["z_std"] = z_std
+            ret["raw_fine"] = raw_f
+            if ep:
+                ret["feat_map_fine"] = rec_f[:, 13 + C:13 + C + 128]
         return ret
 
     def create_ssr(self):

@@ -80,8 +80,8 @@ def test_module_forward_and_run_network(dev):
         assert rel_err(a, b) < 1e-5
         want = orc.query_field(pts.cpu(), vd.cpu(), pc)
         assert rel_err(a, want) < 2e-5
-        with pytest.raises(NotImplementedError):          # forward-only in round 1: loud, not silent
-            coarse(emb)
+        out = coarse(emb)                                 # autograd mode -> fp32 training kernels (MlpFn)
+        assert out.requires_grad and rel_err(out.detach().reshape(7, 64, 11), want) < 2e-5
     finally:
         ops.set_default_precision("tc")
 
@@ -224,3 +224,36 @@ def test_raw2outputs_backward_matches_autograd(dev, white, C, endpoint, with_noi
     got = rg.grad.cpu()
     scale = float(want.abs().max())
     assert float((got - want).abs().max()) < 2e-4 * scale, float((got - want).abs().max()) / scale
+
+
+@pytest.mark.parametrize("variant,C,endpoint", [("object", 0, False), ("ssr", 28, True), ("ssr", 0, False)])
+def test_mlp_backward_matches_autograd(dev, variant, C, endpoint):
+    """k_mlp_bwd_fp32 (through ops.MlpFn and the module's torch.cat of parameters) vs PyTorch autograd
+    through the oracle's functional MLP in float64."""
+    coarse, fine, pc, pf = build_nets(variant, C)
+    gen = torch.Generator().manual_seed(21)
+    M = 150                                             # 2 full 64-row tiles + a ragged one
+    pts = torch.rand(M, 3, generator=gen) * 6 - 3
+    vd = torch.nn.functional.normalize(torch.randn(M, 3, generator=gen), dim=-1)
+    scale = 1.0 if variant == "object" else 10.0
+    ch = 11 + C + (128 if endpoint else 0)
+    g_raw = torch.randn(M, ch, generator=gen)
+    p64 = {k: v.double().requires_grad_(True) for k, v in pf.items()}
+    emb = torch.cat([orc.posenc(pts.double(), 10, scale), orc.posenc(vd.double(), 4)], -1)
+    out64 = orc.mlp_forward(p64, emb, variant, C, endpoint)
+    (out64 * g_raw.double()).sum().backward()
+    fine.zero_grad()
+    out = fine.evaluate("pts", pts.to(dev), vd.to(dev), endpoint, scale)
+    assert rel_err(out.detach(), out64.detach(), floor=1e-2) < 2e-5
+    (out * g_raw.to(dev)).sum().backward()
+    worst = 0.0
+    for name, p in fine.named_parameters():
+        a, b = p64[name].grad.float(), p.grad.cpu()
+        e = float((a - b).abs().max()) / (float(a.abs().max()) + 1e-12)
+        worst = max(worst, e)
+        assert e < 5e-4, (name, e)
+    # second backward accumulates (zero_grad semantics are the caller's)
+    out2 = fine.evaluate("pts", pts.to(dev), vd.to(dev), endpoint, scale)
+    (out2 * g_raw.to(dev)).sum().backward()
+    name, p = next(iter(fine.named_parameters()))
+    assert rel_err(p.grad.cpu(), 2 * p64[name].grad.float(), floor=float(p64[name].grad.abs().max())) < 1e-3
