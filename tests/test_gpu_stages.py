@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as orc
-from tests.util import build_nets, load_golden, rel_err
+from tests.util import build_nets, load_golden, rel_err, relu_margin
 
 pytestmark = pytest.mark.gpu
 
@@ -226,13 +226,13 @@ def test_raw2outputs_backward_matches_autograd(dev, white, C, endpoint, with_noi
     assert float((got - want).abs().max()) < 2e-4 * scale, float((got - want).abs().max()) / scale
 
 
-@pytest.mark.parametrize("variant,C,endpoint", [("object", 0, False), ("ssr", 28, True), ("ssr", 0, False)])
+@pytest.mark.parametrize("variant,C,endpoint", [("object", 0, False), ("ssr", 28, True), ("ssr", 28, False), ("ssr", 5, False), ("ssr", 0, False)])
 def test_mlp_backward_matches_autograd(dev, variant, C, endpoint):
     """k_mlp_bwd_fp32 (through ops.MlpFn and the module's torch.cat of parameters) vs PyTorch autograd
     through the oracle's functional MLP in float64."""
     coarse, fine, pc, pf = build_nets(variant, C)
     gen = torch.Generator().manual_seed(21)
-    M = 150                                             # 2 full 64-row tiles + a ragged one
+    M = 2390 if endpoint else 150          # full 64-row tiles + a ragged one
     pts = torch.rand(M, 3, generator=gen) * 6 - 3
     vd = torch.nn.functional.normalize(torch.randn(M, 3, generator=gen), dim=-1)
     scale = 1.0 if variant == "object" else 10.0
@@ -240,18 +240,22 @@ def test_mlp_backward_matches_autograd(dev, variant, C, endpoint):
     g_raw = torch.randn(M, ch, generator=gen)
     p64 = {k: v.double().requires_grad_(True) for k, v in pf.items()}
     emb = torch.cat([orc.posenc(pts.double(), 10, scale), orc.posenc(vd.double(), 4)], -1)
-    out64 = orc.mlp_forward(p64, emb, variant, C, endpoint)
+    out64, margin = relu_margin(lambda: orc.mlp_forward(p64, emb, variant, C, endpoint))
+    # rows with a hidden unit within fp32 rounding of the ReLU kink get no upstream gradient (util.relu_margin):
+    # the oracle's own fp32-vs-fp64 gradients differ by 3-5 % on this weight set without the filter, 3e-6 with it
+    keep = margin > 5e-6
+    assert int(keep.sum()) > 0.8 * M
+    g_raw = g_raw * keep[:, None]
     (out64 * g_raw.double()).sum().backward()
     fine.zero_grad()
     out = fine.evaluate("pts", pts.to(dev), vd.to(dev), endpoint, scale)
     assert rel_err(out.detach(), out64.detach(), floor=1e-2) < 2e-5
     (out * g_raw.to(dev)).sum().backward()
-    worst = 0.0
+    errs = {}
     for name, p in fine.named_parameters():
         a, b = p64[name].grad.float(), p.grad.cpu()
-        e = float((a - b).abs().max()) / (float(a.abs().max()) + 1e-12)
-        worst = max(worst, e)
-        assert e < 5e-4, (name, e)
+        errs[name] = float((a - b).abs().max()) / (float(a.abs().max()) + 1e-12)
+    assert max(errs.values()) < 5e-4, sorted(errs.items(), key=lambda kv: -kv[1])[:6]
     # second backward accumulates (zero_grad semantics are the caller's)
     out2 = fine.evaluate("pts", pts.to(dev), vd.to(dev), endpoint, scale)
     (out2 * g_raw.to(dev)).sum().backward()
