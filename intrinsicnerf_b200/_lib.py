@@ -5,7 +5,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libinrf.so")
+# INRF_LIB: developer override (e.g. a -DTC2_PROF profiling build of the same sources)
+LIB_PATH = os.environ.get("INRF_LIB") or os.path.join(_HERE, "csrc", "libinrf.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "inrf.h")
 
 PREC_TC, PREC_FP32 = 0, 1

@@ -107,12 +107,17 @@ constexpr int TC_MAX_FILLS = 64;
 // The blob is a sequence of 128-row (or narrower) sub-blocks; consecutive sub-blocks that the MMA
 // warp consumes as ONE operand tile (e.g. the two N halves of a 256-wide layer for one K chunk)
 // are adjacent and streamed as one "fill" of the shared-memory ring.
+// GEMM steps of one tile: trunk layers 0..7, then the tail
+enum TcStep { TS_VIEWS = 8, TS_ALBSH = 9, TS_RES = 10, TS_ALB2SH2 = 11, TS_SEM2 = 12 };
+constexpr int TC_BIAS_FLOATS = 8192;   // fp32 table behind the operand blocks (biases, sigma row, fp32 head weights)
 struct TcProgram {
   int n_blocks;
   int bytes;
   int n_fills;
   int fill_off[TC_MAX_FILLS];
   int fill_bytes[TC_MAX_FILLS];
+  int16_t fill_step[TC_MAX_FILLS];     // TcStep of the GEMM this fill feeds
+  int16_t fill_block0[TC_MAX_FILLS];   // first sub-block of the fill
   TcBlock blk[TC_MAX_BLOCKS];
 };
 int make_tc_program(int variant, int n_classes, TcProgram* prog);
@@ -151,5 +156,6 @@ struct MlpBwdArgs {
 };
 int launch_mlp_bwd_fp32(const MlpBwdArgs& a, cudaStream_t st);
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t st);
+int launch_mlp_tc2(const MlpArgs& a, cudaStream_t st);
 
 }  // namespace inrf

@@ -51,7 +51,7 @@ int make_layout(int variant, int n_classes, NetLayout* L) {
   L->comp = b;
   b = align_up(b + (128 * 256 + 128) * 4, 256);
   L->tc_bias = b;
-  b = align_up(b + 4096 * 4, 1024);   // bias table (<= 2944 floats)
+  b = align_up(b + TC_BIAS_FLOATS * 4, 1024);
   TcProgram prog;
   int rc = make_tc_program(variant, n_classes, &prog);
   if (rc) return rc;
@@ -76,7 +76,9 @@ static void push(TcProgram* p, int layer, int rows, int n0, int k0, int kcols, i
 // bias of `layer` rows [n0, n0+128) as a K=16 operand (accumulator initialisation by MMA)
 static void push_bias(TcProgram* p, int layer, int n0) { push(p, layer, 128, n0, 0, 3, 3); }
 // everything pushed since `start_bytes` becomes one ring fill
-static void close_fill(TcProgram* p, int start_bytes) {
+static void close_fill(TcProgram* p, int start_bytes, int step, int block0) {
+  p->fill_step[p->n_fills] = (int16_t)step;
+  p->fill_block0[p->n_fills] = (int16_t)block0;
   p->fill_off[p->n_fills] = start_bytes;
   p->fill_bytes[p->n_fills] = p->bytes - start_bytes;
   p->n_fills++;
@@ -86,10 +88,11 @@ static void close_fill(TcProgram* p, int start_bytes) {
 int make_tc_program(int variant, int n_classes, TcProgram* p) {
   p->n_blocks = 0; p->bytes = 0; p->n_fills = 0;
   const bool sem = n_classes > 0;
-  int f;
-#define FILL(stmts) do { f = p->bytes; stmts; close_fill(p, f); } while (0)
+  int f, fb, step;
+#define FILL(stmts) do { f = p->bytes; fb = p->n_blocks; stmts; close_fill(p, f, step, fb); } while (0)
   // trunk layers: N = 256 operand tiles (rows 0..127 | 128..255), one fill per K chunk
   for (int l = 0; l < 8; ++l) {
+    step = l;
     FILL(push_bias(p, L_T0 + l, 0); push_bias(p, L_T0 + l, 128));
     if (l == 0 || l == 5) FILL(push(p, L_T0 + l, 128, 0, 0, PE_PTS, 0); push(p, L_T0 + l, 128, 128, 0, PE_PTS, 0));
     if (l == 0) continue;
@@ -99,19 +102,24 @@ int make_tc_program(int variant, int n_classes, TcProgram* p) {
   }
   // views' (composed with feature_linear) [| semantic hidden layer]: N = 128 [256], K = 256, then
   // the 27 direction-encoding columns (K = 32) for the views' rows only
+  step = TS_VIEWS;
   FILL(push_bias(p, -1, 0); if (sem) push_bias(p, L_SEM1, 0));
   for (int c = 0; c < 4; ++c) FILL(push(p, -1, 128, 0, 64 * c, 64, 1); if (sem) push(p, L_SEM1, 128, 0, 64 * c, 64, 0));
   FILL(push(p, L_VIEWS, 128, 0, W_HID, PE_DIR, 0));
   // albedo1 | shading1: one 256-wide GEMM on the trunk output
+  step = TS_ALBSH;
   FILL(push_bias(p, L_ALB1, 0); push_bias(p, L_SH1, 0));
   for (int c = 0; c < 4; ++c) FILL(push(p, L_ALB1, 128, 0, 64 * c, 64, 0); push(p, L_SH1, 128, 0, 64 * c, 64, 0));
   // residual head on relu(views'):  16 x 128 (two K chunks in one fill)
+  step = TS_RES;
   FILL(for (int c = 0; c < 2; ++c) push(p, L_RES, 16, 0, 64 * c, 64, 0));
   // albedo2 (rows 0..2, K 0..127) + shading2 (row 3, K 128..255): block-diagonal 16 x 256
+  step = TS_ALB2SH2;
   FILL(for (int c = 0; c < 4; ++c) push(p, L_ALB2, 16, 0, 64 * c, 64, 2));
   // semantic logits on relu(sem1): ceil16(C) x 128
   if (sem) {
     const int rows = (n_classes + 15) / 16 * 16;
+    step = TS_SEM2;
     FILL(for (int c = 0; c < 2; ++c) push(p, L_SEM2, rows, 0, 64 * c, 64, 0));
   }
 #undef FILL
@@ -172,7 +180,7 @@ __global__ void k_pack_tc_bias(const float* __restrict__ flat, unsigned char* __
   float* t = reinterpret_cast<float*>(packed + P.L.tc_bias);
   const float* cb = reinterpret_cast<const float*>(packed + P.L.comp) + 128 * 256;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 4096) return;
+  if (i >= TC_BIAS_FLOATS) return;
   float v = 0.f;
   if (i < 2048) v = flat[P.L.flat_b[i / 256] + (i % 256)];
   else if (i < 2176) v = cb[i - 2048];
@@ -185,6 +193,14 @@ __global__ void k_pack_tc_bias(const float* __restrict__ flat, unsigned char* __
   else if (i == 2820) v = flat[P.L.flat_b[L_SH2]];
   else if (i < 2824) v = flat[P.L.flat_b[L_RES] + (i - 2821)];
   else if (i < 2824 + P.L.n_classes) v = flat[P.L.flat_b[L_SEM2] + (i - 2824)];
+  else if (i >= 4096 && i < 4096 + 512) {          // residual head, float4 per hidden unit k: (w0k, w1k, w2k, 0)
+    const int k = (i - 4096) >> 2, c = (i - 4096) & 3;
+    v = c < 3 ? flat[P.L.flat_w[L_RES] + c * 128 + k] : 0.f;
+  } else if (i >= 4608 && i < 4608 + 1024) {       // albedo2 (k < 128: w0k, w1k, w2k, 0) | shading2 (k >= 128: wk, 0, 0, 0)
+    const int k = (i - 4608) >> 2, c = (i - 4608) & 3;
+    if (k < 128) v = c < 3 ? flat[P.L.flat_w[L_ALB2] + c * 128 + k] : 0.f;
+    else v = c == 0 ? flat[P.L.flat_w[L_SH2] + (k - 128)] : 0.f;
+  }
   t[i] = v;
 }
 
@@ -243,7 +259,7 @@ int pack_weights(const float* flat, int variant, int n_classes, void* packed, in
   INRF_LAUNCH_CHECK();
   k_compose_views<<<128, 256, 0, st>>>(flat, out, P);
   INRF_LAUNCH_CHECK();
-  k_pack_tc_bias<<<16, 256, 0, st>>>(flat, out, P);
+  k_pack_tc_bias<<<TC_BIAS_FLOATS / 256, 256, 0, st>>>(flat, out, P);
   INRF_LAUNCH_CHECK();
   k_pack_tc_blocks<<<prog.n_blocks, 256, 0, st>>>(flat, out, P, prog);   // 2 KB table by value
   INRF_LAUNCH_CHECK();
