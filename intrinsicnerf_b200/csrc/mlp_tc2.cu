@@ -21,7 +21,7 @@
 //   warps 16-19 front end       : o + d z, range-reduced sin/cos encodings as fp16 UMMA operand tiles;
 //                                 gamma(x) and gamma(d) share one 16 KB tile per stream (gamma(d) is
 //                                 written once layer 5 has consumed gamma(x))
-//   warps 0-15  epilogue        : 8 per stream; tcgen05.ld -> ReLU -> fp16 -> next layer's A operand in
+//   warps 0-15  epilogue        : all 16 on whichever stream completes; tcgen05.ld -> ReLU -> fp16 -> next layer's A operand in
 //                                 place (SWIZZLE_128B K-major); the narrow heads (sigma, albedo2,
 //                                 shading2, residual) are fp32 dot products on the un-rounded
 //                                 accumulators, so no hidden activation of the tail ever goes back to
@@ -47,7 +47,7 @@ constexpr int LAG = 5;                      // stream 1 runs LAG steps behind st
 // shared memory map (bytes)
 constexpr int SM_STREAM = 5 * CHUNK;        // per stream: H (4 chunks, in place) + X (gamma(x) / gamma(d))
 constexpr int SM_X = 4 * CHUNK;             // offset of X inside a stream
-constexpr int SM_SCRATCH = 3 * CHUNK;       // [128][8] fp32 head partials, H chunk 3 at the tile tail
+constexpr int SM_SCRATCH = 3 * CHUNK;       // [3][128][8] fp32 head partials, H chunk 3 at the tile tail
 constexpr int SM_RING = 2 * SM_STREAM;
 constexpr int SM_ONES = SM_RING + NS * SLOT;           // 8 x 16 fp16 "ones" A operand for the bias MMAs
 constexpr int SM_BAR = SM_ONES + 256;
@@ -64,7 +64,7 @@ enum {
   B_WEMPTY = B_WFULL + NS,     // [NS] ring slot consumed (tcgen05.commit multicast to both CTAs)
   B_STREAM = B_WEMPTY + NS,    // per stream: + 4 * s
   B_ACC_FULL = 0,              //   accumulator of the stream complete (commit multicast)
-  B_EPI_DONE = 1,              //   leader only: both CTAs' epilogue warps are done with the accumulator (16 arrivals)
+  B_EPI_DONE = 1,              //   leader only: both CTAs' epilogue warps are done with the accumulator (32 arrivals)
   B_XREADY = 2,                //   leader only: gamma(x) / gamma(d) written in both CTAs (8 arrivals)
   B_XFREE = 3,                 //   X tile no longer read by the tensor core (commit multicast)
   B_COUNT = B_STREAM + 8
@@ -660,8 +660,10 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
 }
 
 // ------------------------------------------------------------------------------------------
-// epilogue warps.  Warp (s, q, jj): stream s, TMEM lanes 32q..32q+31 (one row per thread); of every
-// 64-column chunk it owns columns jj*32..jj*32+31.
+// epilogue warps.  All 16 warps serve whichever stream's accumulator completes next (the streams
+// alternate, so the drain of one accumulator gets twice the warps and finishes in half the time).
+// Warp (q, cq): TMEM lanes 32q..32q+31 (one row per thread); of every 64-column chunk it owns columns
+// cq*16..cq*16+15.
 // ------------------------------------------------------------------------------------------
 // 16 accumulator columns -> ReLU -> fp16 -> 2 swizzled 16-byte stores
 __device__ __forceinline__ void store16(const uint32_t* v, uint32_t dst_chunk, const RowAddr& ra, int unit0) {
@@ -677,153 +679,176 @@ __device__ __forceinline__ void store16(const uint32_t* v, uint32_t dst_chunk, c
 
 __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// NBLK 16-column blocks (block b = this warp's columns of chunk b) with two TMEM loads in flight
+template <int NBLK, class F>
+__device__ __forceinline__ void tmem_chunks16(uint32_t taddr, F&& f) {
+  static_assert(NBLK % 2 == 0, "pairs of blocks");
+  uint32_t va[16], vb[16];
+  tmem_ld16(taddr, va);
+#pragma unroll
+  for (int b = 0; b < NBLK; b += 2) {
+    tmem_wait16(va);
+    tmem_ld16(taddr + (uint32_t)((b + 1) * 64), vb);
+    f(b, va);
+    tmem_wait16(vb);
+    if (b + 2 < NBLK) tmem_ld16(taddr + (uint32_t)((b + 2) * 64), va);
+    f(b + 1, vb);
+  }
+}
+
+struct HeadAcc {          // per-stream partial dot products of the narrow heads (this thread's columns)
+  float sig, alb[3], sh, res[3];
+};
+
 __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* smem, uint32_t smem_base, uint32_t tmem,
-                                         int s, int q, int jj, int lane) {
+                                         int q, int cq, int lane) {
   const int row = q * 32 + lane;
-  const uint32_t acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)s * 256 + (uint32_t)jj * 32;
-  const uint32_t H = smem_base + s * SM_STREAM;
-  float4* scratch = reinterpret_cast<float4*>(smem + s * SM_STREAM + SM_SCRATCH) + row * 2;
-  const int sb = B_STREAM + 4 * s;
-  const uint32_t done = mapa(sy.addr(sb + B_EPI_DONE), 0);
+  const uint32_t lane_col = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cq * 16;
   const bool sem = P.C > 0;
   const float4* hw_res = reinterpret_cast<const float4*>(P.bias + TCB_HW_RES);
   const float4* hw_as = reinterpret_cast<const float4*>(P.bias + TCB_HW_AS);
+  const uint32_t done0 = mapa(sy.addr(B_STREAM + B_EPI_DONE), 0);     // stream 1: + 32 bytes
   RowAddr ra;
   ra.init(row);
+  HeadAcc hs[2];
+  int it_of[2] = {0, 0};
 #ifdef TC2_PROF
-  long long busy = 0, tb = 0;
-  volatile long long* ts = reinterpret_cast<volatile long long*>(smem + SM_BAR + 192) + 2 * s;
-  long long lat_wake = 0;
+  long long busy = 0, tb = 0, lat_wake = 0;
   const bool prof_me = prof_role() >= 0 && blockIdx.x == 0;
-#define PROF_BEGIN() do { tb = clock64(); if (prof_me) lat_wake += tb - ts[0]; } while (0)
-#define PROF_END() do { const long long te = clock64(); busy += te - tb; if (prof_me) ts[1] = te; } while (0)
+#define PROF_BEGIN() do { tb = clock64(); if (prof_me) lat_wake += tb - (reinterpret_cast<volatile long long*>(smem + SM_BAR + 192) + 2 * s)[0]; } while (0)
+#define PROF_END() do { const long long te = clock64(); busy += te - tb; if (prof_me) (reinterpret_cast<volatile long long*>(smem + SM_BAR + 192) + 2 * s)[1] = te; } while (0)
 #else
 #define PROF_BEGIN()
 #define PROF_END()
 #endif
-  for (int it = 0; it < P.n_iter; ++it) {
-    const int64_t tile = ((int64_t)it * 2 + s) * gridDim.x + blockIdx.x;   // may run past the end: stores are masked
-    sy.tile = it;
-    const int64_t m = tile * TILE_M + row;
-    const bool valid = m < P.a.M;
-    float* grow = P.a.raw + (valid ? m : 0) * P.out_ch;
-    // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
-    float sig = 0.f;
-    for (int l = 0; l < 8; ++l) {
-      sy.wait(sb + B_ACC_FULL);
-      PROF_BEGIN();
-      tc_fence_after();
+  for_each_step(P.n_iter, P.n_steps, [&](int s, int k) {
+    const uint32_t acc = lane_col + (uint32_t)s * 256;
+    const uint32_t H = smem_base + s * SM_STREAM;
+    const int sb = B_STREAM + 4 * s;
+    const uint32_t done = done0 + 32u * s;
+    HeadAcc& h = hs[s];
+    sy.tile = it_of[s];
+    sy.wait(sb + B_ACC_FULL);
+    PROF_BEGIN();
+    tc_fence_after();
+    if (k < 8) {
+      // ---- trunk: accumulator of layer k -> A operand of layer k+1 (in place in H) --------------------
       if (P.exp & 1) {
-      } else if (l < 7) {
-        tmem_stream16<8>(acc, [&](int b, const uint32_t* v) { store16(v, H + (b >> 1) * CHUNK, ra, jj * 4 + (b & 1) * 2); });
+      } else if (k < 7) {
+        tmem_chunks16<4>(acc, [&](int b, const uint32_t* v) { store16(v, H + b * CHUNK, ra, cq * 2); });
       } else {                          // + sigma head: fp32 dot on the un-rounded ReLU output (alpha_linear)
-        const float4* aw = reinterpret_cast<const float4*>(P.bias + TCB_ALPHA_W + jj * 32);
-        tmem_stream16<8>(acc, [&](int b, const uint32_t* v) {
+        const float4* aw = reinterpret_cast<const float4*>(P.bias + TCB_ALPHA_W + cq * 16);
+        float sg = 0.f;
+        tmem_chunks16<4>(acc, [&](int b, const uint32_t* v) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 t = __ldg(aw + (b >> 1) * 16 + (b & 1) * 4 + i);
-            sig = fmaf(fmaxf(__uint_as_float(v[4 * i]), 0.f), t.x, sig);
-            sig = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), t.y, sig);
-            sig = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), t.z, sig);
-            sig = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), t.w, sig);
+            const float4 t = __ldg(aw + b * 16 + i);
+            sg = fmaf(fmaxf(__uint_as_float(v[4 * i]), 0.f), t.x, sg);
+            sg = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), t.y, sg);
+            sg = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), t.z, sg);
+            sg = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), t.w, sg);
           }
-          store16(v, H + (b >> 1) * CHUNK, ra, jj * 4 + (b & 1) * 2);
+          store16(v, H + b * CHUNK, ra, cq * 2);
         });
+        h.sig = sg;
       }
       fence_async_smem();
-      tc_fence_before();
-      warp_arrive_leader(done, lane);
-      PROF_END();
-    }
-    // ---- relu(albedo1 | shading1) -> albedo2 / shading2 partial dot products (fp32) -------------------
-    float alb[3] = {0.f, 0.f, 0.f}, sh = 0.f;
-    sy.wait(sb + B_ACC_FULL);
-    PROF_BEGIN();
-    tc_fence_after();
-    if (!(P.exp & 1))
-    tmem_stream16<8>(acc, [&](int b, const uint32_t* v) {     // blocks 0-3: albedo_linear1 hidden units, 4-7: shading
-      const float4* w = hw_as + (b >> 1) * 64 + jj * 32 + (b & 1) * 16;
-      if (b < 4) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 t = __ldg(w + i);
-          const float a = fmaxf(__uint_as_float(v[i]), 0.f);
-          alb[0] = fmaf(a, t.x, alb[0]); alb[1] = fmaf(a, t.y, alb[1]); alb[2] = fmaf(a, t.z, alb[2]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          sh = fmaf(fmaxf(__uint_as_float(v[i]), 0.f), __ldg(reinterpret_cast<const float*>(w + i)), sh);
-      }
-    });
-    tc_fence_before();
-    warp_arrive_leader(done, lane);
-    PROF_END();
-    // ---- relu(views') -> residual partial dot products [endpoint features]; relu(sem1) -> H chunks 0,1 --
-    float res[3] = {0.f, 0.f, 0.f};
-    sy.wait(sb + B_ACC_FULL);
-    PROF_BEGIN();
-    tc_fence_after();
-    {
-      float* g = (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C + jj * 32 : nullptr;   // endpoint feature rows (fp32, post-ReLU)
+    } else if (k == K_ALBSH) {
+      // ---- relu(albedo1 | shading1) -> albedo2 / shading2 partial dot products (fp32) -------------------
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, sh = 0.f;
       if (!(P.exp & 1))
-      tmem_stream16<4>(acc, [&](int b, const uint32_t* v) {
-        const float4* w = hw_res + (b >> 1) * 64 + jj * 32 + (b & 1) * 16;
+      tmem_chunks16<4>(acc, [&](int b, const uint32_t* v) {     // chunks 0,1: albedo_linear1 hidden units, 2,3: shading
+        const float4* w = hw_as + b * 64 + cq * 16;
+        if (b < 2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 t = __ldg(w + i);
-          const float a = fmaxf(__uint_as_float(v[i]), 0.f);
-          res[0] = fmaf(a, t.x, res[0]); res[1] = fmaf(a, t.y, res[1]); res[2] = fmaf(a, t.z, res[2]);
-        }
-        if (g != nullptr) {
+          for (int i = 0; i < 16; ++i) {
+            const float4 t = __ldg(w + i);
+            const float a = fmaxf(__uint_as_float(v[i]), 0.f);
+            a0 = fmaf(a, t.x, a0); a1 = fmaf(a, t.y, a1); a2 = fmaf(a, t.z, a2);
+          }
+        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) g[(b >> 1) * 64 + (b & 1) * 16 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
+          for (int i = 0; i < 16; ++i)
+            sh = fmaf(fmaxf(__uint_as_float(v[i]), 0.f), __ldg(reinterpret_cast<const float*>(w + i)), sh);
         }
       });
-    }
-    if (sem) {
-      tmem_stream16<4>(acc + 128, [&](int b, const uint32_t* v) { store16(v, H + (b >> 1) * CHUNK, ra, jj * 4 + (b & 1) * 2); });
-      fence_async_smem();
-    }
-    // ---- combine the two column halves of every row, sigmoids, raw row -----------------------------------
-    if (jj == 1) {
-      scratch[0] = make_float4(sig, res[0], res[1], res[2]);
-      scratch[1] = make_float4(alb[0], alb[1], alb[2], sh);
-    }
-    asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory");
-    if (jj == 0) {
-      const float4 p0 = scratch[0], p1 = scratch[1];
-      if (valid) {
-        float r3[3], a3[3];
-        r3[0] = sigmoid_((res[0] + p0.y) + __ldg(P.bias + TCB_RES + 0));
-        r3[1] = sigmoid_((res[1] + p0.z) + __ldg(P.bias + TCB_RES + 1));
-        r3[2] = sigmoid_((res[2] + p0.w) + __ldg(P.bias + TCB_RES + 2));
-        a3[0] = sigmoid_((alb[0] + p1.x) + __ldg(P.bias + TCB_ALB2 + 0));
-        a3[1] = sigmoid_((alb[1] + p1.y) + __ldg(P.bias + TCB_ALB2 + 1));
-        a3[2] = sigmoid_((alb[2] + p1.z) + __ldg(P.bias + TCB_ALB2 + 2));
-        const float shd = sigmoid_((sh + p1.w) + __ldg(P.bias + TCB_SH2));
-        const float sigma = (sig + p0.x) + __ldg(P.bias + TCB_ALPHA_B);
+      h.alb[0] = a0; h.alb[1] = a1; h.alb[2] = a2; h.sh = sh;
+    } else if (k == K_VIEWS) {
+      // ---- relu(views') -> residual partial dot products [endpoint features]; relu(sem1) -> H chunks 0,1;
+      //      then combine the four column quarters of every row, sigmoids, raw row --------------------------
+      const int64_t tile = ((int64_t)it_of[s] * 2 + s) * gridDim.x + blockIdx.x;   // may run past the end: stores are masked
+      const int64_t m = tile * TILE_M + row;
+      const bool valid = m < P.a.M;
+      float* grow = P.a.raw + (valid ? m : 0) * P.out_ch;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      {
+        float* g = (P.a.endpoint && valid) ? grow + INRF_RAW_BASE + P.C + cq * 16 : nullptr;   // endpoint feature rows (fp32, post-ReLU)
+        if (!(P.exp & 1))
+        tmem_chunks16<2>(acc, [&](int b, const uint32_t* v) {
+          const float4* w = hw_res + b * 64 + cq * 16;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) grow[i] = __fadd_rn(__fmul_rn(a3[i], shd), r3[i]);
-        grow[3] = sigma;
+          for (int i = 0; i < 16; ++i) {
+            const float4 t = __ldg(w + i);
+            const float a = fmaxf(__uint_as_float(v[i]), 0.f);
+            r0 = fmaf(a, t.x, r0); r1 = fmaf(a, t.y, r1); r2 = fmaf(a, t.z, r2);
+          }
+          if (g != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) grow[4 + i] = a3[i];
-        grow[7] = shd;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) grow[8 + i] = r3[i];
+            for (int i = 0; i < 16; ++i) g[b * 64 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
+          }
+        });
       }
-    }
-    asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory");     // scratch is H chunk 3: read before the next layer-0 epilogue
-    tc_fence_before();
-    warp_arrive_leader(done, lane);
-    PROF_END();
-    // ---- semantic logits -----------------------------------------------------------------------------------
-    if (sem) {
-      sy.wait(sb + B_ACC_FULL);
-      tc_fence_after();
-      for (int c0 = jj * 32; c0 < P.C; c0 += 64) {
+      if (sem) {
+        tmem_chunks16<2>(acc + 128, [&](int b, const uint32_t* v) { store16(v, H + b * CHUNK, ra, cq * 2); });
+        fence_async_smem();
+      }
+      // partials of column quarters 1..3 -> scratch (H chunk 3 of this stream), quarter 0 sums in fixed order
+      float4* scratch = reinterpret_cast<float4*>(smem + s * SM_STREAM + SM_SCRATCH);
+      if (cq != 0) {
+        float4* d = scratch + ((cq - 1) * TILE_M + row) * 2;
+        d[0] = make_float4(h.sig, r0, r1, r2);
+        d[1] = make_float4(h.alb[0], h.alb[1], h.alb[2], h.sh);
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (cq == 0) {
+        float sg = h.sig, al0 = h.alb[0], al1 = h.alb[1], al2 = h.alb[2], shv = h.sh;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 p0 = scratch[(j * TILE_M + row) * 2], p1 = scratch[(j * TILE_M + row) * 2 + 1];
+          sg += p0.x; r0 += p0.y; r1 += p0.z; r2 += p0.w;
+          al0 += p1.x; al1 += p1.y; al2 += p1.z; shv += p1.w;
+        }
+        if (valid) {
+          float r3[3], a3[3];
+          r3[0] = sigmoid_(r0 + __ldg(P.bias + TCB_RES + 0));
+          r3[1] = sigmoid_(r1 + __ldg(P.bias + TCB_RES + 1));
+          r3[2] = sigmoid_(r2 + __ldg(P.bias + TCB_RES + 2));
+          a3[0] = sigmoid_(al0 + __ldg(P.bias + TCB_ALB2 + 0));
+          a3[1] = sigmoid_(al1 + __ldg(P.bias + TCB_ALB2 + 1));
+          a3[2] = sigmoid_(al2 + __ldg(P.bias + TCB_ALB2 + 2));
+          const float shd = sigmoid_(shv + __ldg(P.bias + TCB_SH2));
+          const float sigma = sg + __ldg(P.bias + TCB_ALPHA_B);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) grow[i] = __fadd_rn(__fmul_rn(a3[i], shd), r3[i]);
+          grow[3] = sigma;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) grow[4 + i] = a3[i];
+          grow[7] = shd;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) grow[8 + i] = r3[i];
+        }
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");     // scratch is H chunk 3: read before the next layer-0 epilogue
+      if (!sem) ++it_of[s];
+    } else {
+      // ---- semantic logits: 32-column groups round-robin over the column quarters ---------------------------
+      const int64_t tile = ((int64_t)it_of[s] * 2 + s) * gridDim.x + blockIdx.x;
+      const int64_t m = tile * TILE_M + row;
+      const bool valid = m < P.a.M;
+      float* grow = P.a.raw + (valid ? m : 0) * P.out_ch;
+      for (int c0 = cq * 32; c0 < P.C; c0 += 128) {
         uint32_t v[32];
-        tmem_ld32(acc - jj * 32 + c0, v);
+        tmem_ld32(acc - cq * 16 + c0, v);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -831,10 +856,12 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
             if (c0 + i < P.C) grow[INRF_RAW_BASE + c0 + i] = __uint_as_float(v[i]) + __ldg(P.bias + TCB_SEM2 + c0 + i);
         }
       }
-      tc_fence_before();
-      warp_arrive_leader(done, lane);
+      ++it_of[s];
     }
-  }
+    tc_fence_before();
+    warp_arrive_leader(done, lane);
+    PROF_END();
+  });
 #ifdef TC2_PROF
   { const int role = prof_role(); if (role >= 0) { g_prof[role * 64 + 30] = busy; g_prof[role * 64 + 29] = lat_wake; } }
 #endif
@@ -868,7 +895,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ml
     for (int s = 0; s < 2; ++s) {
       const int sb = B_STREAM + 4 * s;
       mbar_init(sy.addr(sb + B_ACC_FULL), 1);
-      mbar_init(sy.addr(sb + B_EPI_DONE), 16);
+      mbar_init(sy.addr(sb + B_EPI_DONE), 32);
       mbar_init(sy.addr(sb + B_XREADY), 8);
       mbar_init(sy.addr(sb + B_XFREE), 1);
     }
@@ -914,7 +941,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_ml
     fe.xready[1] = mapa(sy.addr(B_STREAM + 4 + B_XREADY), 0);
     fe.run();
   } else {
-    epilogue(P, sy, smem, smem_base, tmem, warp >> 3, warp & 3, (warp >> 2) & 1, lane);
+    epilogue(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
   }
 #ifdef TC2_PROF
   { const int role = prof_role(); if (role >= 0) g_prof[role * 64 + 31] = clock64() - t_start; }
