@@ -174,6 +174,19 @@ int inrf_coarse_z(const float* rays, const float* t_vals, const float* t_rand, i
 int inrf_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w_host,
                   float near, float far, float* rays, void* stream);
 
+/* The same for selected pixels and for the SSR fork's create_rays (SSR/models/rays.py:48-76
+ * get_rays_camera, :79-84 get_rays_world, :223-256 create_rays): pix[N] (device) holds flat pixel indices
+ * row*W + column - e.g. sampling_index (rays.py:153-172) or the select_coords / neighbour pairs of
+ * run_nerf.py:913-932; NULL means all H*W pixels in order (N must be H*W).  convention:
+ * INRF_CAM_OPENGL dir = ((i-cx)/fx, -(j-cy)/fy, -1), INRF_CAM_OPENCV dir = ((i-cx)/fx, (j-cy)/fy, 1);
+ * euclidean != 0 normalises the camera-frame direction first (depth_type "euclidean").  This replaces
+ * the precomputed [n_images, H*W, 11] table (608 MB at the Replica config) by on-demand generation. */
+#define INRF_CAM_OPENGL 0
+#define INRF_CAM_OPENCV 1
+int inrf_rays_from_pixels(const int64_t* pix, int64_t N, int H, int W, float fx, float fy, float cx,
+                          float cy, const float* c2w_host, int convention, int euclidean, float near,
+                          float far, float* rays, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Fused renderer: render_rays (run_nerf.py:415-528) / SSRTrainer.volumetric_rendering
  * (SSR/training/trainer.py:717-808) for one chunk of rays.
@@ -249,6 +262,28 @@ int inrf_meanshift_seeds(const float* points, int64_t P, const float* seeds, int
  * NearestNeighbors.kneighbors on the fitted data does).  queries[Q,3] -> kth_dist[Q].      */
 int inrf_kth_neighbor_dist(const float* points, int64_t P, const float* queries, int64_t Q,
                            int k, float* kth_dist, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Fused training losses: img2mse + compute_intrinsic_loss + cluster term
+ * (object_level/run_nerf_helpers.py:11, 15-86; SSR/training/training_utils.py:124-207; composed at
+ * run_nerf.py:975-1017 / trainer.py:913-990).  Maps are given as pointer + row stride in floats so
+ * that the columns of a render record can be passed in place; rgb (and g_rgb) may be NULL.
+ * gt_rgb[N,3]; label[N]: object mask (mode 0) or semantic label as float (mode 1);
+ * target_albedo[N,3] (Cluster.dest_color) or NULL.
+ * losses[8] (device) = { img, chroma, residual, reflect_sparsity, shading_smooth, far_reflect,
+ *                        intensity, cluster }.
+ * Backward: weights[8] (device) are the upstream gradients of those eight scalars (the loss weights
+ * of the step); the gradient of their weighted sum is WRITTEN to g_* (same strides as the maps).
+ * --------------------------------------------------------------------------------- */
+int inrf_intrinsic_loss_fwd(const float* rgb, int ld_rgb, const float* albedo, int ld_alb,
+                            const float* shading, int ld_sh, const float* residual, int ld_res,
+                            const float* gt_rgb, const float* label, const float* target_albedo,
+                            int64_t N, int mode, float* losses, void* stream);
+int inrf_intrinsic_loss_bwd(const float* rgb, int ld_rgb, const float* albedo, int ld_alb,
+                            const float* shading, int ld_sh, const float* residual, int ld_res,
+                            const float* gt_rgb, const float* label, const float* target_albedo,
+                            int64_t N, int mode, const float* weights, float* g_rgb, float* g_albedo,
+                            float* g_shading, float* g_residual, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,9 @@ _SIGS = {
     "inrf_merge_sorted": (i32, [p, p, i64, i32, i32, p, p, p]),
     "inrf_coarse_z": (i32, [p, p, p, i64, i32, i32, p, p]),
     "inrf_get_rays": (i32, [i32, i32, f32, f32, f32, f32, C.POINTER(C.c_float), f32, f32, p, p]),
+    "inrf_intrinsic_loss_fwd": (i32, [p, i32, p, i32, p, i32, p, i32, p, p, p, i64, i32, p, p]),
+    "inrf_intrinsic_loss_bwd": (i32, [p, i32, p, i32, p, i32, p, i32, p, p, p, i64, i32, p, p, p, p, p, p]),
+    "inrf_rays_from_pixels": (i32, [p, i64, i32, i32, f32, f32, f32, f32, C.POINTER(C.c_float), i32, i32, f32, f32, p, p]),
     "inrf_render_workspace_bytes": (i64, [C.POINTER(RenderCfg), i64]),
     "inrf_render_fwd": (i32, [p, i64, p, p, C.POINTER(RenderCfg)] + [p] * 13 + [p, i64, p]),
     "inrf_mapping_color": (i32, [p, i64, f32, p, p]),

@@ -15,7 +15,8 @@ int launch_sample_pdf(const float* bins, const float* weights, int ld_w, const f
                       const float* u_det, int64_t N, int B, int n_samples, float* samples, int64_t* inds, float* cdf_out, cudaStream_t st);
 int launch_merge_sorted(const float* za, const float* zb, int64_t N, int Sa, int Sb, float* zout, float* zstd, cudaStream_t st);
 int launch_zmid(const float* z, int64_t N, int S, float* zmid, cudaStream_t st);
-int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, float nearv, float farv, float* rays, cudaStream_t st);
+int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int opencv, int euclidean,
+                    float nearv, float farv, const int64_t* pix, int64_t n, float* rays, cudaStream_t st);
 
 static int run_mlp(const MlpArgs& a, int precision, cudaStream_t st) {
   if (precision == INRF_PREC_FP32) return launch_mlp_fp32(a, st);
@@ -217,7 +218,18 @@ int inrf_get_rays(int H, int W, float fx, float fy, float cx, float cy, const fl
                   float* rays, void* stream) {
   INRF_CHECK_ARG(H > 0 && W > 0 && c2w_host && rays, "null pointer / bad size");
   INRF_CHECK_ARG(fx != 0.f && fy != 0.f, "zero focal length");
-  return launch_get_rays(H, W, fx, fy, cx, cy, c2w_host, near, far, rays, (cudaStream_t)stream);
+  return launch_get_rays(H, W, fx, fy, cx, cy, c2w_host, 0, 0, near, far, nullptr, (int64_t)H * W, rays, (cudaStream_t)stream);
+}
+
+int inrf_rays_from_pixels(const int64_t* pix, int64_t N, int H, int W, float fx, float fy, float cx, float cy,
+                          const float* c2w_host, int convention, int euclidean, float near, float far, float* rays,
+                          void* stream) {
+  INRF_CHECK_ARG(H > 0 && W > 0 && c2w_host && (rays || N == 0) && N >= 0, "null pointer / bad size");
+  INRF_CHECK_ARG(fx != 0.f && fy != 0.f, "zero focal length");
+  INRF_CHECK_ARG(convention == INRF_CAM_OPENGL || convention == INRF_CAM_OPENCV, "unknown camera convention");
+  INRF_CHECK_ARG(pix != nullptr || N == (int64_t)H * W, "pix == NULL means the full image: N must be H*W");
+  return launch_get_rays(H, W, fx, fy, cx, cy, c2w_host, convention == INRF_CAM_OPENCV, euclidean != 0, near, far, pix, N,
+                         rays, (cudaStream_t)stream);
 }
 
 int64_t inrf_render_workspace_bytes(const InrfRenderCfg* cfg, int64_t N) {

@@ -405,21 +405,31 @@ __global__ void k_zmid(const float* __restrict__ z, int64_t N, int S, float* __r
   }
 }
 
-// get_rays + render()'s ray packing for a full image (run_nerf_helpers.py:359-368, run_nerf.py:100-128)
-struct Cam { float fx, fy, cx, cy, m[12], nearv, farv; };
-__global__ void k_get_rays(int H, int W, Cam c, float* __restrict__ rays) {
-  const int64_t total = (int64_t)H * W;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+// get_rays + render()'s ray packing (run_nerf_helpers.py:359-368, run_nerf.py:100-128) and its SSR twin
+// create_rays (SSR/models/rays.py:48-76 get_rays_camera, :79-84 get_rays_world, :223-256), for a full image
+// (pix == nullptr) or for selected pixels pix[n] = row * W + column (training batches: sampling_index,
+// rays.py:153-172; run_nerf.py:913-932 - the random draws stay with the caller).
+struct Cam { float fx, fy, cx, cy, m[12], nearv, farv; int opencv, euclidean; };
+__global__ void k_get_rays(int H, int W, Cam c, const int64_t* __restrict__ pix, int64_t total, float* __restrict__ rays) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < total; n += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = pix ? pix[n] : n;
+    if (p < 0) p = 0;
+    if (p >= (int64_t)H * W) p = (int64_t)H * W - 1;
     const int j = (int)(p / W), i = (int)(p - (int64_t)j * W);
-    const float dx = __fdiv_rn(__fsub_rn((float)i, c.cx), c.fx);
-    const float dy = -__fdiv_rn(__fsub_rn((float)j, c.cy), c.fy);
-    const float dz = -1.f;
+    float dx = __fdiv_rn(__fsub_rn((float)i, c.cx), c.fx);
+    float dy = __fdiv_rn(__fsub_rn((float)j, c.cy), c.fy);
+    float dz = 1.f;
+    if (!c.opencv) { dy = -dy; dz = -1.f; }          // OpenGL: x right, y up, camera looks along -z
+    if (c.euclidean) {                                 // depth_type == "euclidean": unit camera-frame directions
+      const float inv = __fdiv_rn(1.f, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+      dx = __fmul_rn(dx, inv); dy = __fmul_rn(dy, inv); dz = __fmul_rn(dz, inv);
+    }
     float d[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)      // torch.sum(dirs[..., None, :] * c2w[:3, :3], -1): ((x*m0 + y*m1) + z*m2)
       d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.m[4 * r]), __fmul_rn(dy, c.m[4 * r + 1])), __fmul_rn(dz, c.m[4 * r + 2]));
     const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-    float* o = rays + p * 11;
+    float* o = rays + n * 11;
     o[0] = c.m[3]; o[1] = c.m[7]; o[2] = c.m[11];
     o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
     o[6] = c.nearv; o[7] = c.farv;
@@ -437,12 +447,13 @@ static inline int grid_for(int64_t total, int block, int cap = 148 * 16) {
   return (int)g;
 }
 
-int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, float nearv, float farv,
-                    float* rays, cudaStream_t st) {
+int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int opencv, int euclidean,
+                    float nearv, float farv, const int64_t* pix, int64_t n, float* rays, cudaStream_t st) {
+  if (n == 0) return INRF_OK;
   Cam c;
-  c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy; c.nearv = nearv; c.farv = farv;
+  c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy; c.nearv = nearv; c.farv = farv; c.opencv = opencv; c.euclidean = euclidean;
   for (int i = 0; i < 12; ++i) c.m[i] = c2w[i];
-  k_get_rays<<<grid_for((int64_t)H * W, 256), 256, 0, st>>>(H, W, c, rays);
+  k_get_rays<<<grid_for(n, 256), 256, 0, st>>>(H, W, c, pix, n, rays);
   INRF_LAUNCH_CHECK();
   return INRF_OK;
 }

@@ -9,7 +9,8 @@ from . import object_level as _ol
 from . import ssr as _ssr
 
 _OBJECT_NAMES = ("Embedder", "get_embedder", "NeRF", "sample_pdf", "get_rays", "get_rays_np", "ndc_rays", "batchify",
-                 "run_network", "batchify_rays", "render", "render_rays", "raw2outputs", "create_nerf")
+                 "run_network", "batchify_rays", "render", "render_rays", "raw2outputs", "create_nerf",
+                 "compute_intrinsic_loss")
 
 
 def install_object_level(run_nerf_module, helpers_module=None):
@@ -25,13 +26,15 @@ def install_object_level(run_nerf_module, helpers_module=None):
 def install_ssr(trainer_module=None, model_utils_module=None, rays_module=None, semantic_nerf_module=None):
     if trainer_module is not None:
         _ssr.install_into(trainer_module.SSRTrainer)
-        for name in ("run_network", "raw2outputs", "sample_pdf", "batchify_rays", "get_embedder", "Semantic_NeRF"):
+        for name in ("run_network", "raw2outputs", "sample_pdf", "batchify_rays", "get_embedder", "Semantic_NeRF", "create_rays",
+                     "compute_intrinsic_loss"):
             if hasattr(trainer_module, name):
                 setattr(trainer_module, name, getattr(_ssr, name))
     if model_utils_module is not None:
         model_utils_module.run_network, model_utils_module.raw2outputs = _ssr.run_network, _ssr.raw2outputs
     if rays_module is not None:
         rays_module.sample_pdf = _ssr.sample_pdf
+        rays_module.create_rays = _ssr.create_rays
     if semantic_nerf_module is not None:
         semantic_nerf_module.Semantic_NeRF, semantic_nerf_module.get_embedder = _ssr.Semantic_NeRF, _ssr.get_embedder
         semantic_nerf_module.Embedder = _ssr.Embedder

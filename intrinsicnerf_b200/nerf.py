@@ -113,6 +113,20 @@ class _FieldNet(nn.Module):
         return out.reshape(-1, out.shape[-1])
 
 
+    @torch.no_grad()
+    def query_points(self, pts, viewdirs=None, endpoint=False, pe_scalar_factor=1.0, chunk=1 << 22):
+        """Dense field query (SSR/extract_colour_mesh.py:149-166: 256^3 grid points through the fine network with
+        zero view directions, then marching cubes on the density): raw rows [M, 11 + C (+128)] for pts[M,3] in
+        `chunk`-row launches, everything staying on the device.  viewdirs None = zeros, as the reference passes."""
+        pts = pts.reshape(-1, 3)
+        out = torch.empty(pts.shape[0], ops.RAW_BASE + self.n_classes + (128 if endpoint else 0), dtype=torch.float32, device=pts.device)
+        for i in range(0, pts.shape[0], chunk):
+            p = pts[i:i + chunk]
+            d = torch.zeros_like(p) if viewdirs is None else viewdirs.reshape(-1, 3)[i:i + chunk]
+            out[i:i + chunk] = ops.mlp_forward(self.packed(), self.variant, self.n_classes, p, d, endpoint, pe_scalar_factor)
+        return out
+
+
 class NeRF(_FieldNet):
     variant = NET_OBJECT
 

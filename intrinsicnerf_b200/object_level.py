@@ -198,6 +198,25 @@ def get_rays(H, W, K, c2w):
     return rays_o, rays_d
 
 
+img2mse = lambda x, y: torch.mean((x - y) ** 2)  # noqa: E731  (run_nerf_helpers.py:11)
+
+
+def compute_intrinsic_loss(albedo, shading, residual, gt_rgb, disp, acc, obj_mask):
+    """Mirror of run_nerf_helpers.py:59-86: (chroma, residual, reflect_sparsity, shading_smooth, far_reflect,
+    intensity) - one fused forward launch and one fused backward launch instead of ~40 small kernels each way.
+    disp / acc only feed compute_depth_weight, whose result the reference discards (it passes w_depth = 1)."""
+    t = ops.intrinsic_losses(None, albedo, shading, residual, gt_rgb, obj_mask, None, "object")
+    return t[1], t[2], t[3], t[4], t[5], t[6]
+
+
+def rays_for_pixels(H, W, K, c2w, select_coords, near, far):
+    """Packed [N, 11] ray records for select_coords[N, 2] = (row, column) - the gather of run_nerf.py:913-932
+    (random pixels + their neighbours) fused with get_rays and render()'s packing."""
+    sc = torch.as_tensor(select_coords)
+    pix = (sc[:, 0].long() * W + sc[:, 1].long()).cuda()
+    return ops.rays_from_pixels(pix, H, W, K[0][0], K[1][1], K[0][2], K[1][2], c2w, near, far, "opengl", "z")
+
+
 def get_rays_np(H, W, K, c2w):
     i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing="xy")
     dirs = np.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -np.ones_like(i)], -1)

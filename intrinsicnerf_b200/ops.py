@@ -230,6 +230,55 @@ def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, en
     return raw2outputs_rec(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True)
 
 
+LOSS_TERMS = ("img", "chroma", "residual", "reflect_sparsity", "shading_smooth", "far_reflect", "intensity", "cluster")
+
+
+class IntrinsicLossFn(torch.autograd.Function):
+    """losses[8] = (img, chroma, residual, reflect_sparsity, shading_smooth, far_reflect, intensity, cluster) in one
+    launch, and the gradient of any weighted sum of them in one more (inrf_intrinsic_loss_fwd/_bwd)."""
+
+    @staticmethod
+    def forward(ctx, rgb, albedo, shading, residual, gt_rgb, label, target, mode):
+        albedo, residual, gt_rgb = _f32(albedo.detach(), "albedo"), _f32(residual.detach(), "residual"), _f32(gt_rgb, "gt_rgb")
+        shading = _f32(shading.detach(), "shading").reshape(-1)
+        label = _f32(label.detach().float() if torch.is_tensor(label) else label, "label").reshape(-1)
+        rgb = None if rgb is None else _f32(rgb.detach(), "rgb")
+        target = None if target is None else _f32(target.detach(), "target_albedo")
+        N = albedo.shape[0]
+        if albedo.shape != (N, 3) or residual.shape != (N, 3) or gt_rgb.shape != (N, 3) or shading.numel() != N or label.numel() != N:
+            raise ValueError("intrinsic loss: albedo/residual/gt_rgb must be [N,3], shading/label [N]")
+        losses = torch.empty(8, dtype=torch.float32, device=albedo.device)
+        with torch.cuda.device(albedo.device):
+            check(_lib.lib().inrf_intrinsic_loss_fwd(_ptr(rgb), 3, _ptr(albedo), 3, _ptr(shading), 1, _ptr(residual), 3, _ptr(gt_rgb),
+                                                     _ptr(label), _ptr(target), N, int(mode), _ptr(losses), _stream()))
+        ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in (rgb, albedo, shading, residual, gt_rgb, label, target)])
+        ctx.cfg = (rgb is not None, target is not None, int(mode))
+        return losses
+
+    @staticmethod
+    def backward(ctx, g_losses):
+        rgb, albedo, shading, residual, gt_rgb, label, target = ctx.saved_tensors
+        has_rgb, has_target, mode = ctx.cfg
+        N = albedo.shape[0]
+        w = _f32(g_losses, "grad")
+        g_alb, g_res, g_sh = torch.empty_like(albedo), torch.empty_like(residual), torch.empty_like(shading)
+        g_rgb = torch.empty_like(rgb) if has_rgb else None
+        with torch.cuda.device(albedo.device):
+            check(_lib.lib().inrf_intrinsic_loss_bwd(_ptr(rgb if has_rgb else None), 3, _ptr(albedo), 3, _ptr(shading), 1, _ptr(residual), 3,
+                                                     _ptr(gt_rgb), _ptr(label), _ptr(target if has_target else None), N, mode, _ptr(w),
+                                                     _ptr(g_rgb), _ptr(g_alb), _ptr(g_sh), _ptr(g_res), _stream()))
+        return g_rgb, g_alb, g_sh, g_res, None, None, None, None
+
+
+def intrinsic_losses(rgb, albedo, shading, residual, gt_rgb, label, target_albedo=None, mode="object"):
+    """All loss terms of one training step as a differentiable tensor [8] (order: LOSS_TERMS).  mode "object":
+    label is the object mask (run_nerf_helpers.py:25-37); mode "ssr": label is the semantic class
+    (training_utils.py:141-152).  rgb / target_albedo may be None (their terms are 0)."""
+    if mode not in ("object", "ssr"):
+        raise ValueError("mode must be 'object' or 'ssr'")
+    return IntrinsicLossFn.apply(rgb, albedo, shading.reshape(-1), residual, gt_rgb, label, target_albedo, 0 if mode == "object" else 1)
+
+
 def sample_pdf(bins, weights, n_samples, u=None, want_inds=False, want_cdf=False):
     bins, weights = _f32(bins, "bins"), _f32(weights, "weights")
     N, B = bins.shape
@@ -287,6 +336,30 @@ def get_rays_packed(H, W, K, c2w, near, far, device):
     with torch.cuda.device(device):
         check(_lib.lib().inrf_get_rays(int(H), int(W), float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), arr,
                                        float(near), float(far), _ptr(rays), _stream()))
+    return rays
+
+
+def rays_from_pixels(pix, H, W, fx, fy, cx, cy, c2w, near, far, convention="opengl", depth_type="z", device=None):
+    """Ray records [N, 11] for flat pixel indices pix[N] = row*W + column (None: the whole image), either
+    camera convention (get_rays, run_nerf_helpers.py:359-368 / create_rays, SSR/models/rays.py:223-256)."""
+    if convention not in ("opengl", "opencv") or depth_type not in ("z", "euclidean"):
+        raise ValueError("convention must be 'opengl' or 'opencv', depth_type 'z' or 'euclidean'")
+    m = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].contiguous()
+    arr = (C.c_float * 12)(*[float(v) for v in m.reshape(-1).tolist()])
+    if pix is None:
+        if device is None:
+            raise ValueError("device is required for full-image generation")
+        n = H * W
+    else:
+        if not torch.is_tensor(pix) or not pix.is_cuda:
+            raise RuntimeError("pix: intrinsicnerf_b200 runs on CUDA tensors only; there is no CPU fallback")
+        pix = pix.detach().to(torch.int64).reshape(-1).contiguous()
+        device, n = pix.device, pix.numel()
+    rays = torch.empty(n, 11, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(_lib.lib().inrf_rays_from_pixels(_ptr(pix), n, int(H), int(W), float(fx), float(fy), float(cx), float(cy), arr,
+                                               1 if convention == "opencv" else 0, 1 if depth_type == "euclidean" else 0,
+                                               float(near), float(far), _ptr(rays), _stream()))
     return rays
 
 

@@ -69,6 +69,34 @@ def sample_pdf(bins, weights, N_samples, det=False):
     return ops.sample_pdf(bins, weights, N_samples, u)[0]
 
 
+def compute_intrinsic_loss(albedo, shading, residual, gt_rgb, disp, acc, semantic_label):
+    """Mirror of SSR/training/training_utils.py:179-207 (pairs are weighted only inside one semantic class)."""
+    t = ops.intrinsic_losses(None, albedo, shading, residual, gt_rgb, semantic_label, None, "ssr")
+    return t[1], t[2], t[3], t[4], t[5], t[6]
+
+
+def create_rays(num_rays, Ts_c2w, height, width, fx, fy, cx, cy, near, far, c2w_staticcam=None, depth_type="z",
+                use_viewdirs=True, convention="opencv"):
+    """Mirror of SSR/models/rays.py:223-256: the [num_rays(images), H*W, 11] ray table, generated on the device
+    (one inrf_rays_from_pixels launch per pose instead of meshgrid + bmm + cat on the host)."""
+    if not use_viewdirs or c2w_staticcam is not None:
+        raise NotImplementedError("only use_viewdirs=True without c2w_staticcam (the reference's training / eval setting)")
+    Ts = torch.as_tensor(Ts_c2w, dtype=torch.float32)
+    if Ts.shape[0] != num_rays:
+        raise ValueError("num_rays must equal the number of poses")
+    dev = Ts.device if Ts.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(num_rays, height * width, 11, dtype=torch.float32, device=dev)
+    for b in range(num_rays):
+        out[b] = ops.rays_from_pixels(None, height, width, fx, fy, cx, cy, Ts[b], near, far, convention, depth_type, dev)
+    return out
+
+
+def rays_for_batch(index_hw, T_c2w, height, width, fx, fy, cx, cy, near, far, depth_type="z", convention="opencv"):
+    """Training-batch rays straight from sampling_index's pixel indices (rays.py:153-172) and the chosen image's
+    pose - equals create_rays(...)[index_b, index_hw] without the 608 MB table."""
+    return ops.rays_from_pixels(index_hw.reshape(-1), height, width, fx, fy, cx, cy, T_c2w, near, far, convention, depth_type)
+
+
 def batchify_rays(render_fn, rays_flat, chunk=1024 * 32):
     pieces = {}
     for i in range(0, rays_flat.shape[0], chunk):

@@ -328,6 +328,74 @@ def replica_rays(H=240, W=320, near=0.1, far=10.0, yaw_deg=0.0):
     return torch.cat([o, d, near * torch.ones_like(d[:, :1]), far * torch.ones_like(d[:, :1]), vd], dim=-1).contiguous()
 
 
+def create_rays(Ts_c2w, H, W, fx, fy, cx, cy, near, far, depth_type="z", convention="opencv"):
+    """SSR/models/rays.py:48-76 get_rays_camera + :79-84 get_rays_world + :223-256 create_rays
+    (use_viewdirs=True, no static camera): [B, H*W, 11]."""
+    Ts = torch.as_tensor(Ts_c2w, dtype=torch.float32)
+    B = Ts.shape[0]
+    jj, ii = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    x = (ii - cx) / fx
+    if convention == "opencv":
+        y, z = (jj - cy) / fy, torch.ones_like(ii)
+    else:
+        y, z = -(jj - cy) / fy, -torch.ones_like(ii)
+    dirs = torch.stack((x, y, z), dim=-1)
+    if depth_type == "euclidean":
+        dirs = dirs * (1.0 / torch.norm(dirs, dim=-1, keepdim=True))
+    dirs_C = dirs.reshape(1, -1, 3).expand(B, -1, -1)
+    dirs_W = torch.matmul(Ts[:, None, :3, :3], dirs_C[..., None]).squeeze(-1)
+    origins = Ts[:, None, :3, -1].expand_as(dirs_W)
+    viewdirs = dirs_W / torch.norm(dirs_W, dim=-1, keepdim=True)
+    nr, fr = near * torch.ones_like(dirs_W[..., :1]), far * torch.ones_like(dirs_W[..., :1])
+    return torch.cat([origins, dirs_W, nr, fr, viewdirs], dim=-1)
+
+
+# ----------------------------------------------------------------------------------
+# Training losses (object_level/run_nerf_helpers.py:11-86; SSR/training/training_utils.py:124-207)
+# ----------------------------------------------------------------------------------
+def _chroma(c):
+    s = torch.sum(c, dim=-1) + 1e-5
+    return c[:, 0] / s, c[:, 1] / s
+
+
+def chroma_weight(color1, color2, l1, l2, mode):
+    """compute_chroma_weight: object fork multiplies both weights by the two object masks
+    (run_nerf_helpers.py:25-35); the SSR fork masks only the first by label equality (training_utils.py:141-152)."""
+    r1, g1 = _chroma(color1)
+    r2, g2 = _chroma(color2)
+    dc = (r1 - r2) ** 2 + (g1 - g2) ** 2
+    if mode == "object":
+        return torch.exp(-60 * dc) * l1 * l2, dc * l1 * l2
+    return torch.exp(-60 * dc) * (l1 == l2).to(dc.dtype), dc
+
+
+def intrinsic_losses(rgb, albedo, shading, residual, gt_rgb, label, target_albedo=None, mode="object"):
+    """(img, chroma, residual, reflect_sparsity, shading_smooth, far_reflect, intensity, cluster): img2mse
+    (run_nerf_helpers.py:11), compute_intrinsic_loss (:59-86 / training_utils.py:179-207; the depth weight
+    it computes is replaced by the constant 1 in the calls at :78-79, :83) and the cluster term
+    (run_nerf.py:987-991)."""
+    zero = albedo.new_zeros(())
+    img = torch.mean((rgb - gt_rgb) ** 2) if rgb is not None else zero
+    r1, g1 = _chroma(albedo)
+    r2, g2 = _chroma(gt_rgb)
+    chroma = torch.mean((r1 - r2) ** 2) + torch.mean((g1 - g2) ** 2)
+    resid = torch.mean(residual ** 2)
+    split = albedo.shape[0] // 2
+    a1, a2 = albedo[:split], albedo[-1 * split:]
+    s1, s2 = shading[:split], shading[-1 * split:]
+    c1, c2 = gt_rgb[:split], gt_rgb[-1 * split:]
+    l1, l2 = label[:split], label[-1 * split:]
+    w, w_inv = chroma_weight(c1, c2, l1, l2, mode)
+    reflect = torch.mean(w * torch.sum((a1 - a2) ** 2, dim=-1))
+    shade = torch.mean(w_inv * (s1 - s2) ** 2)
+    split2 = a1.shape[0] // 2
+    wf, _ = chroma_weight(c1[:split2], c1[-1 * split2:], l1[:split2], l1[-1 * split2:], mode)
+    far = torch.mean(wf * torch.sum((a1[:split2] - a1[-1 * split2:]) ** 2, dim=-1))
+    intens = (torch.mean(gt_rgb) - torch.mean(albedo)) ** 2
+    cluster = torch.mean((albedo - target_albedo) ** 2) if target_albedo is not None else zero
+    return torch.stack([img, chroma, resid, reflect, shade, far, intens, cluster])
+
+
 # ----------------------------------------------------------------------------------
 # Synthetic weights (SURVEY section 8d)
 # ----------------------------------------------------------------------------------

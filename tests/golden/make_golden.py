@@ -200,9 +200,13 @@ def main():
     if "--cluster" in sys.argv:
         cluster_fixtures()
         return
+    if "--aux" in sys.argv:
+        aux_fixtures()
+        return
     object_fixtures()
     ssr_fixtures()
     cluster_fixtures()
+    aux_fixtures()
 
 
 def cluster_fixtures():
@@ -222,6 +226,57 @@ def cluster_fixtures():
                         **tonp(dict(pixels=px, anchors=c.anchors, links=c.links, rgb_centers=c.rgb_centers, query=q,
                                     dest_color=dest, dest_class=dcls, mapped=mapped)))
     print("cluster fixtures written:", c.anchors.shape, c.rgb_centers.shape)
+
+
+def aux_fixtures():
+    """Ray generation and training losses of the unmodified reference."""
+    rn, rh, cl = refshim.load_object_level()
+    sn, mu, rays, tr, tu, scl = refshim.load_ssr()
+    out = {}
+    # ---- rays -------------------------------------------------------------------------
+    H, W = 20, 24                                  # create_rays prints rays_cam[0,1,11] and dirs_C[0,331]
+    K = np.array([[22.5, 0, 11.6], [0, 21.75, 9.4], [0, 0, 1]], dtype=np.float32)
+    poses = np.stack([orc.pose_spherical(30.0, -25.0, 3.5), orc.pose_spherical(-110.0, -40.0, 4.25)]).astype(np.float32)
+    ro, rd = rh.get_rays(H, W, K, torch.tensor(poses[0][:3, :4]))
+    out.update(ray_H=np.array(H), ray_W=np.array(W), ray_K=K, ray_poses=poses, obj_rays_o=ro, obj_rays_d=rd)
+    for conv in ("opencv", "opengl"):
+        for dt in ("z", "euclidean"):
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                r = rays.create_rays(2, torch.tensor(poses), H, W, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]),
+                                     0.1, 10.0, use_viewdirs=True, convention=conv, depth_type=("z" if dt == "z" else "euclidean"))
+            out[f"ssr_rays_{conv}_{dt}"] = r
+    # ---- losses -------------------------------------------------------------------------
+    g = torch.Generator().manual_seed(11)
+    for tag, N in (("even", 64), ("odd", 37)):
+        albedo = torch.rand(N, 3, generator=g).double().requires_grad_(True)
+        shading = torch.rand(N, generator=g).double().requires_grad_(True)
+        residual = (torch.rand(N, 3, generator=g) * 0.2).double().requires_grad_(True)
+        rgb = torch.rand(N, 3, generator=g).double().requires_grad_(True)
+        gt = torch.rand(N, 3, generator=g).double()
+        gt[3] = 0.0                                   # black ground-truth pixel: chromaticity 0/1e-5
+        disp, acc = torch.rand(N, generator=g).double(), torch.rand(N, generator=g).double()
+        mask = (torch.rand(N, generator=g) > 0.3).double()
+        label = torch.randint(0, 3, (N,), generator=g)
+        target = torch.rand(N, 3, generator=g).double()
+        wts = torch.tensor([1.0, 1.0, 0.7, 0.01, 0.02, 0.03, 0.5, 0.4], dtype=torch.float64)
+        for fork, fn, lab in (("obj", rh.compute_intrinsic_loss, mask), ("ssr", tu.compute_intrinsic_loss, label)):
+            for t in (albedo, shading, residual, rgb):
+                t.grad = None
+            ch, rs, rf, sh, fr, it = fn(albedo, shading, residual, gt, disp, acc, lab)
+            img = rh.img2mse(rgb, gt)
+            clu = rh.img2mse(albedo, target)
+            terms = torch.stack([img, ch, rs, rf, sh, fr, it, clu])
+            (terms * wts).sum().backward()
+            out.update({f"loss_{fork}_{tag}_terms": terms, f"loss_{fork}_{tag}_g_albedo": albedo.grad.clone(),
+                        f"loss_{fork}_{tag}_g_shading": shading.grad.clone(), f"loss_{fork}_{tag}_g_residual": residual.grad.clone(),
+                        f"loss_{fork}_{tag}_g_rgb": rgb.grad.clone()})
+        out.update({f"loss_{tag}_albedo": albedo, f"loss_{tag}_shading": shading, f"loss_{tag}_residual": residual, f"loss_{tag}_rgb": rgb,
+                    f"loss_{tag}_gt": gt, f"loss_{tag}_mask": mask, f"loss_{tag}_label": label, f"loss_{tag}_target": target,
+                    f"loss_{tag}_disp": disp, f"loss_{tag}_acc": acc})
+    out["loss_weights"] = wts
+    np.savez_compressed(os.path.join(HERE, "aux.npz"), **meta(), **tonp(out))
+    print("aux fixtures written:", len(out), "arrays")
 
 
 if __name__ == "__main__":

@@ -281,3 +281,25 @@ def test_ssr_training_step(dev, golden_dir):
         for name, p in net.named_parameters():
             a, b = ref[name].grad, p.grad.cpu()
             assert float((a - b).abs().max()) < 2e-3 * float(a.abs().max()) + 1e-9, name
+
+
+def test_dense_grid_query_zero_viewdirs(dev):
+    """SURVEY section 8f row 4 (SSR/extract_colour_mesh.py:149-166): grid points through the fine network with
+    zero view directions - the field query of the meshing script as one chunked device call."""
+    from intrinsicnerf_b200 import ops
+    coarse, fine, pc, pf = build_nets("ssr", 28)
+    n = 21
+    ax = torch.linspace(-2.5, 2.5, n)
+    pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    emb = torch.cat([orc.posenc(pts, 10, 10.0), orc.posenc(torch.zeros_like(pts), 4)], -1)
+    want = orc.mlp_forward(pf, emb, "ssr", 28, False)
+    got = fine.query_points(pts.to(dev), pe_scalar_factor=10.0, chunk=4000)
+    assert got.shape == want.shape
+    assert rel_err(got[:, :11], want[:, :11], floor=1e-2) < 2e-3          # tensor-core path, raw (pre-compositing) values
+    assert float((got[:, 11:].cpu() - want[:, 11:]).abs().max()) < 2e-3 * float(want[:, 11:].abs().max())
+    ops.set_default_precision("fp32")
+    try:
+        got32 = fine.query_points(pts.to(dev), pe_scalar_factor=10.0)
+    finally:
+        ops.set_default_precision("tc")
+    assert rel_err(got32[:, :11], want[:, :11], floor=1e-2) < 2e-5

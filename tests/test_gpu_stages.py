@@ -275,3 +275,90 @@ def test_pair_kernel_matches_fp32_kernel():
     out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "tc_debug.py")], env=env, cwd=root,
                          capture_output=True, text=True, timeout=600)
     assert "TC_DEBUG PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- ray generation for whole images and for sampled pixels ------------------------
+@pytest.mark.parametrize("conv", ["opencv", "opengl"])
+@pytest.mark.parametrize("dt", ["z", "euclidean"])
+def test_rays_from_pixels_matches_reference(dev, golden_dir, conv, dt):
+    """inrf_rays_from_pixels vs the reference's create_rays (golden, both conventions and depth types): origins,
+    near/far exact; directions and view directions to 2 ulp of the largest component (the reference rotates with a
+    batched matmul whose summation order is not specified)."""
+    import intrinsicnerf_b200.ssr as ssr
+    g = load_golden(golden_dir, "aux.npz")
+    H, W, K, poses = int(g["ray_H"]), int(g["ray_W"]), g["ray_K"], torch.tensor(g["ray_poses"])
+    want = torch.tensor(g[f"ssr_rays_{conv}_{dt}"])
+    got = ssr.create_rays(2, poses.to(dev), H, W, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), 0.1, 10.0,
+                          depth_type=dt, convention=conv).cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got[..., 0:3], want[..., 0:3]) and torch.equal(got[..., 6:8], want[..., 6:8])
+    assert float((got - want).abs().max()) <= 2.5e-7 * float(want[..., 3:6].abs().max())
+    # sampled pixels (sampling_index layout: n random pixels followed by their clamped neighbours)
+    gen = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, H * W, (1, 50), generator=gen)
+    sub = ssr.rays_for_batch(idx.to(dev), poses[1], H, W, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), 0.1, 10.0,
+                             depth_type=dt, convention=conv).cpu()
+    assert torch.equal(sub, got[1][idx.reshape(-1)])
+
+
+def test_object_rays_for_pixels(dev, golden_dir):
+    """get_rays + gather + packing of run_nerf.py:913-932 in one launch: bit-exact against the reference's get_rays."""
+    import intrinsicnerf_b200.object_level as ol
+    g = load_golden(golden_dir, "aux.npz")
+    H, W, K, pose = int(g["ray_H"]), int(g["ray_W"]), g["ray_K"], g["ray_poses"][0][:3, :4]
+    ro, rd = torch.tensor(g["obj_rays_o"]), torch.tensor(g["obj_rays_d"])
+    gen = torch.Generator().manual_seed(6)
+    coords = torch.stack([torch.randint(0, H, (40,), generator=gen), torch.randint(0, W, (40,), generator=gen)], -1)
+    rays = ol.rays_for_pixels(H, W, K, pose, coords, 2.0, 6.0).cpu()
+    assert torch.equal(rays[:, 0:3], ro[coords[:, 0], coords[:, 1]])
+    assert torch.equal(rays[:, 3:6], rd[coords[:, 0], coords[:, 1]])
+    d = rd[coords[:, 0], coords[:, 1]]
+    assert float((rays[:, 8:11] - d / torch.norm(d, dim=-1, keepdim=True)).abs().max()) <= 2e-7
+    assert torch.equal(rays[:, 6:8], torch.tensor([2.0, 6.0]).expand(40, 2))
+
+
+# ---- SURVEY section 8f row 2: fused training losses ---------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["even", "odd"])
+@pytest.mark.parametrize("fork", ["obj", "ssr"])
+def test_intrinsic_losses_match_reference(dev, golden_dir, fork, tag):
+    """inrf_intrinsic_loss_fwd/_bwd vs the reference's img2mse + compute_intrinsic_loss + cluster term and their
+    autograd gradients (float64 golden; the kernels take fp32 inputs: 2e-5 relative on the terms, 1e-4 of the
+    largest gradient entry per map)."""
+    from intrinsicnerf_b200 import ops
+    g = load_golden(golden_dir, "aux.npz")
+    f = {k: torch.tensor(g[f"loss_{tag}_{k}"]).float().to(dev) for k in ("albedo", "shading", "residual", "rgb", "gt", "mask", "label", "target")}
+    for k in ("albedo", "shading", "residual", "rgb"):
+        f[k].requires_grad_(True)
+    lab = f["mask"] if fork == "obj" else f["label"]
+    terms = ops.intrinsic_losses(f["rgb"], f["albedo"], f["shading"], f["residual"], f["gt"], lab, f["target"], "object" if fork == "obj" else "ssr")
+    want = torch.tensor(g[f"loss_{fork}_{tag}_terms"])
+    assert rel_err(terms.detach(), want, floor=1e-6) < 2e-5, (terms.detach().cpu(), want)
+    (terms * torch.tensor(g["loss_weights"]).float().to(dev)).sum().backward()
+    for k in ("albedo", "shading", "residual", "rgb"):
+        wg = torch.tensor(g[f"loss_{fork}_{tag}_g_{k}"]).float()
+        assert float((f[k].grad.cpu() - wg).abs().max()) < 1e-4 * float(wg.abs().max()), k
+
+
+def test_compute_intrinsic_loss_mirrors(dev, golden_dir):
+    """The reference-named entry points (6 terms, reference order) composed by the caller exactly as in
+    run_nerf.py:975-981, gradients flowing back through views of one render record."""
+    import intrinsicnerf_b200.object_level as ol
+    import intrinsicnerf_b200.ssr as ssr
+    g = load_golden(golden_dir, "aux.npz")
+    wts = torch.tensor(g["loss_weights"]).float()
+    for fork, fn, key in (("obj", ol.compute_intrinsic_loss, "mask"), ("ssr", ssr.compute_intrinsic_loss, "label")):
+        rec = torch.zeros(64, 13, device=dev)
+        rec[:, 5:8] = torch.tensor(g["loss_even_albedo"]).float()
+        rec[:, 8] = torch.tensor(g["loss_even_shading"]).float()
+        rec[:, 9:12] = torch.tensor(g["loss_even_residual"]).float()
+        rec.requires_grad_(True)
+        gt, lab = torch.tensor(g["loss_even_gt"]).float().to(dev), torch.tensor(g[f"loss_even_{key}"]).float().to(dev)
+        terms = fn(rec[:, 5:8], rec[:, 8], rec[:, 9:12], gt, rec[:, 3], rec[:, 4], lab)
+        want = torch.tensor(g[f"loss_{fork}_even_terms"])[1:7]
+        assert rel_err(torch.stack(terms).detach(), want, floor=1e-6) < 2e-5
+        sum(w * t for w, t in zip(wts[1:7].tolist(), terms)).backward()
+        wg = torch.tensor(g[f"loss_{fork}_even_g_albedo"]).float()
+        # the golden albedo gradient also contains the cluster term (weight 0.4): remove it
+        wg = wg - 0.4 * 2 * (torch.tensor(g["loss_even_albedo"]) - torch.tensor(g["loss_even_target"])).float() / (3 * 64)
+        assert float((rec.grad[:, 5:8].cpu() - wg).abs().max()) < 1e-4 * float(wg.abs().max())
+        assert float(rec.grad[:, 0:5].abs().max()) == 0.0

@@ -162,3 +162,32 @@ def test_ssr_endpoint_and_mlp(ssr):
     emb = torch.cat([orc.posenc(t(g["mlp_x"]), 10, 10.0), orc.posenc(t(g["mlp_d"]), 4)], -1)
     close(orc.mlp_forward(f, emb, "ssr", C), g["mlp_out"])
     close(orc.mlp_forward(f, emb, "ssr", C, endpoint=True), g["mlp_out_endpoint"])
+
+
+# ---- ray generation and training losses ------------------------------------
+def test_oracle_rays_match_reference(golden_dir):
+    g = _load(golden_dir, "aux.npz")
+    H, W, K, poses = int(g["ray_H"]), int(g["ray_W"]), g["ray_K"], torch.tensor(g["ray_poses"])
+    ro, rd = orc.get_rays(H, W, K, poses[0][:3, :4])
+    assert torch.equal(ro, torch.tensor(g["obj_rays_o"])) and torch.equal(rd, torch.tensor(g["obj_rays_d"]))
+    for conv in ("opencv", "opengl"):
+        for dt in ("z", "euclidean"):
+            r = orc.create_rays(poses, H, W, float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), 0.1, 10.0, dt, conv)
+            assert torch.equal(r, torch.tensor(g[f"ssr_rays_{conv}_{dt}"])), (conv, dt)
+
+
+@pytest.mark.parametrize("tag", ["even", "odd"])
+@pytest.mark.parametrize("fork", ["obj", "ssr"])
+def test_oracle_losses_match_reference(golden_dir, fork, tag):
+    """oracle.intrinsic_losses == img2mse + compute_intrinsic_loss + cluster term of the reference, values and
+    autograd gradients (float64 fixtures: 1e-12)."""
+    g = _load(golden_dir, "aux.npz")
+    tt = {k: torch.tensor(g[f"loss_{tag}_{k}"]) for k in ("albedo", "shading", "residual", "rgb", "gt", "mask", "label", "target")}
+    for k in ("albedo", "shading", "residual", "rgb"):
+        tt[k].requires_grad_(True)
+    lab = tt["mask"] if fork == "obj" else tt["label"]
+    terms = orc.intrinsic_losses(tt["rgb"], tt["albedo"], tt["shading"], tt["residual"], tt["gt"], lab, tt["target"], "object" if fork == "obj" else "ssr")
+    assert torch.allclose(terms, torch.tensor(g[f"loss_{fork}_{tag}_terms"]), rtol=1e-12, atol=1e-15)
+    (terms * torch.tensor(g["loss_weights"])).sum().backward()
+    for k in ("albedo", "shading", "residual", "rgb"):
+        assert torch.allclose(tt[k].grad, torch.tensor(g[f"loss_{fork}_{tag}_g_{k}"]), rtol=1e-10, atol=1e-14), k
