@@ -285,6 +285,46 @@ int inrf_intrinsic_loss_bwd(const float* rgb, int ld_rgb, const float* albedo, i
                             int64_t N, int mode, const float* weights, float* g_rgb, float* g_albedo,
                             float* g_shading, float* g_residual, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Full-image driver outputs: what render_path does to every rendered frame on the
+ * host after a 48 B/pixel .cpu().numpy() round trip (object_level/run_nerf.py:164-236,
+ * SSR/training/trainer.py:1241-1441), done on the device from the per-ray record so that only 8-bit /
+ * 16-bit planes (and the float maps the caller really returns) leave HBM.
+ *
+ * inrf_frame_finish: rec[H*W, rec_stride] (the INRF_REC layout above) -> any of the planes below
+ * (every pointer nullable):
+ *   to8b(x) = (uint8)(255 * clip(x, 0, 1)), truncating (run_nerf_helpers.py:13; trainer.py:1241-1242);
+ *   rgb8[P,3] albedo8[P,3] shading8[P] residual8[P,3];
+ *   label:  n_classes == 0 (object fork): label = acc > acc_threshold  (run_nerf.py:174 uses 10, i.e. always 0),
+ *           label8 = to8b((float)label) is the 'acc###.png' plane (run_nerf.py:175, 211);
+ *           n_classes  > 0 (SSR fork):    label = argmax_c sem_logits (first maximum; = argmax of the softmax,
+ *           trainer.py:1243), label8 = (uint8)label;
+ *   vis_label8[P,3] = colour_map[label] (uint8 [n_classes,3], trainer.py:1269/1291);
+ *   entropy[P] = -sum softmax*log_softmax (trainer.py:1244), entropy8 = to8b(entropy);
+ *   disp16 = (uint16)disp, depth_mm16 = (uint16)(depth*1000)  (trainer.py:1351-1352; truncation, values
+ *           outside [0, 65535] wrap modulo 2^16 as numpy's C cast does on x86-64, non-finite -> 0);
+ *   labels64[P] int64: the label plane in the dtype Cluster_Manager.dest_color consumes;
+ *   every sub_step-th row and column (albedo[::2, ::2], label[::2, ::2]; run_nerf.py:183-186,
+ *   trainer.py:1330-1334): sample_pixels[ceil(H/s)*ceil(W/s), 3] fp32, sample_labels[...] int64.
+ * --------------------------------------------------------------------------------- */
+typedef struct InrfFramePlanes {
+  uint8_t* rgb8;        uint8_t* albedo8;     uint8_t* shading8;   uint8_t* residual8;
+  uint8_t* label8;      uint8_t* vis_label8;  uint8_t* entropy8;   float*   entropy;
+  uint16_t* disp16;     uint16_t* depth_mm16; int64_t* labels64;
+  float*   sample_pixels;  int64_t* sample_labels;
+  void* reserved[3];
+} InrfFramePlanes;
+
+int inrf_frame_finish(const float* rec, int32_t H, int32_t W, int32_t rec_stride, int32_t n_classes,
+                      float acc_threshold, const uint8_t* colour_map, int32_t sub_step,
+                      const InrfFramePlanes* out, void* stream);
+
+/* Clustered-albedo and edit images of render_path (run_nerf.py:228-240, trainer.py:1425-1441):
+ * cluster_rgb[P,3] = Cluster_Manager.dest_color(albedo, label);  c8 = to8b(cluster_rgb);
+ * edit8 = to8b(cluster_rgb * shading + residual) with shading / residual read from rec.  c8, edit8 nullable. */
+int inrf_edit_recompose(const float* cluster_rgb, const float* rec, int64_t P, int32_t rec_stride,
+                        uint8_t* c8, uint8_t* edit8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

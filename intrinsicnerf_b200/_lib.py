@@ -25,6 +25,13 @@ class RenderCfg(C.Structure):
                 ("reserved", C.c_int32 * 7)]
 
 
+class FramePlanes(C.Structure):
+    """InrfFramePlanes (include/inrf.h): nullable output planes of inrf_frame_finish."""
+    _fields_ = [(n, C.c_void_p) for n in ("rgb8", "albedo8", "shading8", "residual8", "label8", "vis_label8", "entropy8",
+                                          "entropy", "disp16", "depth_mm16", "labels64", "sample_pixels", "sample_labels")] \
+        + [("reserved", C.c_void_p * 3)]
+
+
 _SIGS = {
     "inrf_last_error_string": (C.c_char_p, []),
     "inrf_version": (i32, []),
@@ -56,6 +63,8 @@ _SIGS = {
     "inrf_choose_anchors": (i32, [p, p, i64, p, p, p, p, p]),
     "inrf_meanshift_seeds": (i32, [p, i64, p, i64, f32, i32, p, p, p, p]),
     "inrf_kth_neighbor_dist": (i32, [p, i64, p, i64, i32, p, p]),
+    "inrf_frame_finish": (i32, [p, i32, i32, i32, i32, f32, p, i32, C.POINTER(FramePlanes), p]),
+    "inrf_edit_recompose": (i32, [p, p, i64, i32, p, p, p]),
 }
 
 

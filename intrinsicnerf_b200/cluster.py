@@ -237,13 +237,18 @@ class Cluster_Manager:
 
     def update_center(self, labels, pixels, quantile=0.3, n_samples=5000, band_factor=0.5):
         print("updating clusers...")
-        labels = np.asarray(labels.cpu() if torch.is_tensor(labels) else labels)
-        pixels = np.asarray(pixels.cpu() if torch.is_tensor(pixels) else pixels)
+        on_device = torch.is_tensor(pixels) and pixels.is_cuda      # render_path hands over device tensors: no host trip
+        if on_device:
+            labels = torch.as_tensor(labels).to(pixels.device)
+        else:
+            labels = np.asarray(labels.cpu() if torch.is_tensor(labels) else labels)
+            pixels = np.asarray(pixels.cpu() if torch.is_tensor(pixels) else pixels)
         self.clusters = []
         for i in range(self.class_num):
-            sel = np.ones(len(pixels), dtype=bool) if (self.ssr_semantics and self.class_num == 1) \
-                else np.squeeze(labels == i).reshape(-1)
-            cls_pixels = pixels[sel]
+            if self.ssr_semantics and self.class_num == 1:
+                cls_pixels = pixels
+            else:
+                cls_pixels = pixels[(labels == i).reshape(-1)]
             if len(cls_pixels) == 0:
                 self.clusters.append(None)
                 print("no pixels belong to class:", i)

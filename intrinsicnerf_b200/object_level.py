@@ -277,6 +277,94 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     return [all_ret[k] for k in main] + [{k: v for k, v in all_ret.items() if k not in main}]
 
 
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)  # noqa: E731  (run_nerf_helpers.py:13; host twin of the kernel's)
+
+
+def imwrite(filename, array):
+    """PNG writer of render_path: imageio like the reference when it is installed, else OpenCV (RGB -> BGR)."""
+    array = array.cpu().numpy() if torch.is_tensor(array) else np.asarray(array)
+    try:
+        import imageio
+        imageio.imwrite(filename, array)
+        return
+    except ImportError:
+        pass
+    import cv2
+    cv2.imwrite(filename, array[..., ::-1] if array.ndim == 3 and array.shape[-1] == 3 else array)
+
+
+def render_record(H, W, K, chunk, c2w, near=0., far=1., **kwargs):
+    """One full frame as the packed per-ray record [H*W, 13] (include/inrf.h) - what render() slices its six
+    maps out of, kept whole so that the frame kernels read every pixel once."""
+    fn, fine, q = kwargs.get("network_fn"), kwargs.get("network_fine"), kwargs.get("network_query_fn")
+    n_imp = kwargs.get("N_importance", 0)
+    if isinstance(q, _FusedQuery) and q.fusable_with(fn, fine) and not kwargs.get("perturb", 0.) \
+            and not kwargs.get("raw_noise_std", 0.) and kwargs.get("use_viewdirs", False) and not kwargs.get("ndc", True) \
+            and kwargs.get("c2w_staticcam") is None:
+        dev = next(fn.parameters()).device
+        rays = ops.get_rays_packed(H, W, K, c2w, near, far, dev)
+        pc, pf = fn.packed(), ((fine if fine is not None else fn).packed() if n_imp > 0 else None)
+        recs = []
+        for i in range(0, rays.shape[0], chunk):
+            o = ops.render_chunk(rays[i:i + chunk], pc, pf, variant=fn.variant, n_samples=kwargs["N_samples"], n_importance=n_imp,
+                                 lindisp=kwargs.get("lindisp", False), white_bkgd=kwargs.get("white_bkgd", False),
+                                 pe_scalar_factor=q.embed_fn.scalar_factor)
+            recs.append(o["rec_fine"] if n_imp > 0 else o["rec_coarse"])
+        return recs[0] if len(recs) == 1 else torch.cat(recs, 0)
+    rgb, disp, acc, albedo, shading, residual, _ = render(H, W, K, chunk=chunk, c2w=c2w, near=near, far=far, **kwargs)
+    cols = [rgb, disp[..., None], acc[..., None], albedo, shading[..., None], residual, torch.zeros_like(acc)[..., None]]
+    return torch.cat([c.reshape(H * W, -1) for c in cols], -1).contiguous()
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                update_cluster=False, b_f=0.5):
+    """Mirror of run_nerf.py:142-272 -> (rgbs [n,H,W,3], disps [n,H,W], cluster_manager).  Per frame the
+    reference copies six float maps to the host (48 B/pixel) and converts them with numpy; here the frame's record
+    stays in HBM, inrf_frame_finish writes the 8-bit planes (11 B/pixel cross PCIe, plus the rgb/disp floats this
+    function returns) and the albedo[::2, ::2] cluster samples, and the c###/edit### pass (dest_color +
+    inrf_edit_recompose) runs on the resident records instead of re-uploading every albedo map."""
+    from .cluster import Cluster_Manager
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    H, W = int(H), int(W)
+    kw = dict(render_kwargs)
+    near, far = kw.pop("near", 0.), kw.pop("far", 1.)
+    rgbs, disps, recs, labels, sample_pixels, sample_labels = [], [], [], [], [], []
+    planes = ("rgb8", "albedo8", "shading8", "residual8", "label8") + (("labels64",) if update_cluster else ())
+    for i, c2w in enumerate(render_poses):
+        c2w = torch.as_tensor(c2w)[:3, :4]
+        with torch.no_grad():
+            rec = render_record(H, W, K, chunk, c2w, near=near, far=far, **kw)
+            f = ops.frame_finish(rec, H, W, 0, planes, acc_threshold=10.0, sub_step=2 if update_cluster else 0)
+        rgbs.append(rec[:, 0:3].reshape(H, W, 3).cpu().numpy())
+        disps.append(rec[:, 3].reshape(H, W).cpu().numpy())
+        if i == 0:
+            print(rgbs[-1].shape, disps[-1].shape)
+        if update_cluster:
+            recs.append(rec)
+            labels.append(f["labels64"])
+            sample_pixels.append(f["sample_pixels"])
+            sample_labels.append(f["sample_labels"])
+        if savedir is not None:
+            for prefix, name in (("", "rgb8"), ("a", "albedo8"), ("s", "shading8"), ("res", "residual8"), ("acc", "label8")):
+                imwrite(os.path.join(savedir, "{}{:03d}.png".format(prefix, i)), f[name])
+    cluster_manager = None
+    if update_cluster:
+        sample_pixels, sample_labels = torch.cat(sample_pixels, 0), torch.cat(sample_labels, 0)
+        cluster_manager = Cluster_Manager(class_num=1, device=sample_pixels.device)
+        print(sample_pixels.shape, sample_labels.shape)
+        cluster_manager.update_center(sample_labels, sample_pixels, band_factor=b_f)
+        print("cluster albedo...")
+        for i, rec in enumerate(recs):
+            result = cluster_manager.dest_color(rec[:, 5:8].contiguous(), labels[i].reshape(-1, 1))
+            c8, e8 = ops.edit_recompose(result, rec)
+            if savedir is not None:
+                imwrite(os.path.join(savedir, "c{:03d}.png".format(i)), c8.reshape(H, W, 3))
+                imwrite(os.path.join(savedir, "edit{:03d}.png".format(i)), e8.reshape(H, W, 3))
+    return np.stack(rgbs, 0), np.stack(disps, 0), cluster_manager
+
+
 def create_nerf(args, device=None):
     """-> (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer), with the
     reference's kwargs keys and checkpoint format ('network_fn_state_dict', ...)."""

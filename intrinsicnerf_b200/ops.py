@@ -418,3 +418,56 @@ def render_chunk(rays, packed_coarse, packed_fine, variant=0, n_classes=0, n_sam
                                 _ptr(out.get("z_std")), _ptr(out.get("raw_coarse")), _ptr(out.get("raw_fine")),
                                 _ptr(out.get("z_fine")), _ptr(out.get("weights_fine")), _ptr(ws), ws.numel(), _stream()))
     return out
+
+
+_PLANE_SPEC = {  # name -> (dtype, trailing width)
+    "rgb8": (torch.uint8, 3), "albedo8": (torch.uint8, 3), "shading8": (torch.uint8, 1), "residual8": (torch.uint8, 3),
+    "label8": (torch.uint8, 1), "vis_label8": (torch.uint8, 3), "entropy8": (torch.uint8, 1), "entropy": (torch.float32, 1),
+    "disp16": (torch.uint16, 1), "depth_mm16": (torch.uint16, 1), "labels64": (torch.int64, 1),
+}
+
+
+def frame_finish(rec, H, W, n_classes=0, planes=("rgb8", "albedo8", "shading8", "residual8", "label8"), acc_threshold=10.0,
+                 colour_map=None, sub_step=0):
+    """inrf_frame_finish: the per-ray record of one rendered frame, rec[H*W, >=13+C], -> dict of device planes
+    shaped [H, W(, 3)] (render_path's to8b / uint16 / label / entropy conversions, run_nerf.py:164-215,
+    trainer.py:1241-1389), plus sample_pixels [ceil(H/s)*ceil(W/s), 3] and sample_labels [.., 1] (the
+    albedo[::s, ::s] / label[::s, ::s] sub-sampling that feeds the cluster refresh) when sub_step=s > 0."""
+    rec = _f32(rec, "rec")
+    if rec.ndim != 2 or rec.shape[0] != H * W:
+        raise ValueError("rec must be [H*W, 13 + n_classes (+128)]")
+    dev = rec.device
+    out, tab = {}, _lib.FramePlanes()
+    for name in planes:
+        dt, w = _PLANE_SPEC[name]
+        t = torch.empty((H, W, 3) if w == 3 else (H, W), dtype=dt, device=dev)
+        out[name] = t
+        setattr(tab, name, t.data_ptr())
+    if sub_step > 0:
+        hs, ws = (H + sub_step - 1) // sub_step, (W + sub_step - 1) // sub_step
+        out["sample_pixels"] = torch.empty(hs * ws, 3, dtype=torch.float32, device=dev)
+        out["sample_labels"] = torch.empty(hs * ws, 1, dtype=torch.int64, device=dev)
+        tab.sample_pixels, tab.sample_labels = out["sample_pixels"].data_ptr(), out["sample_labels"].data_ptr()
+    cmap = None
+    if colour_map is not None:
+        cmap = torch.as_tensor(colour_map).to(device=dev, dtype=torch.uint8).contiguous()
+        if cmap.ndim != 2 or cmap.shape[1] != 3 or cmap.shape[0] < n_classes:
+            raise ValueError("colour_map must be uint8 [>= n_classes, 3]")
+    with torch.cuda.device(dev):
+        check(_lib.lib().inrf_frame_finish(_ptr(rec), int(H), int(W), rec.shape[1], int(n_classes), float(acc_threshold),
+                                           _ptr(cmap), int(sub_step), C.byref(tab), _stream()))
+    return out
+
+
+def edit_recompose(cluster_rgb, rec, want_c8=True, want_edit8=True):
+    """inrf_edit_recompose: c8 = to8b(cluster_rgb), edit8 = to8b(cluster_rgb * shading + residual), both [P, 3] uint8
+    (run_nerf.py:228-240, trainer.py:1425-1441)."""
+    cluster_rgb, rec = _f32(cluster_rgb, "cluster_rgb").reshape(-1, 3), _f32(rec, "rec")
+    P = cluster_rgb.shape[0]
+    if rec.ndim != 2 or rec.shape[0] != P:
+        raise ValueError("rec must have one record per pixel")
+    c8 = torch.empty(P, 3, dtype=torch.uint8, device=rec.device) if want_c8 else None
+    e8 = torch.empty(P, 3, dtype=torch.uint8, device=rec.device) if want_edit8 else None
+    with torch.cuda.device(rec.device):
+        check(_lib.lib().inrf_edit_recompose(_ptr(cluster_rgb), _ptr(rec), P, rec.shape[1], _ptr(c8), _ptr(e8), _stream()))
+    return c8, e8

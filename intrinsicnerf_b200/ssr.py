@@ -190,6 +190,110 @@ class SSRRenderer:
                 ret["feat_map_fine"] = rec_f[:, 13 + C:13 + C + 128]
         return ret
 
+    def render_record(self, flat_rays):
+        """Eval-mode frame as the packed record [N, 13+C] (fine pass when N_importance > 0) - the tensor the maps of
+        render_rays are slices of, kept whole for the frame kernels (render_path)."""
+        C = self.num_valid_semantic_class if self.enable_semantic else 0
+        coarse, fine, Sf = self.ssr_net_coarse, self.ssr_net_fine, self.N_importance
+        if not (isinstance(coarse, Semantic_NeRF) and (fine is None or isinstance(fine, Semantic_NeRF))):
+            raise NotImplementedError("render_record needs intrinsicnerf_b200 Semantic_NeRF networks; there is no fallback path")
+        pc, pf = coarse.packed(), ((fine or coarse).packed() if Sf > 0 else None)
+        recs = []
+        for i in range(0, flat_rays.shape[0], self.chunk):
+            o = ops.render_chunk(flat_rays[i:i + self.chunk], pc, pf, variant=coarse.variant, n_classes=C, n_samples=self.N_samples,
+                                 n_importance=Sf, white_bkgd=self.white_bkgd, pe_scalar_factor=self.embed_fn.scalar_factor)
+            recs.append(o["rec_fine"] if Sf > 0 else o["rec_coarse"])
+        return recs[0] if len(recs) == 1 else torch.cat(recs, 0)
+
+    def render_path(self, rays, save_dir=None, update_cluster=False, b_f=0.5):
+        """Mirror of SSRTrainer.render_path (trainer.py:1221-1443) -> the same 12-tuple
+        (rgbs, disps, deps, vis_deps, sems, vis_sems, entropys, vis_entropys, albedos, shadings, residuals,
+        cluster_manager).  Label arg-max, entropy, colour-map lookup, to8b, the uint16 disparity / millimetre depth
+        planes and the albedo[::2, ::2] cluster samples come from one inrf_frame_finish launch per frame on the
+        resident record; dest_color + inrf_edit_recompose produce c###/edit### without re-uploading anything.
+        vis_deps / vis_entropys are imgviz.depth2rgb colourisations (host-side visualisation, a third-party
+        dependency of the reference): produced when imgviz is importable, else None."""
+        import os
+        import numpy as np
+        from .cluster import Cluster_Manager
+        from .object_level import imwrite
+        try:
+            from imgviz import depth2rgb
+        except ImportError:
+            depth2rgb = None
+        H, W = int(self.H_scaled), int(self.W_scaled)
+        sem = bool(self.enable_semantic)
+        C = self.num_valid_semantic_class if sem else 0
+        planes = ["rgb8", "albedo8", "shading8", "residual8", "disp16", "depth_mm16"]
+        if sem:
+            planes += ["label8", "vis_label8", "entropy", "entropy8", "labels64"]
+        keep = {k: [] for k in ("rgb", "disp", "dep", "vis_dep", "sem", "vis_sem", "ent", "vis_ent", "albedo", "shading", "residual")}
+        recs, labels, sample_pixels, sample_labels = [], [], [], []
+        was_training = bool(self.training)
+        self.training = False
+        try:
+            for i in range(len(rays)):
+                with torch.no_grad():
+                    rec = self.render_record(rays[i].reshape(-1, rays[i].shape[-1]))
+                    f = ops.frame_finish(rec, H, W, C, tuple(planes), colour_map=self.valid_colour_map if sem else None,
+                                         sub_step=2 if (update_cluster and sem) else 0)
+                host = rec[:, :13].cpu().numpy()
+                keep["rgb"].append(host[:, 0:3].reshape(H, W, 3))
+                keep["disp"].append(host[:, 3].reshape(H, W))
+                keep["albedo"].append(host[:, 5:8].reshape(H, W, 3))
+                keep["shading"].append(host[:, 8].reshape(H, W))
+                keep["residual"].append(host[:, 9:12].reshape(H, W, 3))
+                keep["dep"].append(host[:, 12].reshape(H, W))
+                if depth2rgb is not None:
+                    keep["vis_dep"].append(depth2rgb(keep["dep"][-1], min_value=self.near, max_value=self.far))
+                if sem:
+                    keep["sem"].append(f["label8"].cpu().numpy())
+                    keep["vis_sem"].append(f["vis_label8"].cpu().numpy())
+                    keep["ent"].append(f["entropy"].cpu().numpy())
+                    if depth2rgb is not None:
+                        keep["vis_ent"].append(depth2rgb(keep["ent"][-1]))
+                if update_cluster:
+                    if not sem:
+                        raise NotImplementedError("update_cluster needs enable_semantic (the reference reads sem_label here)")
+                    recs.append(rec)
+                    labels.append(f["labels64"])
+                    sample_pixels.append(f["sample_pixels"])
+                    sample_labels.append(f["sample_labels"])
+                if i == 0:
+                    print(keep["rgb"][-1].shape, keep["disp"][-1].shape)
+                if save_dir is not None:
+                    assert os.path.exists(save_dir)
+                    for name, plane in (("rgb", "rgb8"), ("disp", "disp16"), ("albedo", "albedo8"), ("shading", "shading8"),
+                                        ("residual", "residual8"), ("depth", "depth_mm16")):
+                        imwrite(os.path.join(save_dir, "{}_{:03d}.png".format(name, i)), f[plane])
+                    if keep["vis_dep"]:
+                        imwrite(os.path.join(save_dir, "vis_depth_{:03d}.png".format(i)), keep["vis_dep"][-1])
+                    if sem:
+                        imwrite(os.path.join(save_dir, "label_{:03d}.png".format(i)), f["label8"])
+                        imwrite(os.path.join(save_dir, "vis_label_{:03d}.png".format(i)), f["vis_label8"])
+                        imwrite(os.path.join(save_dir, "entropy_{:03d}.png".format(i)), f["entropy8"])
+                        if keep["vis_ent"]:
+                            imwrite(os.path.join(save_dir, "vis_entropy_{:03d}.png".format(i)), keep["vis_ent"][-1])
+        finally:
+            self.training = was_training
+        st = lambda k: np.stack(keep[k], 0) if keep[k] else None  # noqa: E731
+        cluster_manager = None
+        if update_cluster:
+            px, lb = torch.cat(sample_pixels, 0), torch.cat(sample_labels, 0)
+            n_cls = 1 if getattr(self, "no_semantic_tree", False) else self.num_valid_semantic_class
+            cluster_manager = Cluster_Manager(class_num=n_cls, ssr_semantics=True, device=px.device)
+            print(px.shape, lb.shape)
+            cluster_manager.update_center(lb, px, band_factor=b_f)
+            print("cluster albedo...")
+            for i, rec in enumerate(recs):
+                result = cluster_manager.dest_color(rec[:, 5:8].contiguous(), labels[i].reshape(-1, 1))
+                c8, e8 = ops.edit_recompose(result, rec)
+                if save_dir is not None:
+                    imwrite(os.path.join(save_dir, "c{:03d}.png".format(i)), c8.reshape(H, W, 3))
+                    imwrite(os.path.join(save_dir, "edit{:03d}.png".format(i)), e8.reshape(H, W, 3))
+        return (st("rgb"), st("disp"), st("dep"), st("vis_dep"), st("sem"), st("vis_sem"), st("ent"), st("vis_ent"),
+                st("albedo"), st("shading"), st("residual"), cluster_manager)
+
     def create_ssr(self):
         cfg = self.config
         embed_fn, input_ch = get_embedder(cfg["render"]["multires"], cfg["render"]["i_embed"], scalar_factor=10)
@@ -215,6 +319,6 @@ class SSRRenderer:
 
 def install_into(trainer_cls):
     """Rebind the hot-path methods of the reference's SSRTrainer."""
-    for name in ("render_rays", "volumetric_rendering", "create_ssr"):
+    for name in ("render_rays", "volumetric_rendering", "_volumetric_rendering_train", "render_record", "render_path", "create_ssr"):
         setattr(trainer_cls, name, getattr(SSRRenderer, name))
     return trainer_cls

@@ -203,10 +203,14 @@ def main():
     if "--aux" in sys.argv:
         aux_fixtures()
         return
+    if "--frame" in sys.argv:
+        frame_fixtures()
+        return
     object_fixtures()
     ssr_fixtures()
     cluster_fixtures()
     aux_fixtures()
+    frame_fixtures()
 
 
 def cluster_fixtures():
@@ -277,6 +281,152 @@ def aux_fixtures():
     out["loss_weights"] = wts
     np.savez_compressed(os.path.join(HERE, "aux.npz"), **meta(), **tonp(out))
     print("aux fixtures written:", len(out), "arrays")
+
+
+def _edge_maps(H, W, g):
+    """Synthetic frame maps that exercise to8b's corners: <0, >1, exactly 0/1, k/255 boundaries, NaN."""
+    r = lambda *sh: (torch.rand(*sh, generator=g) * 1.4 - 0.2)  # noqa: E731
+    rgb, albedo, shading, residual = r(H, W, 3), r(H, W, 3), r(H, W), r(H, W, 3) * 0.3
+    k = torch.arange(W).float()
+    rgb[0, :, 0] = k / 255.0
+    rgb[0, :, 1] = (k + 100) / 255.0
+    rgb[1, :, 0] = torch.nextafter(k / 255.0, torch.tensor(0.0))
+    rgb[1, :, 1] = torch.nextafter((k + 200) / 255.0, torch.tensor(2.0))
+    rgb[2, 0], rgb[2, 1], rgb[2, 2] = 0.0, 1.0, float("nan")
+    albedo[3, 0] = 0.0                                   # black albedo pixel: mapping_color -> NaN
+    shading[2, 3] = float("nan")
+    return rgb, albedo, shading, residual
+
+
+def frame_fixtures():
+    """What the unmodified render_path of both forks hands to imageio.imwrite / Cluster_Manager for given frame maps
+    (SURVEY section 8f row 3).  render()/render_rays() are replaced by recorded maps (one frame really rendered by the
+    reference network, one synthetic edge-case frame); everything after them is the reference's own code."""
+    import contextlib
+    import io
+    rn, rh, cl = refshim.load_object_level()
+    sn, mu, rays_mod, tr, tu, scl = refshim.load_ssr()
+    out = {}
+    written = {}
+
+    class _IO:
+        @staticmethod
+        def imwrite(filename, arr, *a, **k):
+            written[os.path.basename(filename)] = np.array(arr)
+
+    # ---------------- object fork --------------------------------------------------------------------------
+    os.makedirs("/tmp/_inrf_ref_logs/x", exist_ok=True)
+    torch.manual_seed(SEED)
+    kw_train, kw_test, *_ = rn.create_nerf(refshim.object_args())
+    opaque_(kw_test["network_fn"]), opaque_(kw_test["network_fine"])
+    H, W = 12, 16
+    K = np.array([[18.0, 0, 8.0], [0, 18.0, 6.0], [0, 0, 1]], dtype=np.float32)
+    pose = torch.tensor(orc.pose_spherical(40.0, -30.0, 4.0)).float()
+    with torch.no_grad():
+        real = rn.render(H, W, K, chunk=4096, c2w=pose[:3, :4], near=2., far=6., **kw_test)[:6]
+    g = torch.Generator().manual_seed(5)
+    rgb, albedo, shading, residual = _edge_maps(H, W, g)
+    acc = torch.rand(H, W, generator=g) * 12.0           # some pixels above the (sic) threshold of 10
+    disp = torch.rand(H, W, generator=g) * 3.0
+    frames = [tuple(real), (rgb, disp, acc, albedo, shading, residual)]
+    it = iter(frames)
+    calls = {}
+
+    class CM(cl.Cluster_Manager):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+
+        def update_center(self, labels, pixels, **k):
+            calls["uc_labels"], calls["uc_pixels"], calls["uc_kw"] = np.array(labels), np.array(pixels), dict(k)
+            self.clusters = [None]
+
+        def dest_color(self, rgb, label):
+            calls.setdefault("dc_label", []).append(label.clone())
+            res = torch.flip(rgb, dims=[-1]) * 0.9 + 0.05      # a recorded stand-in for the cluster lookup
+            calls.setdefault("dc_result", []).append(res.clone())
+            return res
+    saved = (rn.render, rn.imageio, rn.Cluster_Manager, rn.tqdm)
+    rn.render = lambda *a, **k: list(next(it)) + [{}]
+    rn.imageio, rn.Cluster_Manager, rn.tqdm = _IO, CM, (lambda x: x)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            rgbs, disps, _ = rn.render_path([pose, pose], (H, W, 18.0), K, 4096, {}, savedir="/tmp", update_cluster=True)
+    finally:
+        rn.render, rn.imageio, rn.Cluster_Manager, rn.tqdm = saved
+    for i, fr in enumerate(frames):
+        for name, v in zip(("rgb", "disp", "acc", "albedo", "shading", "residual"), fr):
+            out[f"obj{i}_{name}"] = v
+        for prefix, key in (("", "rgb8"), ("a", "albedo8"), ("s", "shading8"), ("res", "residual8"), ("acc", "label8"),
+                            ("c", "c8"), ("edit", "edit8")):
+            out[f"obj{i}_{key}"] = written["{}{:03d}.png".format(prefix, i)]
+        out[f"obj{i}_dc_label"], out[f"obj{i}_dc_result"] = calls["dc_label"][i], calls["dc_result"][i]
+    out.update(obj_uc_labels=calls["uc_labels"], obj_uc_pixels=calls["uc_pixels"], obj_rgbs=rgbs, obj_disps=disps)
+
+    # ---------------- SSR fork -----------------------------------------------------------------------------
+    written.clear()
+    calls.clear()
+    C = 6
+    H, W = 10, 14
+    cmap = (torch.rand(C, 3, generator=g) * 255).to(torch.uint8)
+    sframes = []
+    for i in range(2):
+        rgb, albedo, shading, residual = _edge_maps(H, W, g)
+        disp = torch.rand(H, W, generator=g) * 900.0
+        depth = torch.rand(H, W, generator=g) * 9.0
+        logits = torch.randn(H, W, C, generator=g) * 3.0
+        if i == 1:
+            logits[0, 0] = 0.5                              # an exact tie: first maximum wins
+            logits[0, 1, 2], logits[0, 1, 4] = 7.0, 7.0
+        sframes.append(dict(rgb_fine=rgb.reshape(-1, 3), disp_fine=disp.reshape(-1), depth_fine=depth.reshape(-1),
+                            albedo_fine=albedo.reshape(-1, 3), shading_fine=shading.reshape(-1), residual_fine=residual.reshape(-1, 3),
+                            sem_logits_fine=logits.reshape(-1, C)))
+    t = tr.SSRTrainer.__new__(tr.SSRTrainer)
+    t.enable_semantic, t.N_importance, t.valid_colour_map = True, 128, cmap
+    t.H_scaled, t.W_scaled, t.near, t.far, t.num_valid_semantic_class, t.no_semantic_tree = H, W, 0.1, 10.0, C, False
+    sit = iter(sframes)
+
+    def fake_render_rays(r):
+        d = next(sit)
+        d = dict(d)
+        for k in list(d):
+            d[k.replace("_fine", "_coarse")] = d[k]
+        return d
+    t.render_rays = fake_render_rays
+
+    class SCM(scl.Cluster_Manager):
+        def update_center(self, labels, pixels, **k):
+            calls["uc_labels"], calls["uc_pixels"] = np.array(labels), np.array(pixels)
+            self.clusters = [None] * self.class_num
+
+        def dest_color(self, rgb, label):
+            calls.setdefault("dc_label", []).append(label.clone())
+            res = torch.flip(rgb, dims=[-1]) * 0.8 + 0.1
+            calls.setdefault("dc_result", []).append(res.clone())
+            return res
+    saved = (tr.imageio, tr.Cluster_Manager, tr.tqdm, tr.depth2rgb)
+    tr.imageio, tr.Cluster_Manager, tr.tqdm = _IO, SCM, (lambda x: x)
+    tr.depth2rgb = lambda x, **k: np.zeros(x.shape + (3,), np.uint8)   # imgviz is absent here; its output is not pinned
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = t.render_path([None, None], save_dir="/tmp", update_cluster=True)
+    finally:
+        tr.imageio, tr.Cluster_Manager, tr.tqdm, tr.depth2rgb = saved
+    names = ("rgbs", "disps", "deps", "vis_deps", "sems", "vis_sems", "entropys", "vis_entropys", "albedos", "shadings", "residuals")
+    for n, v in zip(names, res[:11]):
+        if n not in ("vis_deps", "vis_entropys"):         # imgviz.depth2rgb is a stub here
+            out["ssr_" + n] = v
+    for i, fr in enumerate(sframes):
+        for k, v in fr.items():
+            out[f"ssr{i}_{k}"] = v
+        for fname, key in (("rgb_", "rgb8"), ("disp_", "disp16"), ("albedo_", "albedo8"), ("shading_", "shading8"),
+                           ("residual_", "residual8"), ("depth_", "depth_mm16"), ("label_", "label8"), ("vis_label_", "vis_label8"),
+                           ("entropy_", "entropy8"), ("c", "c8"), ("edit", "edit8")):
+            out[f"ssr{i}_{key}"] = written["{}{:03d}.png".format(fname, i)]
+        out[f"ssr{i}_dc_label"], out[f"ssr{i}_dc_result"] = calls["dc_label"][i], calls["dc_result"][i]
+    out.update(ssr_uc_labels=calls["uc_labels"], ssr_uc_pixels=calls["uc_pixels"], ssr_colour_map=cmap,
+               ssr_H=np.array(H), ssr_W=np.array(W), ssr_C=np.array(C))
+    np.savez_compressed(os.path.join(HERE, "frame.npz"), **meta(), **tonp(out))
+    print("frame fixtures written:", len(out), "arrays")
 
 
 if __name__ == "__main__":

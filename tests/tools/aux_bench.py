@@ -75,3 +75,44 @@ fused(); ga = alb.grad.clone(); eager()
 err = float((ga - alb.grad).abs().max() / alb.grad.abs().max())
 print(f"AUX losses fwd+bwd, N={N}: fused kernels {t_f:.1f} us vs eager PyTorch composition {t_e:.1f} us ({t_e / t_f:.1f}x), "
       f"albedo-gradient difference {err:.1e}")
+
+# ---- frame: render_path's per-frame conversions on an 800x800 record (section 8f row 3) -----------------------
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+from oracle import frame_oracle as fo  # noqa: E402
+
+rec = torch.rand(H * W, 13, generator=g).to(dev)
+planes = ("rgb8", "albedo8", "shading8", "residual8", "label8", "labels64")
+t_fr = timeit(lambda: ops.frame_finish(rec, H, W, 0, planes, sub_step=2))
+nbytes = H * W * (52 + 11 + 8) + (H // 2) * (W // 2) * 20
+host8 = [torch.empty(H, W, c, dtype=torch.uint8).pin_memory() for c in (3, 3, 1, 3, 1)]
+
+
+def ours_e2e():
+    f = ops.frame_finish(rec, H, W, 0, planes, sub_step=2)
+    for dst, k in zip(host8, planes[:5]):
+        dst.copy_(f[k].reshape(dst.shape), non_blocking=True)
+    torch.cuda.synchronize()
+
+
+def reference_style():
+    m = [rec[:, 0:3], rec[:, 5:8], rec[:, 8], rec[:, 9:12], rec[:, 4]]
+    host = [x.reshape(H, W, -1).cpu().numpy() for x in m]           # .cpu().numpy() per map (run_nerf.py:168-174)
+    out = [fo.to8b(x) for x in host[:4]]
+    label = (host[4] > 10).astype(int)
+    out.append(fo.to8b(label.astype(np.float32)))
+    return out, host[1][::2, ::2, :].reshape(-1, 3), label[::2, ::2].reshape(-1, 1)
+
+
+def wall(fn, reps=10):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+print(f"AUX frame 800x800: inrf_frame_finish {t_fr:.1f} us ({nbytes / t_fr / 1e3:.0f} GB/s moved); per-frame host hand-over "
+      f"{wall(ours_e2e):.2f} ms (kernel + D2H of 11 B/pixel) vs reference-style D2H of float maps + numpy to8b {wall(reference_style):.2f} ms")
