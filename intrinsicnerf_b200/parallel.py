@@ -66,3 +66,102 @@ def render_rays_sharded(rays, render_fn, group=None, gather=True):
         full = gather_records(flat.contiguous(), rays.shape[0], group)
         out[k] = full.reshape((rays.shape[0],) + tuple(v.shape[1:]))
     return out
+
+
+def render_frame_pipelined(rays, record_fn, chunk, group=None):
+    """Full frame on every rank with the gather overlapped: rank r renders its ray_shard() slice chunk by chunk
+    (`record_fn(rays_chunk) -> [n, R]` packed per-ray records) and the all-gather of chunk k (NCCL, its own stream,
+    async_op) runs while chunk k+1 is computed - SURVEY 8e: the collective moves 52 B/ray and is latency-bound, so
+    it is hidden behind the 340 MFLOP/ray of compute instead of being paid at the end of the frame.
+    Returns [N, R] on every rank, bit-identical to the single-process frame (rays are independent)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = rays.shape[0]
+    spans = [ray_shard(n, r, world) for r in range(world)]
+    a, b = spans[rank]
+    if world == 1:
+        parts = [record_fn(rays[i:min(i + chunk, n)]) for i in range(0, n, chunk)]
+        return parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+    steps = max((hi - lo + chunk - 1) // chunk for lo, hi in spans)
+    out, pending = None, None
+
+    def drain(p):
+        work, buf, k = p
+        work.wait()
+        for r, (lo, hi) in enumerate(spans):
+            s0 = lo + k * chunk
+            s1 = min(s0 + chunk, hi)
+            if s1 > s0:
+                out[s0:s1] = buf[r, : s1 - s0]
+    for k in range(steps):
+        s0 = a + k * chunk
+        s1 = min(s0 + chunk, b)
+        rec = record_fn(rays[s0:s1]) if s1 > s0 else None
+        if out is None:
+            # record width: known from the first non-empty local chunk; ranks with an empty shard learn it from rank 0
+            width = torch.tensor([rec.shape[1] if rec is not None else 0], device=rays.device)
+            dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)
+            R = int(width.item())
+            out = rays.new_empty(n, R)
+        send = rays.new_zeros(chunk, R)
+        if rec is not None:
+            send[: rec.shape[0]] = rec
+        buf = rays.new_empty(world, chunk, R)
+        work = dist.all_gather_into_tensor(buf.view(world * chunk, R), send, group=group, async_op=True)
+        if pending is not None:
+            drain(pending)               # chunk k-1 landed while chunk k was being rendered
+        pending = (work, buf, k)
+    if pending is not None:
+        drain(pending)
+    return out
+
+
+class _GatherRows(torch.autograd.Function):
+    """all-gather of ray_shard() row slices with a gradient: backward hands each rank the rows it contributed."""
+
+    @staticmethod
+    def forward(ctx, local, n_total, group):
+        ctx.span = ray_shard(n_total, dist.get_rank(group), dist.get_world_size(group))
+        return gather_records(local.contiguous(), n_total, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.span
+        return g[a:b].contiguous(), None, None
+
+
+def gather_maps_for_loss(local_maps, n_total, group=None):
+    """Training (BASELINE config 5): every rank renders ray_shard(n_total) of the step's rays; the losses pair ray i
+    with ray i + N/2 and with rays of another quarter (compute_intrinsic_loss, training_utils.py:201-205), so the
+    rendered maps (N x ~(14+C) floats, ~170 KB) are all-gathered and every rank evaluates the same full-batch loss.
+    The backward pass returns each rank the gradient rows of its own rays; allreduce_gradients(SUM) then yields
+    exactly the single-process gradient."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dict(local_maps)
+    out = {}
+    for k in sorted(local_maps):
+        v = local_maps[k]
+        flat = v.reshape(v.shape[0], -1)
+        full = _GatherRows.apply(flat, n_total, group)
+        out[k] = full.reshape((n_total,) + tuple(v.shape[1:]))
+    return out
+
+
+def allreduce_gradients(modules, group=None, average=False):
+    """One flat bucket for all parameter gradients of the coarse + fine networks (1.32 M fp32 = 5.3 MB):
+    a single all-reduce instead of one per parameter tensor."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    params = [p for m in modules for p in m.parameters() if p.requires_grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        k = p.numel()
+        p.grad.copy_(flat[off:off + k].view_as(p.grad))
+        off += k

@@ -45,6 +45,28 @@ def _worker(rank, world, port, n, q):
     w = [torch.zeros_like(lin.weight) for _ in range(world)]
     dist.all_gather(w, lin.weight.data)
     ok &= all(torch.equal(w[0], x) for x in w) and bool(w[0].abs().sum() > 0)
+    # chunk-pipelined frame gather: every rank ends with the single-process frame
+    rec_fn = lambda r: torch.cat([torch.sin(r[:, :3]) + r[:, 3:6], r[:, 6:8] * 2], 1)  # noqa: E731
+    for chunk in (128, 256, 4096):
+        ok &= torch.equal(parallel.render_frame_pipelined(rays, rec_fn, chunk), rec_fn(rays))
+    # data-parallel training step: gathered maps + summed gradients == single-process gradients
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(11, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    ref_net = torch.nn.Sequential(torch.nn.Linear(11, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    ref_net.load_state_dict(net.state_dict())
+
+    def loss_fn(m):          # pairs ray i with ray i + N/2 like compute_intrinsic_loss
+        h = m["rgb"].shape[0] // 2
+        return ((m["rgb"][:h] - m["rgb"][h:2 * h]) ** 2).mean() + m["acc"].mean()
+    full_out = ref_net(rays)
+    loss_fn({"rgb": full_out[:, :3], "acc": full_out[:, 3]}).backward()
+    a, b = parallel.ray_shard(n, rank, world)
+    loc = net(rays[a:b])
+    maps = parallel.gather_maps_for_loss({"rgb": loc[:, :3], "acc": loc[:, 3]}, n)
+    loss_fn(maps).backward()
+    parallel.allreduce_gradients([net])
+    for p, q_ in zip(net.parameters(), ref_net.parameters()):
+        ok &= bool(torch.allclose(p.grad, q_.grad, rtol=1e-5, atol=1e-6))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
