@@ -141,7 +141,10 @@ def gather_maps_for_loss(local_maps, n_total, group=None):
     out = {}
     for k in sorted(local_maps):
         v = local_maps[k]
-        flat = v.reshape(v.shape[0], -1)
+        width = 1
+        for d in v.shape[1:]:
+            width *= int(d)
+        flat = v.reshape(v.shape[0], width)          # explicit width: an empty shard has 0 rows
         full = _GatherRows.apply(flat, n_total, group)
         out[k] = full.reshape((n_total,) + tuple(v.shape[1:]))
     return out
