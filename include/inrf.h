@@ -123,6 +123,21 @@ int inrf_mlp_bwd(const float* flat_params, int variant, int n_classes, int endpo
                  const float* emb, int64_t M, const float* raw, const float* stash, const float* grad_raw,
                  float* grad_flat, void* stream);
 
+/* Tensor-core training forward / backward (INRF_PREC_TC arithmetic: fp16 operands, fp32 accumulation).
+ * The forward is the inference kernel with one addition: every activation tile is also written to
+ * `stash_img` (inrf_mlp_stash_img_bytes(M) bytes) as 16 KB images of the tensor-core operand chunks.  The backward
+ * walks those images with tcgen05 GEMMs (dX chain, then all dW in one launch) and ACCUMULATES dL/d(parameters)
+ * into grad_flat like inrf_mlp_bwd; `workspace` needs inrf_mlp_bwd_tc_workspace_bytes(variant, n_classes, M) bytes.
+ * Gradients are scaled on the device by a power of two derived from max|grad_raw| so that fp16 holds them. */
+int64_t inrf_mlp_stash_img_bytes(int64_t M);
+int64_t inrf_mlp_bwd_tc_workspace_bytes(int variant, int n_classes, int64_t M);
+int inrf_mlp_fwd_train_tc(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
+                          const float* pts, const float* viewdirs, const float* rays, const float* z, int S,
+                          const float* emb, int64_t M, float* raw, void* stash_img, void* stream);
+int inrf_mlp_bwd_tc(const void* packed, const float* flat_params, int variant, int n_classes, int endpoint_feat,
+                    int64_t M, const float* raw, const void* stash_img, const float* grad_raw, void* workspace,
+                    int64_t workspace_bytes, float* grad_flat, void* stream);
+
 /* raw2outputs (run_nerf.py:359-412; model_utils.py:39-116).
  * raw[N,S,ch], z[N,S], rays_d given as rays_d[N,ld] with row stride ld floats (ld=3 for a
  * packed [N,3] tensor, 11 to address columns 3:6 of a ray record - pass rays+3).

@@ -45,6 +45,10 @@ _SIGS = {
     "inrf_stash_floats_per_row": (i64, []),
     "inrf_mlp_fwd_train": (i32, [p, i32, i32, i32, f32, p, p, p, p, i32, p, i64, p, p, p]),
     "inrf_mlp_bwd": (i32, [p, i32, i32, i32, f32, p, p, p, p, i32, p, i64, p, p, p, p, p]),
+    "inrf_mlp_stash_img_bytes": (i64, [i64]),
+    "inrf_mlp_bwd_tc_workspace_bytes": (i64, [i32, i32, i64]),
+    "inrf_mlp_fwd_train_tc": (i32, [p, i32, i32, i32, f32, p, p, p, p, i32, p, i64, p, p, p]),
+    "inrf_mlp_bwd_tc": (i32, [p, p, i32, i32, i32, i64, p, p, p, p, i64, p, p]),
     "inrf_raw2outputs": (i32, [p, p, p, i32, p, i64, i32, i32, i32, i32, p, p, p]),
     "inrf_raw2outputs_bwd": (i32, [p, p, p, i32, p, i64, i32, i32, i32, i32, p, p, p, p]),
     "inrf_sample_pdf": (i32, [p, p, i32, p, p, i64, i32, i32, p, p, p, p]),

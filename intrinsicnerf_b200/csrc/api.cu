@@ -158,6 +158,41 @@ int inrf_mlp_bwd(const float* flat_params, int variant, int n_classes, int endpo
   return launch_mlp_bwd_fp32(b, (cudaStream_t)stream);
 }
 
+int64_t inrf_mlp_stash_img_bytes(int64_t M) { return M <= 0 ? 0 : (M + 127) / 128 * IMG_STASH_SLOTS * (int64_t)IMG_BYTES; }
+int64_t inrf_mlp_bwd_tc_workspace_bytes(int variant, int n_classes, int64_t M) { return tc_bwd_workspace_bytes(variant, n_classes, M < 0 ? 0 : M); }
+
+int inrf_mlp_fwd_train_tc(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
+                          const float* pts, const float* viewdirs, const float* rays, const float* z, int S, const float* emb,
+                          int64_t M, float* raw, void* stash_img, void* stream) {
+  INRF_CHECK_ARG(M >= 0 && packed && (M == 0 || (raw && stash_img)), "null pointer / negative size");
+  INRF_CHECK_ARG(pe_scalar_factor > 0.f, "pe_scalar_factor must be positive");
+  INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
+  if (M == 0) return INRF_OK;
+  MlpArgs a{};
+  int rc = fill_addressing(a, pts, viewdirs, rays, z, S, emb);
+  if (rc) return rc;
+  a.packed = packed; a.variant = variant; a.n_classes = n_classes; a.endpoint = endpoint_feat ? 1 : 0;
+  a.pe_scale = pe_scalar_factor; a.M = M; a.raw = raw; a.stash_img = static_cast<unsigned char*>(stash_img);
+  return launch_mlp_tc(a, (cudaStream_t)stream);
+}
+
+int inrf_mlp_bwd_tc(const void* packed, const float* flat_params, int variant, int n_classes, int endpoint_feat, int64_t M,
+                    const float* raw, const void* stash_img, const float* grad_raw, void* workspace, int64_t workspace_bytes,
+                    float* grad_flat, void* stream) {
+  INRF_CHECK_ARG(M >= 0 && packed && flat_params && grad_flat && (M == 0 || (raw && stash_img && grad_raw && workspace)),
+                 "null pointer / negative size");
+  INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
+  if (M == 0) return INRF_OK;
+  if (workspace_bytes < tc_bwd_workspace_bytes(variant, n_classes, M)) { set_error("inrf_mlp_bwd_tc: workspace too small"); return INRF_EWORKSPACE; }
+  INRF_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(stash_img) & 255) == 0,
+                 "stash / workspace must be 256-byte aligned");      // bulk copies need 16 B; the images carry their own swizzle
+  TcBwdArgs b{};
+  b.packed = packed; b.flat = flat_params; b.variant = variant; b.n_classes = n_classes; b.endpoint = endpoint_feat ? 1 : 0;
+  b.M = M; b.raw = raw; b.grad_raw = grad_raw; b.stash_img = static_cast<const unsigned char*>(stash_img);
+  b.work = static_cast<unsigned char*>(workspace); b.grad_flat = grad_flat;
+  return launch_mlp_bwd_tc(b, (cudaStream_t)stream);
+}
+
 int inrf_mlp_fwd_rays(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
                       const float* rays, const float* z, int64_t N, int S, float* raw, int precision, void* stream) {
   INRF_CHECK_ARG(N >= 0 && S > 0 && packed && (N == 0 || (rays && z && raw)), "null pointer / bad size");

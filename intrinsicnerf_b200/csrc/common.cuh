@@ -141,7 +141,22 @@ struct MlpArgs {
   int64_t M;                 // total rows (N*S in ray mode)
   float* raw;                // [M,out_ch]
   float* stash;              // optional [M, STASH_LD] fp32 activations for the backward pass (fp32 path only)
+  unsigned char* stash_img;  // optional tensor-core training stash: IMG_STASH_SLOTS chunk images per 128-row tile
 };
+
+// ---------------------------------------------------------------------------------
+// Tensor-core training path (mlp_tc.cu forward with stash, train_tc.cu backward).
+// Every activation / gradient tile that a GEMM consumes lives in HBM as the exact image of the shared-memory
+// operand chunk: 128 rows x 64 fp16 in the UMMA SWIZZLE_128B layout (8-row atoms of 1024 B, 16-byte unit index
+// XOR (row & 7)), 16 KB.  The same image is a K-major operand (rows = M/N, columns = K: the dX GEMMs) and an
+// MN-major operand (columns = M/N, rows = K: the dW GEMMs), so plain cp.async.bulk copies feed both.
+// ---------------------------------------------------------------------------------
+constexpr int IMG_BYTES = 16384;
+// forward stash slots of one tile
+constexpr int IS_PE = 0, IS_DIR = 1, IS_H = 2 /* + 4*layer + chunk */, IS_V = 34, IS_AS = 36, IS_S1 = 40, IMG_STASH_SLOTS = 42;
+// backward workspace slots of one tile: G = head gradients (g_albedo[0:3] g_shading[3] g_residual[4:7] g_sigma[7]
+// g_sem[8:8+C]), dZ of albedo1|shading1, views', sem1 and of the eight trunk layers
+constexpr int IB_G = 0, IB_DAS = 2, IB_DV = 6, IB_DS1 = 8, IB_DZ = 10 /* + 4*layer + chunk */, IMG_BWD_SLOTS = 42;
 // training stash (fp32, per sample row): post-ReLU outputs of the 8 trunk layers, the feature vector,
 // relu(albedo1|shading1), relu(views) and relu(sem1)
 constexpr int ST_H = 0, ST_FEAT = 2048, ST_AS = 2304, ST_V = 2560, ST_SEM1 = 2688, STASH_LD = 2816;
@@ -156,6 +171,19 @@ struct MlpBwdArgs {
 };
 int launch_mlp_bwd_fp32(const MlpBwdArgs& a, cudaStream_t st);
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t st);
+struct TcBwdArgs {
+  const void* packed;        // packed blob (composed views' matrix, fp32 sections)
+  const float* flat;         // canonical flat parameters
+  int variant, n_classes, endpoint;
+  int64_t M;
+  const float* raw;          // [M, out_ch] forward output
+  const float* grad_raw;     // [M, out_ch]
+  const unsigned char* stash_img;   // forward stash (IMG_STASH_SLOTS images per tile)
+  unsigned char* work;       // inrf_mlp_bwd_tc_workspace_bytes()
+  float* grad_flat;          // accumulated into (+=)
+};
+int64_t tc_bwd_workspace_bytes(int variant, int n_classes, int64_t M);
+int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st);
 int launch_mlp_tc2(const MlpArgs& a, cudaStream_t st);
 
 }  // namespace inrf

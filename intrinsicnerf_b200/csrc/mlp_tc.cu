@@ -247,6 +247,9 @@ __device__ __forceinline__ uint32_t swz(uint32_t chunk_base, int row, int unit) 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void st_global_v4(unsigned char* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -287,6 +290,7 @@ struct RowAddr {
   uint32_t unit[8];
 };
 
+template <bool STASH>
 __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
   RowAddr ra;
 #pragma unroll
@@ -366,6 +370,14 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
     for (int u = 0; u < 4; ++u) st_shared_v4(smem_base + SM_DIR + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     fence_async_smem();
     warp_arrive(sy.addr(B_F_READY), row & 31);
+    if (STASH && tile * TILE_M < P.a.M) {        // training: the same operand images go to the stash
+      unsigned char* g = P.a.stash_img + (tile * IMG_STASH_SLOTS + IS_PE) * (int64_t)IMG_BYTES;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) st_global_v4(g + ra.unit[u], pw[4 * u], pw[4 * u + 1], pw[4 * u + 2], pw[4 * u + 3]);
+      g += (IS_DIR - IS_PE) * IMG_BYTES;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st_global_v4(g + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
+    }
   }
 }
 
@@ -582,7 +594,7 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
 template <bool ADD_BIAS, bool SIGMA, bool GOUT>
 __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __restrict__ bias, uint32_t dst_chunk,
                                             const RowAddr& ra, int unit0, const float* alpha_w_smem, float* sigma_acc,
-                                            float* gout) {
+                                            float* gout, unsigned char* gimg) {
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -615,6 +627,7 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[i] = relu_h2(pack_h2(f[8 * u + 2 * i], f[8 * u + 2 * i + 1]));
     st_shared_v4(dst_chunk + ra.unit[unit0 + u], pk[0], pk[1], pk[2], pk[3]);
+    if (gimg != nullptr) st_global_v4(gimg + ra.unit[unit0 + u], pk[0], pk[1], pk[2], pk[3]);   // training stash image
   }
 }
 
@@ -624,7 +637,7 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
 template <int MODE>
 __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst0, int n_chunks,
                                           const RowAddr& ra, int jj, int lane, Sync& sy, int free_bar0, int ready_bar0,
-                                          const float* alpha_smem, float* sigma_acc, float* gout0) {
+                                          const float* alpha_smem, float* sigma_acc, float* gout0, unsigned char* gimg0) {
 #pragma unroll 1
   for (int cp = 0; cp < n_chunks; cp += 2) {
     uint32_t v0[32], v1[32];
@@ -639,8 +652,9 @@ __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const f
       if (free_bar0 >= 0 && c == 0) sy.wait(free_bar0);     // one "H free" barrier for the whole layer
       float* g = (MODE == 2 && gout0) ? gout0 + col : nullptr;
       const float* aw = (MODE == 1) ? alpha_smem + col : nullptr;
-      if (add_bias) epi_store32<true, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
-      else epi_store32<false, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g);
+      unsigned char* gi = gimg0 ? gimg0 + c * IMG_BYTES : nullptr;
+      if (add_bias) epi_store32<true, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi);
+      else epi_store32<false, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi);
       fence_async_smem();
       tc_fence_before();
       if (ready_bar0 >= 0) warp_arrive(sy.addr(ready_bar0 + c), lane);
@@ -650,6 +664,7 @@ __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const f
 
 __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
 
+template <bool STASH>
 __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* smem, uint32_t smem_base, uint32_t tmem,
                                          int q, int jj, int lane) {
   const int row = q * 32 + lane;
@@ -668,13 +683,16 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     const int64_t m = tile * TILE_M + row;
     const bool valid = m < P.a.M;
     float* grow = P.a.raw + (valid ? m : 0) * P.out_ch;
+    // training: image slot 0 of this tile in the stash (tiles past the end of the batch are not stored)
+    unsigned char* simg = (STASH && tile * TILE_M < P.a.M) ? P.a.stash_img + tile * IMG_STASH_SLOTS * (int64_t)IMG_BYTES : nullptr;
+#define SLOT(s) (simg ? simg + (s) * IMG_BYTES : nullptr)
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
     float sig = 0.f;
     for (int l = 0; l < 8; ++l) {
       sy.wait(B_ACC_FULL + (l & 1));
       tc_fence_after();
-      if (l == 7) epi_layer<1>(add_bias, lane_addr + 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr);
-      else epi_layer<0>(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr);
+      if (l == 7) epi_layer<1>(add_bias, lane_addr + 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28));
+      else epi_layer<0>(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l));
     }
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
@@ -683,17 +701,18 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
       tc_fence_after();
     if (P.a.endpoint)
       epi_layer<2>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
-                   valid ? grow + INRF_RAW_BASE + P.C : nullptr);
+                   valid ? grow + INRF_RAW_BASE + P.C : nullptr, SLOT(IS_V));
     else
-      epi_layer<0>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr);
+      epi_layer<0>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V));
     warp_arrive(sy.addr(B_V_READY), lane);
     // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ---------------------------------
     sy.wait(B_ACC_FULL + 1);
       tc_fence_after();
-    epi_layer<0>(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr);
+    epi_layer<0>(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS));
     // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
     if (sem)
-      epi_layer<0>(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr);
+      epi_layer<0>(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1));
+#undef SLOT
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
     if (sem) sy.wait(B_SEM2_FULL);
@@ -742,7 +761,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int CL>
+template <int CL, bool STASH>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -811,9 +830,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   } else if (warp == 15) {
     issuer(P, sy, smem_base, tmem, CL);
   } else if (warp >= 8 && warp < 12) {
-    front_end(P, sy, smem_base, (warp - 8) * 32 + lane);
+    front_end<STASH>(P, sy, smem_base, (warp - 8) * 32 + lane);
   } else if (warp < 8) {
-    epilogue(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
+    epilogue<STASH>(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
   }
   if (sy.prof != nullptr) sy.prof[63] = clock64() - t_start;
   tc_fence_before();
@@ -875,7 +894,8 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   int grid = (int)(tiles < sms ? tiles : sms);
   grid = grid / cl * cl;                       // whole clusters only
   P.n_iter = (int)((tiles + grid - 1) / grid);
-  void (*kern)(tc::Params) = cl == 2 ? tc::k_mlp_tc<2> : tc::k_mlp_tc<1>;
+  void (*kern)(tc::Params) = a.stash_img ? (cl == 2 ? tc::k_mlp_tc<2, true> : tc::k_mlp_tc<1, true>)
+                                         : (cl == 2 ? tc::k_mlp_tc<2, false> : tc::k_mlp_tc<1, false>);
   INRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);

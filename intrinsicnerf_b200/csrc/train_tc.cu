@@ -1,0 +1,612 @@
+// Tensor-core backward pass of the intrinsic field network (training path, INRF_PREC_TC).
+//
+// The forward (mlp_tc.cu, STASH instantiation) leaves every post-activation tile of a 128-sample tile in HBM as
+// a 16 KB image of the shared-memory UMMA operand chunk (common.cuh: IMG_*).  The backward is a short sequence
+// of launches over those images - nothing is recomputed, and no operand is ever re-laid-out:
+//
+//   k_bwd_heads   per sample: d(loss)/d(pre-sigmoid heads, sigma, logits) from grad_raw and raw -> image G
+//   k_gemm_dx     dZ_out = relu'(H_out) * (sum_k dZ_in[k] W_k)   tcgen05 GEMM, A = gradient images (K-major),
+//                 B = transposed weight tiles (packed per call), epilogue masks with the stashed activation
+//                 image and writes the next gradient image; 10 launches walk heads -> trunk layer 7 -> ... -> 0
+//   k_gemm_dw     dW = dZ^T X for every layer in ONE launch: both operands are read MN-major from the same
+//                 images (rows of the tile are the K dimension), split-K over tiles, fp32 atomics into the
+//                 flat gradient; an all-ones operand tile adds the bias gradient as 16 extra accumulator columns
+//   k_unfold_comp views' = views_linears.0[:, :256] o feature_linear was composed at pack time (pack.cu); its
+//                 gradient is unfolded onto the two original matrices.
+//
+// Arithmetic: fp16 operands (RN) x fp32 accumulation, like the forward.  Gradients are scaled by a power of two
+// chosen from max|grad_raw| (device-side, no host sync) so that fp16 holds them without underflow; the scale is
+// removed in fp32 when dW is written.  Reference semantics: autograd through NeRF.forward
+// (object_level/run_nerf_helpers.py:284-325) / Semantic_NeRF.forward (SSR/models/semantic_nerf.py:123-181).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
+
+namespace inrf {
+namespace ttc {
+using namespace ptx;
+
+constexpr int TILE = 128;
+
+struct ImgRef {                 // image of tile t: base + (t * tslots + slot) * IMG_BYTES
+  const unsigned char* base;
+  int tslots, slot;
+  __host__ __device__ const unsigned char* at(int64_t t, int c = 0) const { return base + (t * tslots + slot + c) * (int64_t)IMG_BYTES; }
+};
+
+__device__ int g_dbg[8];
+
+// ------------------------------------------------------------------------------------------
+// gradient scale: S = 2^(7 - e) with max|grad_raw| in [2^(e-1), 2^e)  ->  scaled maximum in [64, 128)
+// ------------------------------------------------------------------------------------------
+__global__ void k_amax(const float* __restrict__ g, int64_t n, unsigned int* amax_bits) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(g[i]);
+    if (v < 3.0e38f) m = fmaxf(m, v);             // inf / NaN gradients do not pick the scale
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+__device__ __forceinline__ float grad_scale(const unsigned int* amax_bits) {
+  const float a = __uint_as_float(*amax_bits);
+  if (!(a > 0.f)) return 1.f;
+  int e;
+  frexpf(a, &e);
+  return ldexpf(1.f, 7 - e);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_global_v4(unsigned char* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_global_nc_v4(const unsigned char* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// byte offset of 16-byte unit `u` of row `row` inside a chunk image
+__device__ __forceinline__ uint32_t img_unit(int row, int u) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
+}
+
+// ------------------------------------------------------------------------------------------
+// head gradients -> image G (2 chunks): cols 0..2 albedo, 3 shading, 4..6 residual (pre-sigmoid), 7 sigma,
+// 8..8+C semantic logits.  rgb = albedo*shading + residual (run_nerf_helpers.py:320), so
+//   d albedo = g_rgb*shading + g_albedo, d shading = sum g_rgb*albedo + g_shading, d residual = g_rgb + g_residual.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bwd_heads(const float* __restrict__ grad_raw, const float* __restrict__ raw, int out_ch,
+                                                   int C, int64_t M, unsigned char* work, const unsigned int* amax_bits) {
+  const int row = threadIdx.x;
+  const int64_t tile = blockIdx.x, m = tile * TILE + row;
+  const float S = grad_scale(amax_bits);
+  float g[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) g[i] = 0.f;
+  if (m < M) {
+    const float* gr = grad_raw + m * out_ch;
+    const float* rw = raw + m * out_ch;
+    const float sh = rw[7];
+    float dsh = gr[7];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float alb = rw[4 + i], res = rw[8 + i], grgb = gr[i];
+      g[i] = (grgb * sh + gr[4 + i]) * alb * (1.f - alb) * S;
+      g[4 + i] = (grgb + gr[8 + i]) * res * (1.f - res) * S;
+      dsh = fmaf(grgb, alb, dsh);
+    }
+    g[3] = dsh * sh * (1.f - sh) * S;
+    g[7] = gr[3] * S;
+#pragma unroll
+    for (int c = 0; c < MAX_CLASSES; ++c)
+      if (c < C) g[8 + c] = gr[INRF_RAW_BASE + c] * S;
+  }
+  unsigned char* img = work + (tile * IMG_BWD_SLOTS + IB_G) * (int64_t)IMG_BYTES;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float* s = g + ch * 64 + u * 8;
+      st_global_v4(img + ch * IMG_BYTES + img_unit(row, u), pack_h2(s[0], s[1]), pack_h2(s[2], s[3]), pack_h2(s[4], s[5]), pack_h2(s[6], s[7]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// transposed weight tiles for the dX GEMMs: tile = [N rows (input unit n)] x [64 K columns (output unit k)],
+// K-major SWIZZLE_128B, value = d(pre-activation k of the source)/d(input n)
+// ------------------------------------------------------------------------------------------
+enum { BW_PLAIN = 0, BW_COMP, BW_HEAD_AS, BW_HEAD_V, BW_HEAD_SEM, BW_ALPHA };
+struct BwTile { int16_t kind, layer, out0, in0, N, pad; int32_t off; };
+constexpr int BW_MAX_TILES = 48;
+struct BwProgram { int n; int bytes; BwTile t[BW_MAX_TILES]; };
+
+__global__ void k_pack_bwd(const float* __restrict__ flat, const unsigned char* __restrict__ packed, NetLayout L,
+                           const __grid_constant__ BwProgram prog, unsigned char* blob) {
+  const BwTile t = prog.t[blockIdx.x];
+  __half* dst = reinterpret_cast<__half*>(blob + t.off);
+  const float* comp = reinterpret_cast<const float*>(packed + L.comp);
+  for (int e = threadIdx.x; e < t.N * 64; e += blockDim.x) {
+    const int n = e >> 6, k = e & 63;
+    float v = 0.f;
+    switch (t.kind) {
+      case BW_PLAIN: {
+        const LayerDims d = layer_dims(t.layer, L.n_classes);
+        const int o = t.out0 + k, i = t.in0 + n;
+        if (o < d.N && i < d.K) v = flat[L.flat_w[t.layer] + (int64_t)o * d.K + i];
+      } break;
+      case BW_COMP: v = comp[(t.out0 + k) * W_HID + n]; break;
+      case BW_HEAD_AS:          // G cols 0..2 -> albedo hidden units (n < 128), col 3 -> shading hidden units
+        if (n < 128 && k < 3) v = flat[L.flat_w[L_ALB2] + k * 128 + n];
+        else if (n >= 128 && k == 3) v = flat[L.flat_w[L_SH2] + (n - 128)];
+        break;
+      case BW_HEAD_V: if (k >= 4 && k < 7) v = flat[L.flat_w[L_RES] + (k - 4) * 128 + n]; break;
+      case BW_HEAD_SEM: {
+        const int c = t.out0 + k - 8;
+        if (c >= 0 && c < L.n_classes) v = flat[L.flat_w[L_SEM2] + c * 128 + n];
+      } break;
+      case BW_ALPHA: if (k == 7) v = flat[L.flat_w[L_ALPHA] + n]; break;
+    }
+    dst[(img_unit(n, k >> 3) + (k & 7) * 2) >> 1] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dX GEMM: out[128 x N] = mask * (sum_kc A_kc[128 x 64] . B_kc[N x 64]^T (+ addend)), persistent over tiles.
+// warps 0-7 epilogue (TMEM lanes 32*(w&3).., 32-column half (w>>2) of every 64-column chunk), warp 8 producer,
+// warp 9 MMA issuer; 4-stage ring of (A chunk 16 KB + B tile <= 32 KB); two 256-column accumulators so that the
+// epilogue of tile t overlaps the MMAs of tile t+1.
+// ------------------------------------------------------------------------------------------
+constexpr int DX_MAX_K = 10, DX_NS = 4, DX_STAGE = IMG_BYTES + 32768, DX_THREADS = 320;
+constexpr int DX_BAR = DX_NS * DX_STAGE, DX_SMEM = DX_BAR + 256;
+struct DxParams {
+  int n_k, N, n_tiles, n_iter;
+  ImgRef a[DX_MAX_K];
+  const unsigned char* b;
+  ImgRef mask, out;
+  const float* addend;           // optional fp32 rows (first column already applied), row stride addend_ld
+  int addend_ld;
+  int64_t M;
+  const unsigned int* amax_bits;
+  int* dbg;
+};
+enum { DXB_FULL = 0, DXB_EMPTY = DX_NS, DXB_ACC_FULL = 2 * DX_NS, DXB_ACC_EMPTY = 2 * DX_NS + 2, DXB_COUNT = 2 * DX_NS + 4 };
+
+#define TTC_WAIT(addr, par, code)                                          \
+  do {                                                                     \
+    if (!dead && !mbar_wait((addr), (par))) { dead = true; if (atomicCAS(P.dbg, 0, (code)) == 0) { P.dbg[1] = blockIdx.x; P.dbg[2] = threadIdx.x; } } \
+  } while (0)
+
+__global__ void __launch_bounds__(DX_THREADS, 1) k_gemm_dx(const __grid_constant__ DxParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar0 = sb + DX_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DX_BAR + 8 * DXB_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool dead = false;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DX_NS; ++s) { mbar_init(bar0 + 8 * (DXB_FULL + s), 1); mbar_init(bar0 + 8 * (DXB_EMPTY + s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar0 + 8 * (DXB_ACC_FULL + i), 1); mbar_init(bar0 + 8 * (DXB_ACC_EMPTY + i), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc512(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t b_bytes = (uint32_t)P.N * 128u;
+
+  if (warp == 8) {                                     // ---- producer
+    const bool leader = elect_one();
+    int slot = 0;
+    uint32_t par = (1u << DX_NS) - 1;                   // "empty" barriers start released
+    for (int it = 0; it < P.n_iter; ++it) {
+      const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;
+      if (tile >= P.n_tiles) break;
+      for (int kc = 0; kc < P.n_k; ++kc) {
+        TTC_WAIT(bar0 + 8 * (DXB_EMPTY + slot), (par >> slot) & 1u, 1);
+        par ^= 1u << slot;
+        if (leader && !dead) {
+          const uint32_t full = bar0 + 8 * (DXB_FULL + slot), dst = sb + slot * DX_STAGE;
+          mbar_expect_tx(full, IMG_BYTES + b_bytes);
+          bulk_g2s(dst, P.a[kc].at(tile), IMG_BYTES, full);
+          bulk_g2s(dst + IMG_BYTES, P.b + (int64_t)kc * b_bytes, b_bytes, full);
+        }
+        __syncwarp();
+        slot = (slot + 1 == DX_NS) ? 0 : slot + 1;
+      }
+    }
+  } else if (warp == 9) {                              // ---- MMA issuer
+    const bool leader = elect_one();
+    int slot = 0, buf = 0;
+    uint32_t par_full = 0, par_acc = 3u;               // accumulators start drained
+    const uint32_t idesc = idesc_f16(128, P.N, 0, 0);
+    for (int it = 0; it < P.n_iter; ++it) {
+      const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;
+      if (tile >= P.n_tiles) break;
+      TTC_WAIT(bar0 + 8 * (DXB_ACC_EMPTY + buf), (par_acc >> buf) & 1u, 2);
+      par_acc ^= 1u << buf;
+      tc_fence_after();
+      for (int kc = 0; kc < P.n_k; ++kc) {
+        TTC_WAIT(bar0 + 8 * (DXB_FULL + slot), (par_full >> slot) & 1u, 3);
+        par_full ^= 1u << slot;
+        tc_fence_after();
+        if (leader && !dead) {
+          const uint64_t ad = desc_k_sw128(sb + slot * DX_STAGE), bd = desc_k_sw128(sb + slot * DX_STAGE + IMG_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma(tmem + buf * 256, ad + 2 * k, bd + 2 * k, idesc, (kc | k) ? 1u : 0u);
+          tc_commit(bar0 + 8 * (DXB_EMPTY + slot));
+        }
+        __syncwarp();
+        slot = (slot + 1 == DX_NS) ? 0 : slot + 1;
+      }
+      if (leader && !dead) tc_commit(bar0 + 8 * (DXB_ACC_FULL + buf));
+      __syncwarp();
+      buf ^= 1;
+    }
+  } else {                                             // ---- epilogue
+    const int q = warp & 3, jj = warp >> 2, row = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const float S = P.addend ? grad_scale(P.amax_bits) : 1.f;
+    uint32_t uoff[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) uoff[u] = img_unit(row, jj * 4 + u);
+    int buf = 0;
+    uint32_t par_acc = 0;
+    const int n_chunks = P.N >> 6;
+    for (int it = 0; it < P.n_iter; ++it) {
+      const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;
+      if (tile >= P.n_tiles) break;
+      const int64_t m = tile * TILE + row;
+      TTC_WAIT(bar0 + 8 * (DXB_ACC_FULL + buf), (par_acc >> buf) & 1u, 4);
+      par_acc ^= 1u << buf;
+      tc_fence_after();
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + buf * 256 + c * 64 + jj * 32, v);
+        const unsigned char* mk = P.mask.at(tile, c);
+        uint4 mu[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mu[u] = ld_global_nc_v4(mk + uoff[u]);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (P.addend != nullptr && m < P.M) {
+          const float* ad = P.addend + m * P.addend_ld + c * 64 + jj * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaf(ad[i], S, f[i]);
+        }
+        unsigned char* op = const_cast<unsigned char*>(P.out.at(tile, c));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t mw[4] = {mu[u].x, mu[u].y, mu[u].z, mu[u].w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // post-ReLU activations are >= 0: positive <=> its fp16 bits are non-zero and not -0
+            const float lo = (mw[i] & 0x7fffu) ? f[8 * u + 2 * i] : 0.f;
+            const float hi = (mw[i] & 0x7fff0000u) ? f[8 * u + 2 * i + 1] : 0.f;
+            pk[i] = pack_h2(lo, hi);
+          }
+          st_global_v4(op + uoff[u], pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (DXB_ACC_EMPTY + buf));
+      buf ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc512(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// dW GEMM: D[128 out x N in] += sum over the tiles of a split of dZ^T X, both operands MN-major from the images.
+// grid = (items, splits); warps 0-3 epilogue, warp 4 producer, warp 5 issuer; 2-stage ring of (2 + n_x) chunks.
+// Accumulator columns [256, 272) hold dZ^T 1 = the bias gradient.
+// ------------------------------------------------------------------------------------------
+struct DwRect { int row0, nrows, col0, ncols, ld, pad; float* dst; float* bias; };
+struct DwItem { ImgRef a, x; int x_bytes, N, n_rect, pad; DwRect r[4]; };
+constexpr int DW_MAX_ITEMS = 40, DW_STAGE = 6 * IMG_BYTES, DW_THREADS = 192;
+constexpr int DW_ONES = 2 * DW_STAGE, DW_BAR = DW_ONES + 1024, DW_SMEM = DW_BAR + 128;
+struct DwParams {
+  int n_items, n_tiles, n_splits, pad;
+  const unsigned int* amax_bits;
+  int* dbg;
+  DwItem item[DW_MAX_ITEMS];
+};
+enum { DWB_FULL = 0, DWB_EMPTY = 2, DWB_ACC = 4, DWB_COUNT = 5 };
+
+__global__ void __launch_bounds__(DW_THREADS, 1) k_gemm_dw(const __grid_constant__ DwParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const DwItem& I = P.item[blockIdx.x];
+  const int t0 = (int)((int64_t)blockIdx.y * P.n_tiles / P.n_splits), t1 = (int)((int64_t)(blockIdx.y + 1) * P.n_tiles / P.n_splits);
+  if (t0 >= t1) return;
+  const uint32_t sb = smem_u32(smem), bar0 = sb + DW_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + DW_BAR + 8 * DWB_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool dead = false;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(bar0 + 8 * (DWB_FULL + s), 1); mbar_init(bar0 + 8 * (DWB_EMPTY + s), 1); }
+    mbar_init(bar0 + 8 * DWB_ACC, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {                                     // all-ones operand tile (layout-agnostic)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + DW_ONES);
+    for (int i = lane; i < 256; i += 32) ones[i] = 0x3c003c00u;
+    fence_async_smem();
+  }
+  if (warp == 5) tmem_alloc512(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {                                     // ---- producer
+    const bool leader = elect_one();
+    uint32_t par = 3u;
+    for (int t = t0; t < t1; ++t) {
+      const int s = (t - t0) & 1;
+      TTC_WAIT(bar0 + 8 * (DWB_EMPTY + s), (par >> s) & 1u, 11);
+      par ^= 1u << s;
+      if (leader && !dead) {
+        const uint32_t full = bar0 + 8 * (DWB_FULL + s), dst = sb + s * DW_STAGE;
+        mbar_expect_tx(full, 2 * IMG_BYTES + (uint32_t)I.x_bytes);
+        bulk_g2s(dst, I.a.at(t), 2 * IMG_BYTES, full);
+        bulk_g2s(dst + 2 * IMG_BYTES, I.x.at(t), (uint32_t)I.x_bytes, full);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {                              // ---- MMA issuer
+    const bool leader = elect_one();
+    uint32_t par = 0;
+    const uint32_t idesc = idesc_f16(128, I.N, 1, 1), idesc_b = idesc_f16(128, 16, 1, 1);
+    const uint64_t ones = desc_flat(sb + DW_ONES, 256, 128);
+    for (int t = t0; t < t1; ++t) {
+      const int s = (t - t0) & 1;
+      TTC_WAIT(bar0 + 8 * (DWB_FULL + s), (par >> s) & 1u, 12);
+      par ^= 1u << s;
+      tc_fence_after();
+      if (leader && !dead) {
+        const uint32_t st = sb + s * DW_STAGE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = desc_mn_sw128(st + k * 2048, IMG_BYTES), xd = desc_mn_sw128(st + 2 * IMG_BYTES + k * 2048, IMG_BYTES);
+          const uint32_t acc = (t > t0 || k > 0) ? 1u : 0u;
+          tc_mma(tmem, ad, xd, idesc, acc);
+          tc_mma(tmem + 256, ad, ones, idesc_b, acc);
+        }
+        tc_commit(bar0 + 8 * (DWB_EMPTY + s));
+      }
+      __syncwarp();
+    }
+    if (leader && !dead) tc_commit(bar0 + 8 * DWB_ACC);
+    __syncwarp();
+  } else {                                             // ---- epilogue: accumulator -> fp32 atomics
+    TTC_WAIT(bar0 + 8 * DWB_ACC, 0u, 13);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float inv = 1.f / grad_scale(P.amax_bits);
+    uint32_t v[32];
+    for (int ri = 0; ri < I.n_rect; ++ri) {
+      const DwRect R = I.r[ri];
+      const bool mine = row >= R.row0 && row < R.row0 + R.nrows && !dead;
+      if (R.ncols > 0) {
+        for (int g = R.col0 >> 5; g <= (R.col0 + R.ncols - 1) >> 5; ++g) {
+          tmem_ld32(lane_addr + g * 32, v);
+          tmem_ld_wait();
+          if (mine) {
+            float* d = R.dst + (int64_t)(row - R.row0) * R.ld - R.col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = g * 32 + i;
+              if (col >= R.col0 && col < R.col0 + R.ncols) atomicAdd(d + col, __uint_as_float(v[i]) * inv);
+            }
+          }
+        }
+      }
+      if (R.bias != nullptr) {
+        tmem_ld32(lane_addr + 256, v);
+        tmem_ld_wait();
+        if (mine) atomicAdd(R.bias + (row - R.row0), __uint_as_float(v[0]) * inv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc512(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// unfold the gradient of the composed views' matrix: Wc = Wv1 Wf, bc = Wv1 bf + bv  (Wv1 = views weight[:, :256])
+//   dWv1 += dWc Wf^T + dbc (x) bf;  dWf += Wv1^T dWc;  dbf += Wv1^T dbc;  dbv += dbc
+// ------------------------------------------------------------------------------------------
+__global__ void k_unfold_comp(const float* __restrict__ flat, NetLayout L, const float* __restrict__ dcomp, float* grad) {
+  const float* vw = flat + L.flat_w[L_VIEWS];
+  const float* fw = flat + L.flat_w[L_FEAT];
+  const float* fb = flat + L.flat_b[L_FEAT];
+  const float* dwc = dcomp;
+  const float* dbc = dcomp + 128 * W_HID;
+  const int j = threadIdx.x;               // 256 threads
+  if (blockIdx.x < 128) {                  // dWv1[n][j]
+    const int n = blockIdx.x;
+    float acc = dbc[n] * fb[j];
+    for (int k = 0; k < W_HID; ++k) acc = fmaf(dwc[n * W_HID + k], fw[j * W_HID + k], acc);
+    grad[L.flat_w[L_VIEWS] + n * (W_HID + PE_DIR) + j] += acc;
+    if (j == 0) grad[L.flat_b[L_VIEWS] + n] += dbc[n];
+  } else {                                 // dWf[jf][k = thread], dbf[jf]
+    const int jf = blockIdx.x - 128, k = threadIdx.x;
+    float acc = 0.f, accb = 0.f;
+    for (int n = 0; n < 128; ++n) {
+      const float w = vw[n * (W_HID + PE_DIR) + jf];
+      acc = fmaf(w, dwc[n * W_HID + k], acc);
+      accb = fmaf(w, dbc[n], accb);
+    }
+    grad[L.flat_w[L_FEAT] + jf * W_HID + k] += acc;
+    if (k == 0) grad[L.flat_b[L_FEAT] + jf] += accb;
+  }
+}
+
+}  // namespace ttc
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+static inline int64_t n_tiles_of(int64_t M) { return (M + ttc::TILE - 1) / ttc::TILE; }
+static inline int64_t up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+constexpr int64_t WS_HEAD = 4096;                                     // amax word + padding
+constexpr int64_t WS_COMP = (128 * W_HID + 128) * 4;                 // gradient of the composed views' matrix + bias
+constexpr int64_t WS_BLOB = ttc::BW_MAX_TILES * 32768;               // transposed weight tiles
+
+int64_t tc_bwd_workspace_bytes(int variant, int n_classes, int64_t M) {
+  (void)variant; (void)n_classes;
+  return up(WS_HEAD + WS_COMP, 1024) + WS_BLOB + n_tiles_of(M) * IMG_BWD_SLOTS * (int64_t)IMG_BYTES;
+}
+
+int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
+  using namespace ttc;
+  if (a.M == 0) return INRF_OK;
+  NetLayout L;
+  int rc = make_layout(a.variant, a.n_classes, &L);
+  if (rc) return rc;
+  const bool sem = a.n_classes > 0;
+  const int C = a.n_classes, out_ch = raw_channels(C, a.endpoint);
+  const int64_t T = n_tiles_of(a.M);
+  if (T > 0x7fffffff / IMG_BWD_SLOTS) { set_error("batch too large for one backward call"); return INRF_EUNSUPPORTED; }
+  unsigned char* ws = a.work;
+  unsigned int* amax = reinterpret_cast<unsigned int*>(ws);
+  float* dcomp = reinterpret_cast<float*>(ws + WS_HEAD);
+  unsigned char* blob = ws + up(WS_HEAD + WS_COMP, 1024);
+  unsigned char* img = blob + WS_BLOB;
+  int* dbg = nullptr;
+  INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, ttc::g_dbg));
+  INRF_CUDA(cudaMemsetAsync(ws, 0, WS_HEAD + WS_COMP, st));
+  static const bool checked = getenv("INRF_TC_CHECK") != nullptr && getenv("INRF_TC_CHECK")[0] == '1';
+  if (checked) INRF_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(int), st));
+  int dev = 0, sms = 148;
+  INRF_CUDA(cudaGetDevice(&dev));
+  INRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  k_amax<<<sms * 4, 256, 0, st>>>(a.grad_raw, a.M * out_ch, amax);
+  INRF_LAUNCH_CHECK();
+  k_bwd_heads<<<(unsigned)T, 128, 0, st>>>(a.grad_raw, a.raw, out_ch, C, a.M, img, amax);
+  INRF_LAUNCH_CHECK();
+
+  // ---- dX GEMM sequence and its weight tiles ---------------------------------------------------------
+  auto W = [&](int slot) { return ImgRef{img, IMG_BWD_SLOTS, slot}; };
+  auto F = [&](int slot) { return ImgRef{a.stash_img, IMG_STASH_SLOTS, slot}; };
+  BwProgram prog;
+  prog.n = 0; prog.bytes = 0;
+  DxParams G[12];
+  int ng = 0;
+  auto begin = [&](int N, ImgRef mask, ImgRef out) {
+    DxParams& g = G[ng];
+    memset(&g, 0, sizeof(g));
+    g.N = N; g.mask = mask; g.out = out; g.b = blob + prog.bytes; g.M = a.M; g.amax_bits = amax; g.dbg = dbg; g.n_tiles = (int)T;
+  };
+  auto add = [&](ImgRef src, int kind, int layer, int out0, int in0) {
+    DxParams& g = G[ng];
+    g.a[g.n_k++] = src;
+    BwTile& t = prog.t[prog.n++];
+    t.kind = (int16_t)kind; t.layer = (int16_t)layer; t.out0 = (int16_t)out0; t.in0 = (int16_t)in0; t.N = (int16_t)g.N; t.pad = 0;
+    t.off = prog.bytes;
+    prog.bytes += g.N * 128;
+  };
+  // relu'(albedo1|shading1) * (G . [albedo2; shading2])
+  begin(256, F(IS_AS), W(IB_DAS)); add(W(IB_G), BW_HEAD_AS, 0, 0, 0); ++ng;
+  // relu'(views') * (G . residual head (+ endpoint-feature gradient))
+  begin(128, F(IS_V), W(IB_DV)); add(W(IB_G), BW_HEAD_V, 0, 0, 0);
+  if (a.endpoint) { G[ng].addend = a.grad_raw + INRF_RAW_BASE + C; G[ng].addend_ld = out_ch; }
+  ++ng;
+  if (sem) {
+    begin(128, F(IS_S1), W(IB_DS1));
+    add(W(IB_G), BW_HEAD_SEM, 0, 0, 0); add(W(IB_G + 1), BW_HEAD_SEM, 0, 64, 0);
+    ++ng;
+  }
+  // trunk output: albedo1|shading1, views' (composed), sem1 and sigma branches meet
+  begin(256, F(IS_H + 28), W(IB_DZ + 28));
+  for (int c = 0; c < 4; ++c) add(W(IB_DAS + c), BW_PLAIN, c < 2 ? L_ALB1 : L_SH1, (c & 1) * 64, 0);
+  for (int c = 0; c < 2; ++c) add(W(IB_DV + c), BW_COMP, -1, c * 64, 0);
+  if (sem) for (int c = 0; c < 2; ++c) add(W(IB_DS1 + c), BW_PLAIN, L_SEM1, c * 64, 0);
+  add(W(IB_G), BW_ALPHA, 0, 0, 0);
+  ++ng;
+  for (int l = 7; l >= 1; --l) {          // dZ_{l-1} = relu'(H_{l-1}) * (dZ_l W_l[:, hidden part])
+    begin(256, F(IS_H + 4 * (l - 1)), W(IB_DZ + 4 * (l - 1)));
+    for (int c = 0; c < 4; ++c) add(W(IB_DZ + 4 * l + c), BW_PLAIN, L_T0 + l, c * 64, l == 5 ? PE_PTS : 0);
+    ++ng;
+  }
+  if (prog.n > BW_MAX_TILES || prog.bytes > WS_BLOB) { set_error("internal: backward weight program too long"); return INRF_EINVAL; }
+  k_pack_bwd<<<prog.n, 256, 0, st>>>(a.flat, static_cast<const unsigned char*>(a.packed), L, prog, blob);
+  INRF_LAUNCH_CHECK();
+  INRF_CUDA(cudaFuncSetAttribute(k_gemm_dx, cudaFuncAttributeMaxDynamicSharedMemorySize, DX_SMEM));
+  const int grid = (int)(T < sms ? T : sms);
+  for (int i = 0; i < ng; ++i) {
+    G[i].n_iter = (int)((T + grid - 1) / grid);
+    k_gemm_dx<<<grid, DX_THREADS, DX_SMEM, st>>>(G[i]);
+    INRF_LAUNCH_CHECK();
+  }
+
+  // ---- dW: one launch, one item per (GEMM, 128 output rows) --------------------------------------------
+  static DwParams D;                       // 9 KB table, rebuilt per call (single-threaded host semantics like the reference)
+  memset(&D, 0, sizeof(D));
+  D.n_tiles = (int)T; D.amax_bits = amax; D.dbg = dbg;
+  float* gf = a.grad_flat;
+  auto item = [&](ImgRef az, ImgRef x, int n_x, int N) -> DwItem& {
+    DwItem& it = D.item[D.n_items++];
+    it.a = az; it.x = x; it.x_bytes = n_x * IMG_BYTES; it.N = N; it.n_rect = 0;
+    return it;
+  };
+  auto rect = [&](DwItem& it, int row0, int nrows, int col0, int ncols, float* dst, int ld, float* bias) {
+    DwRect& r = it.r[it.n_rect++];
+    r.row0 = row0; r.nrows = nrows; r.col0 = col0; r.ncols = ncols; r.ld = ld; r.dst = dst; r.bias = bias;
+  };
+  for (int l = 0; l < 8; ++l) {
+    const LayerDims d = layer_dims(L_T0 + l, C);
+    for (int h = 0; h < 2; ++h) {
+      float* w = gf + L.flat_w[L_T0 + l] + (int64_t)128 * h * d.K;
+      float* b = gf + L.flat_b[L_T0 + l] + 128 * h;
+      if (l == 0 || l == 5) rect(item(W(IB_DZ + 4 * l + 2 * h), F(IS_PE), 1, 64), 0, 128, 0, PE_PTS, w, d.K, l == 0 ? b : nullptr);
+      if (l > 0) rect(item(W(IB_DZ + 4 * l + 2 * h), F(IS_H + 4 * (l - 1)), 4, 256), 0, 128, 0, 256, w + (l == 5 ? PE_PTS : 0), d.K, b);
+    }
+  }
+  rect(item(W(IB_DAS), F(IS_H + 28), 4, 256), 0, 128, 0, 256, gf + L.flat_w[L_ALB1], 256, gf + L.flat_b[L_ALB1]);
+  rect(item(W(IB_DAS + 2), F(IS_H + 28), 4, 256), 0, 128, 0, 256, gf + L.flat_w[L_SH1], 256, gf + L.flat_b[L_SH1]);
+  rect(item(W(IB_DV), F(IS_H + 28), 4, 256), 0, 128, 0, 256, dcomp, 256, dcomp + 128 * W_HID);
+  rect(item(W(IB_DV), F(IS_DIR), 1, 32), 0, 128, 0, PE_DIR, gf + L.flat_w[L_VIEWS] + W_HID, W_HID + PE_DIR, nullptr);
+  if (sem) rect(item(W(IB_DS1), F(IS_H + 28), 4, 256), 0, 128, 0, 256, gf + L.flat_w[L_SEM1], 256, gf + L.flat_b[L_SEM1]);
+  {
+    DwItem& it = item(W(IB_G), F(IS_AS), 4, 256);            // G^T relu(albedo1|shading1)
+    rect(it, 0, 3, 0, 128, gf + L.flat_w[L_ALB2], 128, gf + L.flat_b[L_ALB2]);
+    rect(it, 3, 1, 128, 128, gf + L.flat_w[L_SH2], 128, gf + L.flat_b[L_SH2]);
+    rect(it, 4, 3, 0, 0, nullptr, 0, gf + L.flat_b[L_RES]);
+    rect(it, 7, 1, 0, 0, nullptr, 0, gf + L.flat_b[L_ALPHA]);
+  }
+  rect(item(W(IB_G), F(IS_V), 2, 128), 4, 3, 0, 128, gf + L.flat_w[L_RES], 128, nullptr);
+  rect(item(W(IB_G), F(IS_H + 28), 4, 256), 7, 1, 0, 256, gf + L.flat_w[L_ALPHA], 256, nullptr);
+  if (sem) rect(item(W(IB_G), F(IS_S1), 2, 128), 8, C, 0, 128, gf + L.flat_w[L_SEM2], 128, gf + L.flat_b[L_SEM2]);
+  if (D.n_items > DW_MAX_ITEMS) { set_error("internal: too many dW items"); return INRF_EINVAL; }
+  int splits = (2 * sms + D.n_items - 1) / D.n_items;
+  if (splits > T) splits = (int)T;
+  if (splits < 1) splits = 1;
+  D.n_splits = splits;
+  INRF_CUDA(cudaFuncSetAttribute(k_gemm_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+  k_gemm_dw<<<dim3(D.n_items, splits), DW_THREADS, DW_SMEM, st>>>(D);
+  INRF_LAUNCH_CHECK();
+  k_unfold_comp<<<128 + 256, 256, 0, st>>>(a.flat, L, dcomp, gf);
+  INRF_LAUNCH_CHECK();
+  if (checked) {
+    int h[8];
+    INRF_CUDA(cudaStreamSynchronize(st));
+    INRF_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[0] != 0) { set_error("mlp_bwd_tc watchdog: wait %d stuck (cta %d, thread %d)", h[0], h[1], h[2]); return INRF_ECUDA; }
+  }
+  return INRF_OK;
+}
+
+}  // namespace inrf

@@ -84,8 +84,9 @@ class _FieldNet(nn.Module):
         return self._packed_blob
 
     def needs_grad(self):
-        """True when the call must be recorded by autograd (training): the fp32 training kernels are
-        used (forward with activation stash + backward); otherwise the tensor-core inference path."""
+        """True when the call must be recorded by autograd (training): the training kernels are used (forward
+        with activation stash + backward; tensor cores by default, strict fp32 CUDA cores under
+        ops.set_default_precision("fp32")); otherwise the tensor-core inference path."""
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def flat_params_diff(self):
@@ -103,7 +104,8 @@ class _FieldNet(nn.Module):
         if self.needs_grad():
             if not next(self.parameters()).is_cuda:
                 raise RuntimeError("intrinsicnerf_b200 networks run on CUDA only: call .cuda() first (no CPU fallback)")
-            return ops.MlpFn.apply(self.flat_params_diff(), self.variant, C, bool(endpoint), float(pe_scalar_factor), mode, a, b)
+            fn = ops.MlpFn if ops.default_precision() == ops.PREC_FP32 else ops.MlpTcFn
+            return fn.apply(self.flat_params_diff(), self.variant, C, bool(endpoint), float(pe_scalar_factor), mode, a, b)
         if mode == "pts":
             return ops.mlp_forward(self.packed(), self.variant, C, a, b, endpoint, pe_scalar_factor)
         if mode == "rays":

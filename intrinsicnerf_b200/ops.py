@@ -201,6 +201,57 @@ class MlpFn(torch.autograd.Function):
         return g_flat, None, None, None, None, None, None, None
 
 
+class MlpTcFn(torch.autograd.Function):
+    """Differentiable field-network evaluation on the tensor cores (training path, default).
+
+    forward : inrf_mlp_fwd_train_tc - the tcgen05 inference kernel, additionally writing every activation tile to
+              the stash as 16 KB operand images (5.25 KB per sample)
+    backward: inrf_mlp_bwd_tc       - tcgen05 dX chain + one dW launch over those images -> dL/d(flat parameters)
+    fp16 operands / fp32 accumulation in both directions; `set_default_precision("fp32")` selects MlpFn instead."""
+
+    @staticmethod
+    def forward(ctx, flat, variant, n_classes, endpoint, pe_scalar_factor, mode, a, b):
+        flat_c = _f32(flat.detach(), "flat_params")
+        packed = pack_weights(flat_c, variant, n_classes)
+        L = _lib.lib()
+        ch = RAW_BASE + n_classes + (128 if endpoint else 0)
+        pts = vd = rays = z = emb = None
+        S = 1
+        if mode == "pts":
+            pts, vd = _f32(a, "pts").reshape(-1, 3), _f32(b, "viewdirs").reshape(-1, 3)
+            M = pts.shape[0]
+        elif mode == "rays":
+            rays, z = _f32(a, "rays"), _f32(b, "z")
+            S = z.shape[1]
+            M = z.numel()
+        else:
+            emb = _f32(a, "embedded").reshape(-1, 90)
+            M = emb.shape[0]
+        dev = flat_c.device
+        raw = torch.empty(M, ch, dtype=torch.float32, device=dev)
+        stash = torch.empty(int(L.inrf_mlp_stash_img_bytes(M)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(L.inrf_mlp_fwd_train_tc(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor), _ptr(pts), _ptr(vd),
+                                          _ptr(rays), _ptr(z), S, _ptr(emb), M, _ptr(raw), _ptr(stash), _stream()))
+        ctx.save_for_backward(flat_c, packed, raw, stash)
+        ctx.cfg = (variant, n_classes, bool(endpoint), M)
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        variant, n_classes, endpoint, M = ctx.cfg
+        flat_c, packed, raw, stash = ctx.saved_tensors
+        g_raw = _f32(g_raw, "grad_raw").reshape(M, -1)
+        g_flat = torch.zeros_like(flat_c)
+        L = _lib.lib()
+        nbytes = int(L.inrf_mlp_bwd_tc_workspace_bytes(variant, n_classes, M))
+        ws = _Workspace.get(flat_c.device, nbytes, "bwd")
+        with torch.cuda.device(flat_c.device):
+            check(L.inrf_mlp_bwd_tc(_ptr(packed), _ptr(flat_c), variant, n_classes, int(endpoint), M, _ptr(raw), _ptr(stash),
+                                    _ptr(g_raw), _ptr(ws), ws.numel(), _ptr(g_flat), _stream()))
+        return g_flat, None, None, None, None, None, None, None
+
+
 class CompositeFn(torch.autograd.Function):
     """raw2outputs with a CUDA backward for `raw` (z_vals, rays_d and the noise are constants in the
     reference: z_samples is detached, run_nerf.py:501).  Lets a foreign PyTorch network train
@@ -368,8 +419,8 @@ class _Workspace:
     bufs = {}
 
     @classmethod
-    def get(cls, device, nbytes):
-        key = str(device)
+    def get(cls, device, nbytes, tag=""):
+        key = str(device) + tag
         b = cls.bufs.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=device)

@@ -97,6 +97,54 @@ def mlp_forward(params, emb, variant="object", n_classes=0, endpoint=False):
     return torch.cat(cols, dim=-1)
 
 
+def mlp_forward_tc_arith(params, emb, variant="object", n_classes=0, endpoint=False, masks=None):
+    """The same network in the ARITHMETIC of the tensor-core kernels: every GEMM operand
+    (weights and incoming activations) rounded to fp16 (round-to-nearest, straight-through gradient), products
+    and sums exact, biases / sigma head / sigmoids unrounded, views_linears.0 o feature_linear composed into one
+    matrix before rounding.  Not a different algorithm - it exists because a ReLU unit whose pre-activation lies
+    within the operand rounding of zero takes the other branch in exact arithmetic, and one flipped (sample, unit)
+    pair is a full-size difference in that sample's gradient: gradient parity of the tensor-core training path is
+    measured against THIS function (float64 inputs), value parity against mlp_forward.
+    ``masks`` (optional): one 0/1 tensor per ReLU in call order (trunk 0..7, albedo1, shading1, views, [sem1]);
+    when given, relu(z) is evaluated as z * mask, i.e. with the branch decisions of another run of the same network
+    (the kernel's, read back from its activation stash) - the network is piecewise linear, so autograd then yields the
+    exact gradient for precisely those decisions.
+    Returns (out, margin): margin[m] = min |pre-activation| over every ReLU of sample m."""
+    names = OBJECT_HEADS if variant == "object" else SSR_HEADS
+    rnd = lambda x: x + (x.to(torch.float16).to(x.dtype) - x).detach()  # noqa: E731
+    margins = []
+
+    def lin(name, x):
+        return rnd(x) @ rnd(params[name + ".weight"]).t() + params[name + ".bias"]
+
+    def relu(z):
+        margins.append(z.detach().abs().amin(dim=1))
+        if masks is not None:
+            return z * masks[len(margins) - 1].to(z.dtype)
+        return torch.relu(z)
+
+    pe_pts, pe_dir = emb[:, :63], emb[:, 63:]
+    h = pe_pts
+    for i, name in enumerate(TRUNK):
+        h = relu(lin(name, h))
+        if i == 4:
+            h = torch.cat([pe_pts, h], dim=-1)
+    sigma = _lin(params, names["alpha"], h)
+    albedo = torch.sigmoid(lin(names["albedo2"], relu(lin(names["albedo1"], h))))
+    shading = torch.sigmoid(lin(names["shading2"], relu(lin(names["shading1"], h))))
+    wv, wf = params[names["views"] + ".weight"], params[names["feature"] + ".weight"]
+    wc = wv[:, :256] @ wf
+    bc = wv[:, :256] @ params[names["feature"] + ".bias"] + params[names["views"] + ".bias"]
+    h2 = relu(rnd(h) @ rnd(wc).t() + rnd(pe_dir) @ rnd(wv[:, 256:]).t() + bc)
+    residual = torch.sigmoid(lin(names["residual"], h2))
+    cols = [albedo * shading + residual, sigma, albedo, shading, residual]
+    if variant == "ssr" and n_classes > 0:
+        cols.append(lin(names["sem2"], relu(lin(names["sem1"], h))))
+    if endpoint:
+        cols.append(h2)
+    return torch.cat(cols, dim=-1), torch.stack(margins, 0).amin(0)
+
+
 def query_field(pts, viewdirs, params, variant="object", n_classes=0, endpoint=False,
                 pe_scale_pts=1.0, netchunk=65536):
     """run_network: object_level/run_nerf.py:42-56, SSR/models/model_utils.py:19-35.

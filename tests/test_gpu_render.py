@@ -34,6 +34,31 @@ def _object_kwargs(coarse, fine, **over):
     return kw
 
 
+def _check_param_grads(pairs, precision):
+    """fp32 training mode: 2e-3 of each parameter's largest gradient vs the exact oracle.  Tensor-core mode: the same
+    oracle takes the other ReLU branch for ~0.05 % of the (sample, unit) pairs (fp16 operand rounding), each a
+    full-size difference in one sample's contribution - on these few-thousand-sample batches that is percent-level on
+    single entries, so the end-to-end bar is direction + magnitude (cosine > 0.999, norm within 2 %); the tight
+    per-entry bar of the tensor-core backward lives in test_gpu_train_tc.py against the kernel-arithmetic oracle."""
+    for ref, net in pairs:
+        for name, p in net.named_parameters():
+            a, b = ref[name].grad.double().reshape(-1), p.grad.cpu().double().reshape(-1)
+            if precision == "fp32":
+                assert float((a - b).abs().max()) < 2e-3 * float(a.abs().max()) + 1e-9, name
+            elif float(a.norm()) == 0.0:                     # a head the loss does not reach (e.g. the coarse colour heads)
+                assert float(b.abs().max()) < 1e-9, name
+            else:
+                cos = float((a @ b) / (a.norm() * b.norm() + 1e-300))
+                assert cos > 0.999 and abs(float(b.norm() / (a.norm() + 1e-300)) - 1.0) < 0.02, (name, cos)
+
+
+@pytest.fixture
+def train_precision(request, monkeypatch):
+    from intrinsicnerf_b200 import ops
+    monkeypatch.setattr(ops, "_DEFAULT_PRECISION", ops.PREC_FP32 if request.param == "fp32" else ops.PREC_TC)
+    return request.param
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
 def test_render_rays_golden(dev, golden_dir, obj_nets, precision):
     """The reference's own outputs (golden) for the deterministic, stochastic (pytest hooks),
@@ -218,7 +243,8 @@ def test_training_step_through_stage_kernels_with_foreign_network(dev):
             assert float((a - b).abs().max()) < 2e-3 * float(a.abs().max()) + 1e-9, name
 
 
-def test_training_step_with_our_modules(dev):
+@pytest.mark.parametrize("train_precision", ["fp32", "tc"], indirect=True)
+def test_training_step_with_our_modules(dev, train_precision):
     """run_nerf.py:942-1019 shape: render(..., retraw=True) under autograd with OUR NeRF modules, a loss
     on fine and coarse maps, loss.backward(): parameter gradients equal full autograd through the CPU
     oracle (perturb=0 so that both sides see identical samples)."""
@@ -237,10 +263,7 @@ def test_training_step_with_our_modules(dev):
     loss = ((out["rgb_map"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean() + 0.1 * out["albedo_map"].mean() \
         + 0.05 * out["shading_map"].mean() + 0.05 * out["residual0"].mean()
     loss.backward()
-    for ref, net in ((cc, coarse), (cf, fine)):
-        for name, p in net.named_parameters():
-            a, b = ref[name].grad, p.grad.cpu()
-            assert float((a - b).abs().max()) < 2e-3 * float(a.abs().max()) + 1e-9, name
+    _check_param_grads(((cc, coarse), (cf, fine)), train_precision)
     # and an optimizer step runs, after which the inference path sees the new weights
     opt = torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()), lr=5e-4)
     opt.step()
@@ -249,7 +272,8 @@ def test_training_step_with_our_modules(dev):
     assert torch.isfinite(after["rgb_map"]).all()
 
 
-def test_ssr_training_step(dev, golden_dir):
+@pytest.mark.parametrize("train_precision", ["fp32", "tc"], indirect=True)
+def test_ssr_training_step(dev, golden_dir, train_precision):
     """SSRTrainer.step shape (trainer.py:882-990): volumetric_rendering in training mode, cross-entropy on the
     semantic logits + photometric loss, backward through our kernels; gradients vs the oracle."""
     from intrinsicnerf_b200 import ssr
@@ -277,10 +301,7 @@ def test_ssr_training_step(dev, golden_dir):
     out = t.render_rays(rays.to(dev))
     lab = labels.to(dev)
     (ce(out["sem_logits_fine"], lab) + ce(out["sem_logits_coarse"], lab) + (out["rgb_fine"] ** 2).mean() + out["depth_fine"].mean()).backward()
-    for ref, net in ((cc, coarse), (cf, fine)):
-        for name, p in net.named_parameters():
-            a, b = ref[name].grad, p.grad.cpu()
-            assert float((a - b).abs().max()) < 2e-3 * float(a.abs().max()) + 1e-9, name
+    _check_param_grads(((cc, coarse), (cf, fine)), train_precision)
 
 
 def test_dense_grid_query_zero_viewdirs(dev):

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as orc
+from intrinsicnerf_b200 import ops as ops_mod
 from tests.util import build_nets, load_golden, rel_err, relu_margin
 
 pytestmark = pytest.mark.gpu
@@ -227,7 +228,7 @@ def test_raw2outputs_backward_matches_autograd(dev, white, C, endpoint, with_noi
 
 
 @pytest.mark.parametrize("variant,C,endpoint", [("object", 0, False), ("ssr", 28, True), ("ssr", 28, False), ("ssr", 5, False), ("ssr", 0, False)])
-def test_mlp_backward_matches_autograd(dev, variant, C, endpoint):
+def test_mlp_backward_matches_autograd(dev, variant, C, endpoint, monkeypatch):
     """k_mlp_bwd_fp32 (through ops.MlpFn and the module's torch.cat of parameters) vs PyTorch autograd
     through the oracle's functional MLP in float64."""
     coarse, fine, pc, pf = build_nets(variant, C)
@@ -248,6 +249,7 @@ def test_mlp_backward_matches_autograd(dev, variant, C, endpoint):
     g_raw = g_raw * keep[:, None]
     (out64 * g_raw.double()).sum().backward()
     fine.zero_grad()
+    monkeypatch.setattr(ops_mod, "_DEFAULT_PRECISION", ops_mod.PREC_FP32)      # the strict-fp32 training mode
     out = fine.evaluate("pts", pts.to(dev), vd.to(dev), endpoint, scale)
     assert rel_err(out.detach(), out64.detach(), floor=1e-2) < 2e-5
     (out * g_raw.to(dev)).sum().backward()

@@ -65,7 +65,12 @@ def ours_fwd_only():
         t.render_rays(rays)
 
 
-ms_ours = timeit(ours)
+from intrinsicnerf_b200 import ops  # noqa: E402
+
+ms_ours = timeit(ours)                       # default training mode: tensor cores (ops.MlpTcFn)
+ops.set_default_precision("fp32")
+ms_fp32 = timeit(ours)                       # strict fp32 CUDA-core mode (ops.MlpFn)
+ops.set_default_precision("tc")
 ms_inf = timeit(ours_fwd_only)
 
 torch.set_default_device("cuda")
@@ -86,6 +91,6 @@ def eager():
 
 ms_eager = timeit(eager)
 flop = N * 256 * 2 * (692224 + 128 * C) * 3
-print(f"TRAIN step (render+backward) N={N} rays, 64+128, C={C}: ours {ms_ours:.2f} ms ({flop / ms_ours / 1e9:.1f} TFLOP/s fp32), "
-      f"eager PyTorch composition on the same GPU {ms_eager:.2f} ms ({ms_eager / ms_ours:.2f}x); "
-      f"eval render of the same rays (tcgen05 path) {ms_inf:.2f} ms")
+print(f"TRAIN step (render+backward) N={N} rays, 64+128, C={C}: tensor-core mode {ms_ours:.2f} ms ({flop / ms_ours / 1e9:.1f} TFLOP/s), "
+      f"strict-fp32 mode {ms_fp32:.2f} ms, eager PyTorch composition on the same GPU {ms_eager:.2f} ms "
+      f"({ms_eager / ms_ours:.2f}x vs tensor-core mode); eval render of the same rays {ms_inf:.2f} ms")

@@ -74,3 +74,26 @@ def relu_margin(fn):
     finally:
         torch.relu = real
     return out, torch.stack(margins, 0).amin(0)
+
+
+def decode_images(buf, n_tiles, slots):
+    """Tensor-core operand images (include/inrf.h: inrf_mlp_fwd_train_tc) -> [n_tiles, slots, 128, 64] float32:
+    each image is 128 rows x 64 fp16 in 8-row atoms of 1024 B, the 16-byte unit index XORed with (row & 7)."""
+    x = buf[: n_tiles * slots * 16384].view(torch.float16).reshape(n_tiles, slots, 16, 8, 8, 8)
+    r = torch.arange(8, device=buf.device).view(8, 1)
+    u = torch.arange(8, device=buf.device).view(1, 8)
+    idx = (u ^ r).view(1, 1, 1, 8, 8, 1).expand(n_tiles, slots, 16, 8, 8, 8)
+    return torch.gather(x, 4, idx).reshape(n_tiles, slots, 128, 64).float()
+
+
+def stash_activations(stash, M, n_classes):
+    """Decoded forward stash -> dict of [M, width] activations: 'pe' 64, 'dir' 32, 'h0'..'h7' 256, 'v' 128, 'as' 256, ['s1' 128]."""
+    T = (M + 127) // 128
+    img = decode_images(stash, T, 42)
+    rows = lambda s0, n: img[:, s0:s0 + n].permute(0, 2, 1, 3).reshape(T * 128, 64 * n)[:M].cpu()  # noqa: E731
+    out = {"pe": rows(0, 1), "dir": rows(1, 1)[:, :32], "v": rows(34, 2), "as": rows(36, 4)}
+    for l in range(8):
+        out[f"h{l}"] = rows(2 + 4 * l, 4)
+    if n_classes > 0:
+        out["s1"] = rows(40, 2)
+    return out
