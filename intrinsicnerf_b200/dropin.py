@@ -10,7 +10,7 @@ from . import ssr as _ssr
 
 _OBJECT_NAMES = ("Embedder", "get_embedder", "NeRF", "sample_pdf", "get_rays", "get_rays_np", "ndc_rays", "batchify",
                  "run_network", "batchify_rays", "render", "render_rays", "raw2outputs", "create_nerf",
-                 "compute_intrinsic_loss")
+                 "compute_intrinsic_loss", "render_path", "img2mse", "to8b")
 
 
 def install_object_level(run_nerf_module, helpers_module=None):
@@ -27,7 +27,7 @@ def install_ssr(trainer_module=None, model_utils_module=None, rays_module=None, 
     if trainer_module is not None:
         _ssr.install_into(trainer_module.SSRTrainer)
         for name in ("run_network", "raw2outputs", "sample_pdf", "batchify_rays", "get_embedder", "Semantic_NeRF", "create_rays",
-                     "compute_intrinsic_loss"):
+                     "compute_intrinsic_loss", "Cluster_Manager"):
             if hasattr(trainer_module, name):
                 setattr(trainer_module, name, getattr(_ssr, name))
     if model_utils_module is not None:

@@ -14,9 +14,18 @@ rebinds them on the reference's ``SSRTrainer`` so ``train_SSR_main.py`` runs unc
 """
 import torch
 
+from . import cluster as _cluster
 from . import ops
 from .nerf import Embedder, Semantic_NeRF, get_embedder  # noqa: F401
 from .object_level import batchify, _split_rec  # noqa: F401
+
+
+class Cluster_Manager(_cluster.Cluster_Manager):
+    """SSR/training/cluster.py's manager: the shared implementation with the fork's two deviations switched on
+    (cluster dirs relative to the config dir; class_num == 1 ignores the labels)."""
+
+    def __init__(self, class_num=0, cluster_config_file=None, device=torch.device("cuda")):
+        super().__init__(class_num=class_num, cluster_config_file=cluster_config_file, ssr_semantics=True, device=device)
 
 
 def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
@@ -215,7 +224,6 @@ class SSRRenderer:
         dependency of the reference): produced when imgviz is importable, else None."""
         import os
         import numpy as np
-        from .cluster import Cluster_Manager
         from .object_level import imwrite
         try:
             from imgviz import depth2rgb
@@ -281,7 +289,7 @@ class SSRRenderer:
         if update_cluster:
             px, lb = torch.cat(sample_pixels, 0), torch.cat(sample_labels, 0)
             n_cls = 1 if getattr(self, "no_semantic_tree", False) else self.num_valid_semantic_class
-            cluster_manager = Cluster_Manager(class_num=n_cls, ssr_semantics=True, device=px.device)
+            cluster_manager = Cluster_Manager(class_num=n_cls, device=px.device)
             print(px.shape, lb.shape)
             cluster_manager.update_center(lb, px, band_factor=b_f)
             print("cluster albedo...")

@@ -22,8 +22,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_uniform", "smsp__cycles_active.avg"]
 
 
-def launches(tag):
-    src = os.path.join(GP, "launches.csv")
+def launches(tag, csv_name="launches.csv", out_name="launches_summary", command="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"):
+    src = os.path.join(GP, csv_name)
     if not os.path.exists(src):
         return
     rows = []
@@ -40,9 +40,9 @@ def launches(tag):
         agg[k][0] += 1
         agg[k][1] += v
     tot = sum(v for _, v in rows)
-    with open(os.path.join(OUT, f"{tag}_launches_summary.md"), "w") as f:
+    with open(os.path.join(OUT, f"{tag}_{out_name}.md"), "w") as f:
         f.write(f"# Launch list summary ({tag})\n\nncu --metrics gpu__time_duration.sum --clock-control none, command: "
-                "`python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (cold-cache, serialised: compare shares).\n\n"
+                f"`{command}` (cold-cache, serialised: compare shares).\n\n"
                 f"{len(rows)} launches, {tot / 1e3:.2f} ms total\n\n| kernel | launches | total us | share | avg us |\n|---|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {k} | {n} | {t:.1f} | {100 * t / tot:.1f}% | {t / n:.1f} |\n")
@@ -72,6 +72,7 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
+    launches(tag, "launches_train.csv", "launches_train_summary", "python tests/tools/train_target.py  (3 SSR training steps: render + backward, 1024 rays)")
     for n in sorted(os.listdir(GP)):
         if n.endswith(".ncu-rep"):
             full(tag, n[:-8])
