@@ -286,9 +286,9 @@ def main():
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": ach_tf / pk["bf16_tflops"],
-                     # DRAM bytes per launch: ncu --set full of the same kernel (profiles/r01b_prof_mlp_tc_r01b_raw.md):
-                     # (35.2 MB read + 282.3 MB written) / 7 680 000 rows = 41.3 B/row vs 48 B/row algorithmic (44 raw + 4 z)
-                     "traffic": (b - a) * (N_SAMPLES + N_IMPORTANCE) * 41.3, "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)",
+                     # DRAM bytes per launch: ncu --set full of the same kernel (profiles/r01e_prof_mlp_tc_raw.md):
+                     # (35.1 MB read + 282.7 MB written) / 7 680 000 rows = 41.4 B/row vs 48 B/row algorithmic (44 raw + 4 z)
+                     "traffic": (b - a) * (N_SAMPLES + N_IMPORTANCE) * 41.4, "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)",
                      "kernel_ms": k_ms, "launch_rows": (b - a) * (N_SAMPLES + N_IMPORTANCE),
                      "whole_step_frac": value / world * FLOP_PER_RAY / 1e12 / (pk["bf16_sustained"] or pk["bf16_tflops"]),
                      "hbm_frac_algorithmic": value / world * BYTES_PER_RAY / 1e9 / pk["hbm_gbs"]},
