@@ -553,7 +553,7 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   }
 
   // ---- dW: one launch, one item per (GEMM, 128 output rows) --------------------------------------------
-  static DwParams D;                       // 9 KB table, rebuilt per call (single-threaded host semantics like the reference)
+  DwParams D;                              // 9 KB launch table, rebuilt per call (pointers depend on the caller's buffers)
   memset(&D, 0, sizeof(D));
   D.n_tiles = (int)T; D.amax_bits = amax; D.dbg = dbg;
   float* gf = a.grad_flat;

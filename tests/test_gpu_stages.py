@@ -151,6 +151,16 @@ def test_merge_sorted_exact(dev):
         assert torch.equal(out.cpu(), want)
         if Sb > 0:
             assert rel_err(std, torch.std(zb, dim=-1, unbiased=False), floor=1e-3) < 1e-5
+    # both lists ascending (what the renderer passes): the rank-merge fast path, incl. ties within and across lists
+    for Sa, Sb, N in ((64, 128, 4099), (64, 0, 7), (5, 3, 9), (1, 1, 3), (300, 724, 5), (1, 128, 2)):
+        za = torch.sort(torch.rand(N, Sa, generator=gen) * 4 + 2, dim=-1)[0]
+        zb = torch.sort(torch.rand(N, Sb, generator=gen) * 4 + 2, dim=-1)[0]
+        if Sb > 2:
+            zb[:, 1] = zb[:, 0]
+            zb[:, 2] = za[:, min(2, Sa - 1)]
+            zb = torch.sort(zb, dim=-1)[0]
+        out, std = ops.merge_sorted(za.to(dev), zb.to(dev), Sb > 0)
+        assert torch.equal(out.cpu(), torch.sort(torch.cat([za, zb], -1), -1)[0]), (Sa, Sb)
     from intrinsicnerf_b200._lib import InrfError
     with pytest.raises(InrfError):
         ops.merge_sorted(torch.zeros(2, 1000, device=dev), torch.zeros(2, 100, device=dev))

@@ -40,3 +40,22 @@ t0 = time.perf_counter()
 idx, _ = co.nearest_anchor(c.anchors.cpu(), co.map_color(px[:20000]))
 t_cpu = time.perf_counter() - t0
 print(f"CLUSTER_BENCH cpu_oracle nearest_anchor 20000 px x {A} anchors: {t_cpu:.3f}s ({20000 / t_cpu / 1e3:.1f} kpx/s, {torch.get_num_threads()} threads)")
+# the reference's update_center core (sklearn on the host, cluster.py:136-141) on a bounded sample of the same mixture
+try:
+    import numpy as np
+    from sklearn.cluster import MeanShift, estimate_bandwidth
+    Ps = min(P, 200000)
+    X = co.map_color(px[:Ps]).numpy()
+    t0 = time.perf_counter()
+    bw = max(estimate_bandwidth(X, quantile=0.3, n_samples=5000) * 0.5, 0.01)
+    ms = MeanShift(bandwidth=bw, bin_seeding=True).fit(X)
+    t_sk = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    c2 = cl.Cluster(device=dev)
+    c2.update_center(px[:Ps].numpy(), band_factor=0.5)
+    torch.cuda.synchronize()
+    t_us = time.perf_counter() - t0
+    print(f"CLUSTER_BENCH update_center on {Ps} px: sklearn estimate_bandwidth + MeanShift(bin_seeding) on the host {t_sk:.2f}s "
+          f"({len(ms.cluster_centers_)} clusters) vs CUDA path {t_us:.3f}s ({c2.rgb_centers.shape[0]} clusters)")
+except ImportError:
+    pass
