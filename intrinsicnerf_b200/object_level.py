@@ -317,30 +317,42 @@ def render_record(H, W, K, chunk, c2w, near=0., far=1., **kwargs):
 
 
 def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
-                update_cluster=False, b_f=0.5):
+                update_cluster=False, b_f=0.5, sharded=False, group=None):
     """Mirror of run_nerf.py:142-272 -> (rgbs [n,H,W,3], disps [n,H,W], cluster_manager).  Per frame the
     reference copies six float maps to the host (48 B/pixel) and converts them with numpy; here the frame's record
     stays in HBM, inrf_frame_finish writes the 8-bit planes (11 B/pixel cross PCIe, plus the rgb/disp floats this
     function returns) and the albedo[::2, ::2] cluster samples, and the c###/edit### pass (dest_color +
-    inrf_edit_recompose) runs on the resident records instead of re-uploading every albedo map."""
+    inrf_edit_recompose) runs on the resident records instead of re-uploading every albedo map.
+
+    ``sharded=True`` under torch.distributed (BASELINE config 4: 100 views over 8 GPUs): rank r renders views
+    r, r+world, ... (parallel.image_shard) and writes their PNGs under the global view index; the cluster samples are
+    all-gathered so that every rank fits the same (deterministic) cluster manager, and rgbs / disps come back complete
+    and in view order on every rank (one NCCL all-gather of 16 B/pixel)."""
+    from . import parallel
     from .cluster import Cluster_Manager
+    import torch.distributed as dist
     H, W, focal = hwf
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
     H, W = int(H), int(W)
     kw = dict(render_kwargs)
     near, far = kw.pop("near", 0.), kw.pop("far", 1.)
-    rgbs, disps, recs, labels, sample_pixels, sample_labels = [], [], [], [], [], []
+    n_views = len(render_poses)
+    world = dist.get_world_size(group) if (sharded and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    mine = parallel.image_shard(n_views, rank, world)
+    rgbd, recs, labels, sample_pixels, sample_labels = [], [], [], [], []
     planes = ("rgb8", "albedo8", "shading8", "residual8", "label8") + (("labels64",) if update_cluster else ())
-    for i, c2w in enumerate(render_poses):
-        c2w = torch.as_tensor(c2w)[:3, :4]
+    dev = None
+    for i in mine:
+        c2w = torch.as_tensor(render_poses[i])[:3, :4]
         with torch.no_grad():
             rec = render_record(H, W, K, chunk, c2w, near=near, far=far, **kw)
             f = ops.frame_finish(rec, H, W, 0, planes, acc_threshold=10.0, sub_step=2 if update_cluster else 0)
-        rgbs.append(rec[:, 0:3].reshape(H, W, 3).cpu().numpy())
-        disps.append(rec[:, 3].reshape(H, W).cpu().numpy())
-        if i == 0:
-            print(rgbs[-1].shape, disps[-1].shape)
+        dev = rec.device
+        rgbd.append(rec[:, 0:4].reshape(H, W, 4))
+        if i == mine[0]:
+            print((H, W, 3), (H, W))
         if update_cluster:
             recs.append(rec)
             labels.append(f["labels64"])
@@ -349,6 +361,24 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
         if savedir is not None:
             for prefix, name in (("", "rgb8"), ("a", "albedo8"), ("s", "shading8"), ("res", "residual8"), ("acc", "label8")):
                 imwrite(os.path.join(savedir, "{}{:03d}.png".format(prefix, i)), f[name])
+    if world > 1:
+        dev = dev or torch.device("cuda", torch.cuda.current_device())
+        per = (n_views + world - 1) // world                                     # views per rank, padded
+
+        def gather_views(parts, tail, dtype):                                    # [n_mine, *tail] -> [n_views, *tail] in view order
+            buf = torch.zeros((per,) + tail, dtype=dtype, device=dev)
+            if parts:
+                buf[: len(parts)] = torch.stack(parts, 0)
+            out = torch.empty((world, per) + tail, dtype=dtype, device=dev)
+            dist.all_gather_into_tensor(out.view((world * per,) + tail), buf, group=group)
+            return out.transpose(0, 1).reshape((world * per,) + tail)[:n_views]   # view v sits at [v % world, v // world]
+        all_rgbd = gather_views(rgbd, (H, W, 4), torch.float32)
+        if update_cluster:
+            ns = ((H + 1) // 2) * ((W + 1) // 2)
+            sample_pixels = list(gather_views(sample_pixels, (ns, 3), torch.float32))
+            sample_labels = list(gather_views(sample_labels, (ns, 1), torch.int64))
+    else:
+        all_rgbd = torch.stack(rgbd, 0) if rgbd else torch.zeros(0, H, W, 4)
     cluster_manager = None
     if update_cluster:
         sample_pixels, sample_labels = torch.cat(sample_pixels, 0), torch.cat(sample_labels, 0)
@@ -356,13 +386,14 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
         print(sample_pixels.shape, sample_labels.shape)
         cluster_manager.update_center(sample_labels, sample_pixels, band_factor=b_f)
         print("cluster albedo...")
-        for i, rec in enumerate(recs):
-            result = cluster_manager.dest_color(rec[:, 5:8].contiguous(), labels[i].reshape(-1, 1))
+        for i, rec, lab in zip(mine, recs, labels):
+            result = cluster_manager.dest_color(rec[:, 5:8].contiguous(), lab.reshape(-1, 1))
             c8, e8 = ops.edit_recompose(result, rec)
             if savedir is not None:
                 imwrite(os.path.join(savedir, "c{:03d}.png".format(i)), c8.reshape(H, W, 3))
                 imwrite(os.path.join(savedir, "edit{:03d}.png".format(i)), e8.reshape(H, W, 3))
-    return np.stack(rgbs, 0), np.stack(disps, 0), cluster_manager
+    host = all_rgbd.cpu().numpy()
+    return np.ascontiguousarray(host[..., 0:3]), np.ascontiguousarray(host[..., 3]), cluster_manager
 
 
 def create_nerf(args, device=None):

@@ -44,11 +44,38 @@ if rank == 0:
     print(f"MULTI frame {H}x{W} over {world} GPUs: pipelined gather == single-GPU frame on every rank: {bool(flag.item())}; "
           f"{ev0.elapsed_time(ev1):.2f} ms per frame")
 
+# ---- 1b. image-sharded render_path (config 4 shape: views round-robin over the ranks) -----------------------------------
+import contextlib  # noqa: E402
+import io  # noqa: E402
+import tempfile  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+e10, _ = ol.get_embedder(10, 0)
+e4, _ = ol.get_embedder(4, 0)
+kwp = dict(network_fn=coarse, network_fine=fine, network_query_fn=ol._FusedQuery(e10, e4, 65536), N_samples=64, N_importance=128,
+           perturb=False, white_bkgd=True, raw_noise_std=0., use_viewdirs=True, ndc=False, lindisp=False, near=2., far=6.)
+Hs = Ws = 48
+Ks = orc.blender_intrinsics(Hs, Ws)
+poses = [torch.tensor(orc.pose_spherical(a, -30.0, 4.0)).float() for a in (0.0, 50.0, 100.0, 150.0, 200.0)]
+with tempfile.TemporaryDirectory() as d1, tempfile.TemporaryDirectory() as d2, contextlib.redirect_stdout(io.StringIO()):
+    r1, dsp1, cm1 = ol.render_path(poses, (Hs, Ws, Ks[0][0]), Ks, 4096, kwp, savedir=d1, update_cluster=True)
+    r2, dsp2, cm2 = ol.render_path(poses, (Hs, Ws, Ks[0][0]), Ks, 4096, kwp, savedir=d2, update_cluster=True, sharded=True)
+    mine = parallel.image_shard(len(poses), rank, world)
+    files_ok = all(open(os.path.join(d1, f"{p}{i:03d}.png"), "rb").read() == open(os.path.join(d2, f"{p}{i:03d}.png"), "rb").read()
+                   for i in mine for p in ("", "a", "s", "res", "acc", "c", "edit"))
+    n_files = len(os.listdir(d2))
+ok = np.array_equal(r1, r2) and np.array_equal(dsp1, dsp2, equal_nan=True) and files_ok and n_files == 7 * len(mine) \
+    and torch.equal(cm1.clusters[0].anchors, cm2.clusters[0].anchors) and torch.equal(cm1.clusters[0].rgb_centers, cm2.clusters[0].rgb_centers)
+flag = torch.tensor([int(ok)], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"MULTI render_path over {world} GPUs ({len(poses)} views {Hs}x{Ws}, update_cluster): maps, PNG bytes and cluster state equal the "
+          f"single-process run on every rank: {bool(flag.item())}")
+
 # ---- 2. data-parallel training step ----------------------------------------------------------------------------------------
 ops.set_default_precision("fp32")
 N = 512
-e10, _ = ol.get_embedder(10, 0)
-e4, _ = ol.get_embedder(4, 0)
 kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=ol._FusedQuery(e10, e4, 65536), N_samples=64, N_importance=128,
           perturb=0., white_bkgd=True, raw_noise_std=0.)
 batch = rays[torch.randperm(H * W, generator=torch.Generator().manual_seed(0))[:N].to(dev)]
