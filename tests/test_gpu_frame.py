@@ -118,7 +118,7 @@ def test_object_render_path_end_to_end(tmp_path):
               perturb=False, white_bkgd=True, raw_noise_std=0., use_viewdirs=True, ndc=False, lindisp=False, near=2., far=6.)
     H = W = 40
     K = np.array([[55.0, 0, 20.0], [0, 55.0, 20.0], [0, 0, 1]], dtype=np.float32)
-    poses = [torch.tensor(orc.pose_spherical(a, -30.0, 4.0)).float() for a in (20.0, 140.0)]
+    poses = [torch.as_tensor(orc.pose_spherical(a, -30.0, 4.0)).float() for a in (20.0, 140.0)]
     rgbs, disps, cm = ol.render_path(poses, (H, W, 55.0), K, 1024, kw, savedir=str(tmp_path), update_cluster=True)
     assert rgbs.shape == (2, H, W, 3) and disps.shape == (2, H, W) and cm is not None and cm.clusters[0] is not None
     for i, pose in enumerate(poses):
