@@ -293,6 +293,42 @@ def imwrite(filename, array):
     cv2.imwrite(filename, array[..., ::-1] if array.ndim == 3 and array.shape[-1] == 3 else array)
 
 
+class _FrameWriter:
+    """Host hand-over of finished frames, one frame behind the renderer: the planes of frame k are copied to pinned
+    host memory on a side stream (ordered after frame k's kernels only) and written as PNGs while the GPU renders
+    frame k+1 - the reference's loop instead blocks on `.cpu()` and encodes with the GPU idle (run_nerf.py:168-215)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.pending = None
+
+    def submit(self, planes, names):
+        """planes: {name: device uint8/uint16 tensor}; names: {name: file path}.  Returns immediately."""
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        host = {}
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for k, path in names.items():
+                t = planes[k]
+                t.record_stream(self.stream)
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t, non_blocking=True)
+                host[path] = h
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.flush()                                   # write the PREVIOUS frame while this one's copies are in flight
+        self.pending = (done, host)
+
+    def flush(self):
+        if self.pending is not None:
+            done, host = self.pending
+            done.synchronize()
+            for path, h in host.items():
+                imwrite(path, h.numpy())
+            self.pending = None
+
+
 def render_record(H, W, K, chunk, c2w, near=0., far=1., **kwargs):
     """One full frame as the packed per-ray record [H*W, 13] (include/inrf.h) - what render() slices its six
     maps out of, kept whole so that the frame kernels read every pixel once."""
@@ -344,6 +380,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
     rgbd, recs, labels, sample_pixels, sample_labels = [], [], [], [], []
     planes = ("rgb8", "albedo8", "shading8", "residual8", "label8") + (("labels64",) if update_cluster else ())
     dev = None
+    writer = None
     for i in mine:
         c2w = torch.as_tensor(render_poses[i])[:3, :4]
         with torch.no_grad():
@@ -359,8 +396,11 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
             sample_pixels.append(f["sample_pixels"])
             sample_labels.append(f["sample_labels"])
         if savedir is not None:
-            for prefix, name in (("", "rgb8"), ("a", "albedo8"), ("s", "shading8"), ("res", "residual8"), ("acc", "label8")):
-                imwrite(os.path.join(savedir, "{}{:03d}.png".format(prefix, i)), f[name])
+            writer = writer or _FrameWriter(dev)
+            writer.submit(f, {name: os.path.join(savedir, "{}{:03d}.png".format(prefix, i)) for prefix, name in
+                              (("", "rgb8"), ("a", "albedo8"), ("s", "shading8"), ("res", "residual8"), ("acc", "label8"))})
+    if writer is not None:
+        writer.flush()
     if world > 1:
         dev = dev or torch.device("cuda", torch.cuda.current_device())
         per = (n_views + world - 1) // world                                     # views per rank, padded
@@ -390,8 +430,11 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
             result = cluster_manager.dest_color(rec[:, 5:8].contiguous(), lab.reshape(-1, 1))
             c8, e8 = ops.edit_recompose(result, rec)
             if savedir is not None:
-                imwrite(os.path.join(savedir, "c{:03d}.png".format(i)), c8.reshape(H, W, 3))
-                imwrite(os.path.join(savedir, "edit{:03d}.png".format(i)), e8.reshape(H, W, 3))
+                writer = writer or _FrameWriter(rec.device)
+                writer.submit({"c8": c8.reshape(H, W, 3), "edit8": e8.reshape(H, W, 3)},
+                              {"c8": os.path.join(savedir, "c{:03d}.png".format(i)), "edit8": os.path.join(savedir, "edit{:03d}.png".format(i))})
+        if writer is not None:
+            writer.flush()
     host = all_rgbd.cpu().numpy()
     return np.ascontiguousarray(host[..., 0:3]), np.ascontiguousarray(host[..., 3]), cluster_manager
 

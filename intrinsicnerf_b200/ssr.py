@@ -235,31 +235,21 @@ class SSRRenderer:
         planes = ["rgb8", "albedo8", "shading8", "residual8", "disp16", "depth_mm16"]
         if sem:
             planes += ["label8", "vis_label8", "entropy", "entropy8", "labels64"]
-        keep = {k: [] for k in ("rgb", "disp", "dep", "vis_dep", "sem", "vis_sem", "ent", "vis_ent", "albedo", "shading", "residual")}
-        recs, labels, sample_pixels, sample_labels = [], [], [], []
+        from .object_level import _FrameWriter
+        base, sem_dev, recs, labels, sample_pixels, sample_labels = [], [], [], [], [], []
+        writer = None
+        n_frames = len(rays)
         was_training = bool(self.training)
         self.training = False
         try:
-            for i in range(len(rays)):
+            for i in range(n_frames):
                 with torch.no_grad():
                     rec = self.render_record(rays[i].reshape(-1, rays[i].shape[-1]))
                     f = ops.frame_finish(rec, H, W, C, tuple(planes), colour_map=self.valid_colour_map if sem else None,
                                          sub_step=2 if (update_cluster and sem) else 0)
-                host = rec[:, :13].cpu().numpy()
-                keep["rgb"].append(host[:, 0:3].reshape(H, W, 3))
-                keep["disp"].append(host[:, 3].reshape(H, W))
-                keep["albedo"].append(host[:, 5:8].reshape(H, W, 3))
-                keep["shading"].append(host[:, 8].reshape(H, W))
-                keep["residual"].append(host[:, 9:12].reshape(H, W, 3))
-                keep["dep"].append(host[:, 12].reshape(H, W))
-                if depth2rgb is not None:
-                    keep["vis_dep"].append(depth2rgb(keep["dep"][-1], min_value=self.near, max_value=self.far))
+                base.append(rec[:, :13] if rec.shape[1] == 13 else rec[:, :13].contiguous())     # the float maps the caller gets back
                 if sem:
-                    keep["sem"].append(f["label8"].cpu().numpy())
-                    keep["vis_sem"].append(f["vis_label8"].cpu().numpy())
-                    keep["ent"].append(f["entropy"].cpu().numpy())
-                    if depth2rgb is not None:
-                        keep["vis_ent"].append(depth2rgb(keep["ent"][-1]))
+                    sem_dev.append((f["label8"], f["vis_label8"], f["entropy"]))
                 if update_cluster:
                     if not sem:
                         raise NotImplementedError("update_cluster needs enable_semantic (the reference reads sem_label here)")
@@ -268,23 +258,41 @@ class SSRRenderer:
                     sample_pixels.append(f["sample_pixels"])
                     sample_labels.append(f["sample_labels"])
                 if i == 0:
-                    print(keep["rgb"][-1].shape, keep["disp"][-1].shape)
+                    print((H, W, 3), (H, W))
                 if save_dir is not None:
                     assert os.path.exists(save_dir)
-                    for name, plane in (("rgb", "rgb8"), ("disp", "disp16"), ("albedo", "albedo8"), ("shading", "shading8"),
-                                        ("residual", "residual8"), ("depth", "depth_mm16")):
-                        imwrite(os.path.join(save_dir, "{}_{:03d}.png".format(name, i)), f[plane])
-                    if keep["vis_dep"]:
-                        imwrite(os.path.join(save_dir, "vis_depth_{:03d}.png".format(i)), keep["vis_dep"][-1])
+                    names = {plane: os.path.join(save_dir, "{}_{:03d}.png".format(name, i)) for name, plane in
+                             (("rgb", "rgb8"), ("disp", "disp16"), ("albedo", "albedo8"), ("shading", "shading8"),
+                              ("residual", "residual8"), ("depth", "depth_mm16"))}
                     if sem:
-                        imwrite(os.path.join(save_dir, "label_{:03d}.png".format(i)), f["label8"])
-                        imwrite(os.path.join(save_dir, "vis_label_{:03d}.png".format(i)), f["vis_label8"])
-                        imwrite(os.path.join(save_dir, "entropy_{:03d}.png".format(i)), f["entropy8"])
-                        if keep["vis_ent"]:
-                            imwrite(os.path.join(save_dir, "vis_entropy_{:03d}.png".format(i)), keep["vis_ent"][-1])
+                        names.update({plane: os.path.join(save_dir, "{}_{:03d}.png".format(name, i)) for name, plane in
+                                      (("label", "label8"), ("vis_label", "vis_label8"), ("entropy", "entropy8"))})
+                    writer = writer or _FrameWriter(rec.device)
+                    writer.submit(f, names)              # PNGs of frame i are written while frame i+1 renders
+            if writer is not None:
+                writer.flush()
         finally:
             self.training = was_training
-        st = lambda k: np.stack(keep[k], 0) if keep[k] else None  # noqa: E731
+        # one device->host copy of the returned float maps for all frames (the reference does six per frame)
+        host = torch.stack(base, 0).cpu().numpy() if base else np.zeros((0, H * W, 13), np.float32)
+        keep = {"rgb": host[:, :, 0:3].reshape(n_frames, H, W, 3), "disp": host[:, :, 3].reshape(n_frames, H, W),
+                "albedo": host[:, :, 5:8].reshape(n_frames, H, W, 3), "shading": host[:, :, 8].reshape(n_frames, H, W),
+                "residual": host[:, :, 9:12].reshape(n_frames, H, W, 3), "dep": host[:, :, 12].reshape(n_frames, H, W),
+                "vis_dep": None, "sem": None, "vis_sem": None, "ent": None, "vis_ent": None}
+        if sem and sem_dev:
+            keep["sem"] = torch.stack([t[0] for t in sem_dev], 0).cpu().numpy()
+            keep["vis_sem"] = torch.stack([t[1] for t in sem_dev], 0).cpu().numpy()
+            keep["ent"] = torch.stack([t[2] for t in sem_dev], 0).cpu().numpy()
+        if depth2rgb is not None and n_frames:             # imgviz colourisations (host-side visualisation only)
+            keep["vis_dep"] = np.stack([depth2rgb(d, min_value=self.near, max_value=self.far) for d in keep["dep"]], 0)
+            if keep["ent"] is not None:
+                keep["vis_ent"] = np.stack([depth2rgb(e) for e in keep["ent"]], 0)
+            if save_dir is not None:
+                for i in range(n_frames):
+                    imwrite(os.path.join(save_dir, "vis_depth_{:03d}.png".format(i)), keep["vis_dep"][i])
+                    if keep["vis_ent"] is not None:
+                        imwrite(os.path.join(save_dir, "vis_entropy_{:03d}.png".format(i)), keep["vis_ent"][i])
+        st = lambda k: (np.ascontiguousarray(keep[k]) if keep[k] is not None and n_frames else None)  # noqa: E731
         cluster_manager = None
         if update_cluster:
             px, lb = torch.cat(sample_pixels, 0), torch.cat(sample_labels, 0)
@@ -297,8 +305,11 @@ class SSRRenderer:
                 result = cluster_manager.dest_color(rec[:, 5:8].contiguous(), labels[i].reshape(-1, 1))
                 c8, e8 = ops.edit_recompose(result, rec)
                 if save_dir is not None:
-                    imwrite(os.path.join(save_dir, "c{:03d}.png".format(i)), c8.reshape(H, W, 3))
-                    imwrite(os.path.join(save_dir, "edit{:03d}.png".format(i)), e8.reshape(H, W, 3))
+                    writer = writer or _FrameWriter(rec.device)
+                    writer.submit({"c8": c8.reshape(H, W, 3), "edit8": e8.reshape(H, W, 3)},
+                                  {"c8": os.path.join(save_dir, "c{:03d}.png".format(i)), "edit8": os.path.join(save_dir, "edit{:03d}.png".format(i))})
+            if writer is not None:
+                writer.flush()
         return (st("rgb"), st("disp"), st("dep"), st("vis_dep"), st("sem"), st("vis_sem"), st("ent"), st("vis_ent"),
                 st("albedo"), st("shading"), st("residual"), cluster_manager)
 
