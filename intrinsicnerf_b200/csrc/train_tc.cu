@@ -434,14 +434,30 @@ __global__ void k_unfold_comp(const float* __restrict__ flat, NetLayout L, const
   const float* dwc = dcomp;
   const float* dbc = dcomp + 128 * W_HID;
   const int j = threadIdx.x;               // 256 threads
-  if (blockIdx.x < 128) {                  // dWv1[n][j]
-    const int n = blockIdx.x;
-    float acc = dbc[n] * fb[j];
-    for (int k = 0; k < W_HID; ++k) acc = fmaf(dwc[n * W_HID + k], fw[j * W_HID + k], acc);
-    grad[L.flat_w[L_VIEWS] + n * (W_HID + PE_DIR) + j] += acc;
-    if (j == 0) grad[L.flat_b[L_VIEWS] + n] += dbc[n];
+  if (blockIdx.x < 16) {                   // dWv1[n][j] for 8 rows n per block; Wf is staged through shared memory in
+    __shared__ float s_fw[256][33];        // 32-column slabs so that the global reads run along k (coalesced)
+    __shared__ float s_dw[8][32];
+    const int n0 = blockIdx.x * 8;
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = dbc[n0 + r] * fb[j];
+    for (int k0 = 0; k0 < W_HID; k0 += 32) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < 256 * 32; e += 256) s_fw[e >> 5][e & 31] = fw[(e >> 5) * W_HID + k0 + (e & 31)];
+      s_dw[j >> 5][j & 31] = dwc[(n0 + (j >> 5)) * W_HID + k0 + (j & 31)];
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < 32; ++kk) {
+        const float w = s_fw[j][kk];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(s_dw[r][kk], w, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) grad[L.flat_w[L_VIEWS] + (n0 + r) * (W_HID + PE_DIR) + j] += acc[r];
+    if (j < 8) grad[L.flat_b[L_VIEWS] + n0 + j] += dbc[n0 + j];
   } else {                                 // dWf[jf][k = thread], dbf[jf]
-    const int jf = blockIdx.x - 128, k = threadIdx.x;
+    const int jf = blockIdx.x - 16, k = threadIdx.x;
     float acc = 0.f, accb = 0.f;
     for (int n = 0; n < 128; ++n) {
       const float w = vw[n * (W_HID + PE_DIR) + jf];
@@ -598,7 +614,7 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   INRF_CUDA(cudaFuncSetAttribute(k_gemm_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
   k_gemm_dw<<<dim3(D.n_items, splits), DW_THREADS, DW_SMEM, st>>>(D);
   INRF_LAUNCH_CHECK();
-  k_unfold_comp<<<128 + 256, 256, 0, st>>>(a.flat, L, dcomp, gf);
+  k_unfold_comp<<<16 + 256, 256, 0, st>>>(a.flat, L, dcomp, gf);
   INRF_LAUNCH_CHECK();
   if (checked) {
     int h[8];

@@ -161,8 +161,12 @@ class SSRRenderer:
             ret["raw_fine"] = o["raw_fine"]
             if self.endpoint_feat:
                 ret["feat_map_fine"] = o["rec_fine"][:, 13 + C:13 + C + 128]
-        for k in ret:
-            if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
+        # the reference's per-key "contains nan or inf" report (trainer.py:804-806) with ONE host synchronisation
+        # instead of two per key
+        keys = list(ret)
+        bad = torch.stack([(~torch.isfinite(ret[k])).any() for k in keys]).tolist()
+        for k, b in zip(keys, bad):
+            if b:
                 print(f"! [Numerical Error] {k} contains nan or inf.")
         return ret
 
