@@ -83,3 +83,27 @@ def test_seeded_init_equals_oracle_init():
     p = orc.init_params("object")
     for k, v in net.state_dict().items():
         assert torch.equal(v, p[k]), k
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors of InrfRenderCfg / InrfFramePlanes have the size and field offsets a C compiler gives the
+    header's structs (include/inrf.h is plain C: it must also compile as C, not only as C++/CUDA)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    fields_cfg = [n for n, _ in _lib.RenderCfg._fields_]
+    fields_pl = [n for n, _ in _lib.FramePlanes._fields_]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER}"', 'int main(void) {',
+             '  printf("%zu %zu\\n", sizeof(InrfRenderCfg), sizeof(InrfFramePlanes));']
+    lines += [f'  printf("%zu\\n", offsetof(InrfRenderCfg, {f}));' for f in fields_cfg]
+    lines += [f'  printf("%zu\\n", offsetof(InrfFramePlanes, {f}));' for f in fields_pl]
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert [int(out[0]), int(out[1])] == [C.sizeof(_lib.RenderCfg), C.sizeof(_lib.FramePlanes)]
+    want = [getattr(_lib.RenderCfg, f).offset for f in fields_cfg] + [getattr(_lib.FramePlanes, f).offset for f in fields_pl]
+    assert [int(x) for x in out[2:]] == want
