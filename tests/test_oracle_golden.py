@@ -191,3 +191,49 @@ def test_oracle_losses_match_reference(golden_dir, fork, tag):
     (terms * torch.tensor(g["loss_weights"])).sum().backward()
     for k in ("albedo", "shading", "residual", "rgb"):
         assert torch.allclose(tt[k].grad, torch.tensor(g[f"loss_{fork}_{tag}_g_{k}"]), rtol=1e-10, atol=1e-14), k
+
+
+def test_tc_arithmetic_oracle_is_the_same_network():
+    """oracle.mlp_forward_tc_arith (fp16-rounded GEMM operands, the arithmetic of the tensor-core kernels) evaluates the
+    same network as mlp_forward: values agree to the operand-rounding level, pinning its own ReLU branch decisions
+    changes nothing, and its straight-through gradient is close to the exact one on samples away from the ReLU kinks."""
+    import torch
+    from oracle import nerf_oracle as orc
+    for variant, C, endpoint in (("object", 0, False), ("ssr", 7, True)):
+        pc, _ = orc.seeded_nets(variant, C)
+        g = torch.Generator().manual_seed(0)
+        pts = torch.rand(64, 3, generator=g, dtype=torch.float64) * 4 - 2
+        vd = torch.nn.functional.normalize(torch.randn(64, 3, generator=g, dtype=torch.float64), dim=-1)
+        emb = torch.cat([orc.posenc(pts, 10, 10.0 if variant == "ssr" else 1.0), orc.posenc(vd, 4)], -1)
+        p64 = {k: v.double().requires_grad_(True) for k, v in pc.items()}
+        exact = orc.mlp_forward(p64, emb, variant, C, endpoint)
+        arith, margin = orc.mlp_forward_tc_arith(p64, emb, variant, C, endpoint)
+        assert arith.shape == exact.shape and margin.shape == (64,) and bool((margin >= 0).all())
+        assert float((arith - exact).detach().abs().max()) < 2e-3
+        # masks recorded from the function's own activations reproduce it exactly
+        names = orc.OBJECT_HEADS if variant == "object" else orc.SSR_HEADS
+        with torch.no_grad():
+            rnd = lambda x: x.to(torch.float16).double()  # noqa: E731
+            masks, h = [], emb[:, :63]
+            for i, name in enumerate(orc.TRUNK):
+                z = rnd(h) @ rnd(p64[name + ".weight"]).t() + p64[name + ".bias"]
+                masks.append(z > 0)
+                h = torch.relu(z)
+                if i == 4:
+                    h = torch.cat([emb[:, :63], h], -1)
+            lin = lambda n, x: rnd(x) @ rnd(p64[n + ".weight"]).t() + p64[n + ".bias"]  # noqa: E731
+            masks += [lin(names["albedo1"], h) > 0, lin(names["shading1"], h) > 0]
+            wv, wf = p64[names["views"] + ".weight"], p64[names["feature"] + ".weight"]
+            zv = rnd(h) @ rnd(wv[:, :256] @ wf).t() + rnd(emb[:, 63:]) @ rnd(wv[:, 256:]).t() \
+                + wv[:, :256] @ p64[names["feature"] + ".bias"] + p64[names["views"] + ".bias"]
+            masks.append(zv > 0)
+            if C > 0:
+                masks.append(lin(names["sem1"], h) > 0)
+        pinned, _ = orc.mlp_forward_tc_arith(p64, emb, variant, C, endpoint, masks=masks)
+        assert float((pinned - arith).detach().abs().max()) < 1e-12
+        keep = (margin > 5e-3).double()[:, None]
+        if float(keep.sum()) >= 4:
+            w = torch.randn(exact.shape, generator=g, dtype=torch.float64) * keep
+            ga = torch.autograd.grad((arith * w).sum(), p64["pts_linears.3.weight"], retain_graph=True)[0]
+            ge = torch.autograd.grad((exact * w).sum(), p64["pts_linears.3.weight"])[0]
+            assert float((ga - ge).abs().max()) < 2e-2 * float(ge.abs().max())
