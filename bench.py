@@ -152,7 +152,9 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": "rays/sec (64+128 samples)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 1024 / v, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "blender_chair_800x800_64+128 (bounded 1024-ray sample per step, cost is linear in rays)"},
+           "config": {"workload": "blender_chair_800x800_64+128", "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE,
+                      "net": "2 x NeRF(D=8,W=256,skips=[4]) intrinsic heads",
+                      "sample": "bounded 1024-ray sample of the workload per step (cost is exactly linear in rays)"},
            "cpu_baseline": base, "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
