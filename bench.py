@@ -160,6 +160,107 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def run_room0(args, rank, local, world, dev, dist):
+    """Secondary line (not the headline): the SSR fork's renderer on Replica-shaped input.  One step = 8 frames of
+    320x240 (614 400 rays) through SSRRenderer-equivalent calls; `value` device-resident via inrf_render_fwd,
+    `e2e` through SSRRenderer.render_rays with host rays and D2H of rgb / depth / semantic logits."""
+    import intrinsicnerf_b200 as inrf
+    from intrinsicnerf_b200 import ops, ssr
+    C, Hh, Ww, frames = 28, 240, 320, 8
+    flop_per_ray = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * 2 * (692224 + 128 * C)          # SURVEY 8d, SSR network
+    torch.manual_seed(20220414)
+    mk = lambda: inrf.Semantic_NeRF(True, C, D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27,  # noqa: E731
+                                    use_viewdirs=True).to(dev)
+    coarse, fine = mk(), mk()
+    poses = torch.eye(4).repeat(frames, 1, 1)
+    for i in range(frames):
+        a = math.radians(45.0 * i + 5.0 * rank)
+        poses[i, 0, 0], poses[i, 0, 2], poses[i, 2, 0], poses[i, 2, 2] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
+    rays_dev = ssr.create_rays(frames, poses, Hh, Ww, Ww / 2, Ww / 2, (Ww - 1) / 2, (Hh - 1) / 2, 0.1, 10.0).reshape(-1, 11).contiguous()
+    n_rays = rays_dev.shape[0]
+    rays_host = rays_dev.cpu().pin_memory()
+    pc, pf = coarse.packed(), fine.packed()
+
+    class T(ssr.SSRRenderer):
+        pass
+    t = T()
+    t.N_samples, t.N_importance, t.perturb, t.raw_noise_std, t.training = N_SAMPLES, N_IMPORTANCE, 0.0, 0.0, False
+    t.white_bkgd, t.enable_semantic, t.num_valid_semantic_class, t.endpoint_feat = False, True, C, False
+    t.netchunk = t.chunk = 76800
+    t.ssr_net_coarse, t.ssr_net_fine = coarse, fine
+    t.embed_fn, _ = ssr.get_embedder(10, 0, scalar_factor=10)
+    t.embeddirs_fn, _ = ssr.get_embedder(4, 0, scalar_factor=1)
+    chunks = [(i, min(i + 76800, n_rays)) for i in range(0, n_rays, 76800)]
+
+    def step_device():
+        for a_, b_ in chunks:
+            ops.render_chunk(rays_dev[a_:b_], pc, pf, variant=1, n_classes=C, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE,
+                             white_bkgd=False, pe_scalar_factor=10.0)
+
+    out_host = [torch.empty(n_rays, c, pin_memory=True) for c in (3, 1, C)]
+
+    def step_e2e():
+        r = rays_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            d = t.render_rays(r)
+        for dst, k in zip(out_host, ("rgb_fine", "depth_fine", "sem_logits_fine")):
+            dst.copy_(d[k].reshape(n_rays, -1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s_, e_ in ev:
+            s_.record()
+            fn()
+            e_.record()
+        barrier()
+        tt = torch.tensor([sum(s_.elapsed_time(e_) for s_, e_ in ev)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    with torch.no_grad():
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms_dev = timed(step_device, args.steps, max(3, args.warmup))
+        clocks = sampler.stop() if rank == 0 else None
+        e2e_steps = max(2, args.steps // 2)
+        ms_e2e = timed(step_e2e, e2e_steps, 1)
+    if rank == 0:
+        pk = peaks()
+        value = n_rays * world * args.steps / (ms_dev * 1e-3)
+        out = {"metric": "rays/sec (64+128 samples)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f16 operands (RN) x f32 accumulate on tcgen05; everything else f32",
+               "data": "synthetic (random-init weights, reference seed 20220414; Replica-shaped cameras)",
+               "config": {"workload": "replica_room0_320x240_64+128_C28", "frames_per_step_per_gpu": frames, "rays_per_step_per_gpu": n_rays,
+                          "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "net": "2 x Semantic_NeRF(D=8,W=256,skips=[4], C=28)",
+                          "parallelism": f"rays sharded by image, dp{world}, no data-path collective",
+                          "l2": "no explicit flush: per-step working set >> 126 MB L2"},
+               "e2e": {"value": n_rays * world * e2e_steps / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(n_rays * 44),
+                       "d2h_bytes_per_step": int(n_rays * (4 + C) * 4),
+                       "api": "SSRRenderer.render_rays(host rays) + D2H of rgb_fine, depth_fine, sem_logits_fine (raw_* materialised as the API requires)"},
+               "gpu_launches": 8 * len(chunks) * args.steps,
+               "roofline": {"bound": "tensor", "kernel": "k_mlp_tc (whole step)", "achieved": value / world * flop_per_ray / 1e12,
+                            "peak": pk["bf16_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": value / world * flop_per_ray / 1e12 / (pk["bf16_sustained"] or pk["bf16_tflops"]), "traffic": None,
+                            "peak_source": pk["source"] + ", sustained bf16 (whole step)"},
+               "clocks": clocks, "cpu_baseline": None}
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,6 +270,9 @@ def main():
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--chunk", type=int, default=160000, help="rays per inrf_render_fwd call (bounds the raw scratch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="chair", choices=["chair", "room0"],
+                    help="chair: the BASELINE headline config (default). room0: BASELINE config 3 - Replica room_0 shape "
+                         "(320x240 frames, Semantic_NeRF with 28 classes, near 0.1 / far 10, PE scale 10), 8 frames per step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -190,6 +294,8 @@ def main():
     from intrinsicnerf_b200 import object_level as ol, ops
     ops.set_default_precision(args.precision)
 
+    if args.workload == "room0":
+        return run_room0(args, rank, local, world, dev, dist)
     # random-init weights of the reference architecture, reference seed (run_nerf.py:1130)
     torch.manual_seed(20220414)
     mk = lambda: inrf.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(dev)  # noqa: E731
