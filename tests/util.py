@@ -97,3 +97,13 @@ def stash_activations(stash, M, n_classes):
     if n_classes > 0:
         out["s1"] = rows(40, 2)
     return out
+
+
+def encode_images(x):
+    """Inverse of decode_images: [n_tiles, slots, 128, 64] values -> flat uint8 buffer of fp16 operand images."""
+    n_tiles, slots = x.shape[:2]
+    v = x.to(torch.float16).reshape(n_tiles, slots, 16, 8, 8, 8)
+    r = torch.arange(8, device=x.device).view(8, 1)
+    u = torch.arange(8, device=x.device).view(1, 8)
+    idx = (u ^ r).view(1, 1, 1, 8, 8, 1).expand(n_tiles, slots, 16, 8, 8, 8)
+    return torch.gather(v, 4, idx).contiguous().view(torch.uint8).reshape(-1)    # XOR is an involution: same gather
