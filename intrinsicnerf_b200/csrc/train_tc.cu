@@ -9,8 +9,9 @@
 //                 B = transposed weight tiles (packed per call), epilogue masks with the stashed activation
 //                 image and writes the next gradient image; 10 launches walk heads -> trunk layer 7 -> ... -> 0
 //   k_gemm_dw     dW = dZ^T X for every layer in ONE launch: both operands are read MN-major from the same
-//                 images (rows of the tile are the K dimension), split-K over tiles, fp32 atomics into the
-//                 flat gradient; an all-ones operand tile adds the bias gradient as 16 extra accumulator columns
+//                 images (rows of the tile are the K dimension), split-K over tiles into partial tiles that
+//                 k_dw_reduce adds in a fixed order (bit-reproducible gradients); an all-ones operand tile adds the
+//                 bias gradient as 16 extra accumulator columns
 //   k_unfold_comp views' = views_linears.0[:, :256] o feature_linear was composed at pack time (pack.cu); its
 //                 gradient is unfolded onto the two original matrices.
 //
@@ -313,11 +314,13 @@ __global__ void __launch_bounds__(DX_THREADS, 1) k_gemm_dx(const __grid_constant
 struct DwRect { int row0, nrows, col0, ncols, ld, pad; float* dst; float* bias; };
 struct DwItem { ImgRef a, x; int x_bytes, N, n_rect, pad; DwRect r[4]; };
 constexpr int DW_MAX_ITEMS = 40, DW_STAGE = 6 * IMG_BYTES, DW_THREADS = 192;
+constexpr int DW_MAX_SPLITS = 16, DW_PART_LD = 288;          // partial tile of one (item, split): 128 rows x (256 + 32) fp32
 constexpr int DW_ONES = 2 * DW_STAGE, DW_BAR = DW_ONES + 1024, DW_SMEM = DW_BAR + 128;
 struct DwParams {
   int n_items, n_tiles, n_splits, pad;
   const unsigned int* amax_bits;
   int* dbg;
+  float* part;                   // [n_items][n_splits][128][DW_PART_LD] split-K partial accumulators
   DwItem item[DW_MAX_ITEMS];
 };
 enum { DWB_FULL = 0, DWB_EMPTY = 2, DWB_ACC = 4, DWB_COUNT = 5 };
@@ -387,40 +390,57 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_gemm_dw(const __grid_constant
     }
     if (leader && !dead) tc_commit(bar0 + 8 * DWB_ACC);
     __syncwarp();
-  } else {                                             // ---- epilogue: accumulator -> fp32 atomics
+  } else {                                             // ---- epilogue: accumulator -> this split's partial tile
+    // (no atomics: k_dw_reduce adds the splits in a fixed order, so the weight gradients are bit-reproducible)
     TTC_WAIT(bar0 + 8 * DWB_ACC, 0u, 13);
     tc_fence_after();
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    const float inv = 1.f / grad_scale(P.amax_bits);
+    float* part = P.part + (((int64_t)blockIdx.x * P.n_splits + blockIdx.y) * 128 + row) * DW_PART_LD;
     uint32_t v[32];
-    for (int ri = 0; ri < I.n_rect; ++ri) {
-      const DwRect R = I.r[ri];
-      const bool mine = row >= R.row0 && row < R.row0 + R.nrows && !dead;
-      if (R.ncols > 0) {
-        for (int g = R.col0 >> 5; g <= (R.col0 + R.ncols - 1) >> 5; ++g) {
-          tmem_ld32(lane_addr + g * 32, v);
-          tmem_ld_wait();
-          if (mine) {
-            float* d = R.dst + (int64_t)(row - R.row0) * R.ld - R.col0;
+    const int n_groups = (I.N + 31) >> 5;
+    for (int g = 0; g <= n_groups; ++g) {                // the last round reads the bias columns [256, 272)
+      const int col = g < n_groups ? g * 32 : 256;
+      tmem_ld32(lane_addr + col, v);
+      tmem_ld_wait();
+      float4* d = reinterpret_cast<float4*>(part + col);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = g * 32 + i;
-              if (col >= R.col0 && col < R.col0 + R.ncols) atomicAdd(d + col, __uint_as_float(v[i]) * inv);
-            }
-          }
-        }
-      }
-      if (R.bias != nullptr) {
-        tmem_ld32(lane_addr + 256, v);
-        tmem_ld_wait();
-        if (mine) atomicAdd(R.bias + (row - R.row0), __uint_as_float(v[0]) * inv);
-      }
+      for (int i = 0; i < 8; ++i)
+        d[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc512(tmem);
+}
+
+// split-K reduction of the dW partial tiles: every gradient element has exactly one (item, rectangle) that owns it, its
+// splits are added in index order, the gradient scale is removed in fp32 and the result accumulated into the caller's
+// buffer - deterministic, unlike fp32 atomics
+__global__ void __launch_bounds__(256) k_dw_reduce(const __grid_constant__ DwParams P) {
+  const DwItem& I = P.item[blockIdx.x];
+  const float inv = 1.f / grad_scale(P.amax_bits);
+  const float* part = P.part + (int64_t)blockIdx.x * P.n_splits * 128 * DW_PART_LD;
+  const int64_t sstride = (int64_t)128 * DW_PART_LD;
+  for (int ri = 0; ri < I.n_rect; ++ri) {
+    const DwRect R = I.r[ri];
+    const int total = R.nrows * R.ncols;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int r = e / R.ncols, c = e - r * R.ncols;
+      const float* p = part + (int64_t)(R.row0 + r) * DW_PART_LD + R.col0 + c;
+      float acc = 0.f;
+      for (int sp = 0; sp < P.n_splits; ++sp) acc += p[sp * sstride];
+      R.dst[(int64_t)r * R.ld + c] += acc * inv;
+    }
+    if (R.bias != nullptr) {
+      for (int r = threadIdx.x; r < R.nrows; r += blockDim.x) {
+        const float* p = part + (int64_t)(R.row0 + r) * DW_PART_LD + 256;
+        float acc = 0.f;
+        for (int sp = 0; sp < P.n_splits; ++sp) acc += p[sp * sstride];
+        R.bias[r] += acc * inv;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -479,10 +499,11 @@ static inline int64_t up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 constexpr int64_t WS_HEAD = 4096;                                     // amax word + padding
 constexpr int64_t WS_COMP = (128 * W_HID + 128) * 4;                 // gradient of the composed views' matrix + bias
 constexpr int64_t WS_BLOB = ttc::BW_MAX_TILES * 32768;               // transposed weight tiles
+constexpr int64_t WS_PART = (int64_t)ttc::DW_MAX_ITEMS * ttc::DW_MAX_SPLITS * 128 * ttc::DW_PART_LD * 4;   // dW split-K partials
 
 int64_t tc_bwd_workspace_bytes(int variant, int n_classes, int64_t M) {
   (void)variant; (void)n_classes;
-  return up(WS_HEAD + WS_COMP, 1024) + WS_BLOB + n_tiles_of(M) * IMG_BWD_SLOTS * (int64_t)IMG_BYTES;
+  return up(WS_HEAD + WS_COMP, 1024) + WS_BLOB + WS_PART + n_tiles_of(M) * IMG_BWD_SLOTS * (int64_t)IMG_BYTES;
 }
 
 int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
@@ -499,7 +520,8 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   unsigned int* amax = reinterpret_cast<unsigned int*>(ws);
   float* dcomp = reinterpret_cast<float*>(ws + WS_HEAD);
   unsigned char* blob = ws + up(WS_HEAD + WS_COMP, 1024);
-  unsigned char* img = blob + WS_BLOB;
+  float* part = reinterpret_cast<float*>(blob + WS_BLOB);
+  unsigned char* img = blob + WS_BLOB + WS_PART;
   int* dbg = nullptr;
   INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, ttc::g_dbg));
   INRF_CUDA(cudaMemsetAsync(ws, 0, WS_HEAD + WS_COMP, st));
@@ -571,7 +593,7 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   // ---- dW: one launch, one item per (GEMM, 128 output rows) --------------------------------------------
   DwParams D;                              // 9 KB launch table, rebuilt per call (pointers depend on the caller's buffers)
   memset(&D, 0, sizeof(D));
-  D.n_tiles = (int)T; D.amax_bits = amax; D.dbg = dbg;
+  D.n_tiles = (int)T; D.amax_bits = amax; D.dbg = dbg; D.part = part;
   float* gf = a.grad_flat;
   auto item = [&](ImgRef az, ImgRef x, int n_x, int N) -> DwItem& {
     DwItem& it = D.item[D.n_items++];
@@ -608,11 +630,14 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   if (sem) rect(item(W(IB_G), F(IS_S1), 2, 128), 8, C, 0, 128, gf + L.flat_w[L_SEM2], 128, gf + L.flat_b[L_SEM2]);
   if (D.n_items > DW_MAX_ITEMS) { set_error("internal: too many dW items"); return INRF_EINVAL; }
   int splits = (2 * sms + D.n_items - 1) / D.n_items;
-  if (splits > T) splits = (int)T;
+  if (splits > DW_MAX_SPLITS) splits = DW_MAX_SPLITS;
+  if (splits > T) splits = (int)T;              // every split owns at least one tile, so every partial tile is written
   if (splits < 1) splits = 1;
   D.n_splits = splits;
   INRF_CUDA(cudaFuncSetAttribute(k_gemm_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
   k_gemm_dw<<<dim3(D.n_items, splits), DW_THREADS, DW_SMEM, st>>>(D);
+  INRF_LAUNCH_CHECK();
+  k_dw_reduce<<<D.n_items, 256, 0, st>>>(D);
   INRF_LAUNCH_CHECK();
   k_unfold_comp<<<16 + 256, 256, 0, st>>>(a.flat, L, dcomp, gf);
   INRF_LAUNCH_CHECK();

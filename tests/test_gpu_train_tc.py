@@ -117,3 +117,16 @@ def test_rays_mode_and_embedded_mode_agree():
         grads.append(torch.cat([p.grad.reshape(-1) for p in fine.parameters()]).clone())
     assert float((grads[0] - grads[1]).abs().max()) < 2e-3 * float(grads[1].abs().max())
     assert ops.default_precision() == ops.PREC_TC
+
+
+def test_tc_training_gradients_are_bit_reproducible():
+    """No atomics anywhere in the tensor-core backward (split-K partial tiles are added in a fixed order): two runs on the
+    same inputs give identical parameter gradients, bit for bit."""
+    fine, pf, pts, vd, scale, g_raw, emb = _inputs("ssr", 28, False, 3000, 9, 1.0)
+    runs = []
+    for _ in range(2):
+        fine.zero_grad()
+        out = fine.evaluate("pts", pts.to(DEV), vd.to(DEV), False, scale)
+        (out * g_raw.to(DEV)).sum().backward()
+        runs.append(torch.cat([p.grad.reshape(-1) for p in fine.parameters()]).clone())
+    assert torch.equal(runs[0], runs[1])
