@@ -9,7 +9,6 @@ nearest-centre labelling, voxel anchor selection, nearest-anchor lookup) are CUD
 (csrc/cluster.cu) and only the few-hundred-element control logic (seed binning, duplicate
 removal) is host code, restating sklearn/cluster/_mean_shift.py.
 """
-import ctypes as C
 import json
 import os
 
