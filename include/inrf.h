@@ -34,6 +34,9 @@ extern "C" {
 #define INRF_EUNSUPPORTED -2   /* configuration outside what the kernels implement */
 #define INRF_ECUDA        -3   /* CUDA runtime error (message carries cudaGetErrorString) */
 #define INRF_EWORKSPACE   -4   /* workspace too small */
+#define INRF_ERANGE       -5   /* a value left the fp16 range of the tensor-core path (weights at pack time,
+                                  hidden activations or gradients at run time): results of that launch are
+                                  saturated, not inf/NaN; rerun with INRF_PREC_FP32 */
 
 /* Network variants.  Both are the 8x256 trunk with skip at layer 4, PE L=10 / L=4. */
 #define INRF_NET_OBJECT 0      /* NeRF           object_level/run_nerf_helpers.py:247-325 */
@@ -57,6 +60,15 @@ extern "C" {
 
 const char* inrf_last_error_string(void);
 int inrf_version(void);
+
+/* Deferred device status.  No entry point synchronises the device, so a condition that only a running
+ * kernel can detect - a tensor-core kernel whose barrier watchdog tripped (INRF_ECUDA), a weight /
+ * activation / gradient outside the fp16 range of INRF_PREC_TC (INRF_ERANGE) - is recorded by the kernel in
+ * a 64-byte pinned host buffer (the only allocation the library makes, one per device, on first use) and
+ * reported by the NEXT inrf_pack_weights / inrf_mlp_* / inrf_render_fwd call on that device, which returns
+ * the code without launching anything.  inrf_poll_status() checks explicitly (after the caller has
+ * synchronised its stream, it reports everything enqueued so far); it clears the record.              */
+int inrf_poll_status(void);
 
 /* ---------------------------------------------------------------------------------
  * Weights

@@ -35,6 +35,7 @@ class FramePlanes(C.Structure):
 _SIGS = {
     "inrf_last_error_string": (C.c_char_p, []),
     "inrf_version": (i32, []),
+    "inrf_poll_status": (i32, []),
     "inrf_flat_param_count": (i64, [i32, i32]),
     "inrf_packed_bytes": (i64, [i32, i32]),
     "inrf_pack_weights": (i32, [p, i32, i32, p, i64, p]),
@@ -98,7 +99,15 @@ class InrfError(RuntimeError):
     pass
 
 
+class InrfRangeError(InrfError):
+    """INRF_ERANGE: a weight, activation or gradient left the fp16 range of the tensor-core path."""
+
+
+E_RANGE = -5
+
+
 def check(rc):
     if rc < 0:
-        raise InrfError(f"libinrf error {rc}: {lib().inrf_last_error_string().decode()}")
+        cls = InrfRangeError if rc == E_RANGE else InrfError
+        raise cls(f"libinrf error {rc}: {lib().inrf_last_error_string().decode()}")
     return rc

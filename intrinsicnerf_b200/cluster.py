@@ -256,8 +256,8 @@ class Cluster_Manager:
             cl.update_center(cls_pixels, quantile=quantile, n_samples=n_samples, band_factor=band_factor)
             self.clusters.append(cl)
 
-    def _per_class(self, rgb, label, result, fn):
-        if self.ssr_semantics and self.class_num == 1 and self.clusters[0] is not None:
+    def _per_class(self, rgb, label, result, fn, ignore_labels=False):
+        if ignore_labels and self.clusters[0] is not None:
             return fn(self.clusters[0], rgb)
         for i in range(self.class_num):
             if self.clusters[i] is None:
@@ -269,7 +269,10 @@ class Cluster_Manager:
         return result
 
     def dest_color(self, rgb, label):
-        return self._per_class(rgb, label, rgb.clone(), lambda c, x: c.dest_color(x))
+        # the SSR fork ignores the labels when there is a single class - in dest_color only
+        # (SSR/training/cluster.py:75-77); its dest_class still masks by label == i (:85-97)
+        return self._per_class(rgb, label, rgb.clone(), lambda c, x: c.dest_color(x),
+                               ignore_labels=self.ssr_semantics and self.class_num == 1)
 
     def dest_class(self, rgb, label):
         res = torch.zeros([rgb.shape[0], 1], dtype=torch.long, device=rgb.device)

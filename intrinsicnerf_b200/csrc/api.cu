@@ -68,7 +68,9 @@ using namespace inrf;
 extern "C" {
 
 const char* inrf_last_error_string(void) { return last_error(); }
-int inrf_version(void) { return 100; }
+int inrf_version(void) { return 200; }
+int inrf_poll_status(void) { return status_poll(); }
+#define INRF_POLL() do { int rc__ = status_poll(); if (rc__) return rc__; } while (0)
 
 int64_t inrf_flat_param_count(int variant, int n_classes) {
   NetLayout L;
@@ -83,6 +85,7 @@ int64_t inrf_packed_bytes(int variant, int n_classes) {
 }
 
 int inrf_pack_weights(const float* flat_params, int variant, int n_classes, void* packed, int64_t packed_bytes, void* stream) {
+  INRF_POLL();
   INRF_CHECK_ARG(flat_params && packed, "null pointer");
   return pack_weights(flat_params, variant, n_classes, packed, packed_bytes, (cudaStream_t)stream);
 }
@@ -96,6 +99,7 @@ int inrf_embed(const float* x, int64_t M, int n_freqs, float scalar_factor, floa
 
 int inrf_mlp_fwd(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
                  const float* pts, const float* viewdirs, int64_t M, float* raw, int precision, void* stream) {
+  INRF_POLL();
   INRF_CHECK_ARG(M >= 0 && packed && (M == 0 || (pts && viewdirs && raw)), "null pointer / negative size");
   INRF_CHECK_ARG(pe_scalar_factor > 0.f, "pe_scalar_factor must be positive");
   INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
@@ -107,6 +111,7 @@ int inrf_mlp_fwd(const void* packed, int variant, int n_classes, int endpoint_fe
 
 int inrf_mlp_fwd_embedded(const void* packed, int variant, int n_classes, int endpoint_feat, const float* emb,
                           int64_t M, float* raw, int precision, void* stream) {
+  INRF_POLL();
   INRF_CHECK_ARG(M >= 0 && packed && (M == 0 || (emb && raw)), "null pointer / negative size");
   INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
   MlpArgs a{};
@@ -164,6 +169,7 @@ int64_t inrf_mlp_bwd_tc_workspace_bytes(int variant, int n_classes, int64_t M) {
 int inrf_mlp_fwd_train_tc(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
                           const float* pts, const float* viewdirs, const float* rays, const float* z, int S, const float* emb,
                           int64_t M, float* raw, void* stash_img, void* stream) {
+  INRF_POLL();
   INRF_CHECK_ARG(M >= 0 && packed && (M == 0 || (raw && stash_img)), "null pointer / negative size");
   INRF_CHECK_ARG(pe_scalar_factor > 0.f, "pe_scalar_factor must be positive");
   INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
@@ -179,6 +185,7 @@ int inrf_mlp_fwd_train_tc(const void* packed, int variant, int n_classes, int en
 int inrf_mlp_bwd_tc(const void* packed, const float* flat_params, int variant, int n_classes, int endpoint_feat, int64_t M,
                     const float* raw, const void* stash_img, const float* grad_raw, void* workspace, int64_t workspace_bytes,
                     float* grad_flat, void* stream) {
+  INRF_POLL();
   INRF_CHECK_ARG(M >= 0 && packed && flat_params && grad_flat && (M == 0 || (raw && stash_img && grad_raw && workspace)),
                  "null pointer / negative size");
   INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
@@ -195,6 +202,7 @@ int inrf_mlp_bwd_tc(const void* packed, const float* flat_params, int variant, i
 
 int inrf_mlp_fwd_rays(const void* packed, int variant, int n_classes, int endpoint_feat, float pe_scalar_factor,
                       const float* rays, const float* z, int64_t N, int S, float* raw, int precision, void* stream) {
+  INRF_POLL();
   INRF_CHECK_ARG(N >= 0 && S > 0 && packed && (N == 0 || (rays && z && raw)), "null pointer / bad size");
   INRF_CHECK_ARG(pe_scalar_factor > 0.f, "pe_scalar_factor must be positive");
   INRF_CHECK_ARG(!(variant == INRF_NET_OBJECT && endpoint_feat), "object network has no endpoint feature");
@@ -279,6 +287,7 @@ int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, con
                     const float* u, const float* noise_coarse, const float* noise_fine, float* rec_coarse,
                     float* rec_fine, float* z_std, float* raw_coarse, float* raw_fine, float* z_fine,
                     float* weights_fine, void* workspace, int64_t workspace_bytes, void* stream) {
+  INRF_POLL();
   int rc = check_cfg(cfg);
   if (rc) return rc;
   const InrfRenderCfg& c = *cfg;

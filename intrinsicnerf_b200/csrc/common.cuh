@@ -31,6 +31,35 @@ int cuda_fail(cudaError_t e, const char* what);
 #define INRF_LAUNCH_CHECK() INRF_CUDA(cudaGetLastError())
 
 // ---------------------------------------------------------------------------------
+// Deferred device status (status.cu).  Kernels cannot return codes, and no hot entry point may
+// synchronise, so a kernel that trips its barrier watchdog or leaves the fp16 range writes a small
+// record into a pinned, device-mapped host buffer (one per device, 64 bytes, allocated on first use);
+// the host reads it - a plain memory load - at the entry of the next inrf_* call (status_poll) and
+// turns it into an error code + message.  Records: [0] code, [1..6] details.
+// ---------------------------------------------------------------------------------
+enum DevStatusCode {
+  DST_NONE = 0,
+  DST_WATCHDOG = 1,      // a role of a tensor-core kernel waited > watchdog cycles on an mbarrier
+  DST_SMEM_ALIGN = 2,    // dynamic shared memory base not 1024-byte aligned
+  DST_F16_ACT = 3,       // a hidden activation reached the fp16 limit (saturated at 65504)
+  DST_F16_WEIGHT = 4,    // a weight / bias does not fit fp16 (saturated at pack time)
+  DST_F16_GRAD = 5,      // non-finite value in the tensor-core backward (fp16 gradient range)
+};
+int* status_flag_dev();                 // device-visible pointer of the current device's record (nullptr: error set)
+int status_poll();                      // INRF_OK, or INRF_ECUDA / INRF_ERANGE with the message set; clears the record
+#ifdef __CUDACC__
+// one writer per launch is elected by the caller (a device-side atomicCAS on its own claim word)
+__device__ __forceinline__ void status_raise(int* flag, int code, int a = 0, int b = 0, int c = 0, int d = 0, int e = 0) {
+  if (flag == nullptr) return;
+  volatile int* f = flag;
+  f[1] = a; f[2] = b; f[3] = c; f[4] = d; f[5] = e;
+  __threadfence_system();
+  f[0] = code;
+  __threadfence_system();
+}
+#endif
+
+// ---------------------------------------------------------------------------------
 // Network description (fixed architecture: D=8, W=256, skips=[4], PE L=10 / L=4)
 // ---------------------------------------------------------------------------------
 constexpr int W_HID = 256;

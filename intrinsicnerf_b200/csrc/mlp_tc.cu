@@ -83,7 +83,10 @@ struct Params {
   int out_ch, C, sem_rows;
   int bias_mma;                   // 1: accumulators are initialised with the bias by an MMA (default)
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
-  int* dbg;                       // [16] watchdog record (device)
+  int* dbg;                       // [16] per-launch abort / claim words (device, cleared before every launch)
+  int* status;                    // pinned host record the next API call reads (common.cuh: status_raise)
+  long long watchdog;             // cycles a blocking barrier wait may take before the launch is abandoned
+  int fault;                      // test hook (INRF_TC_FAULT=n, first n launches): the weight producer stops after three fills
   long long* prof;                // optional wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
 };
@@ -175,17 +178,19 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
 // flag and lets every role run to the end (garbage out, but no hung GPU and no lost context)
 // ------------------------------------------------------------------------------------------
 // out-of-line spin with watchdog; returns true when the wait was abandoned (dead)
-__device__ __noinline__ bool slow_wait_impl(uint32_t bar_addr, uint32_t parity, int id, int tile, int* dbg, long long* prof) {
+__device__ __noinline__ bool slow_wait_impl(uint32_t bar_addr, uint32_t parity, int id, int tile, int* dbg, long long* prof,
+                                            int* status, long long watchdog) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   bool dead = false;
   while (!mbar_try(bar_addr, parity)) {
     if ((++spins & 0x3ff) == 0) {
       if (*(volatile int*)dbg != 0) { dead = true; break; }
-      if (clock64() - t0 > 3000000000LL) {
-        if (atomicCAS(dbg, 0, 1) == 0) {
+      if (clock64() - t0 > watchdog) {
+        if (atomicCAS(dbg, 0, 1) == 0) {        // first to give up: tell the host (next API call) and every other role
           dbg[1] = id; dbg[2] = threadIdx.x >> 5; dbg[3] = tile; dbg[4] = blockIdx.x; dbg[5] = (int)parity;
           __threadfence();
+          status_raise(status, DST_WATCHDOG, id, threadIdx.x >> 5, tile, blockIdx.x, 1);
         }
         dead = true;
         break;
@@ -207,6 +212,8 @@ struct Sync {             // lives in registers (never escapes by address)
   uint32_t bar0;          // smem address of barrier 0
   uint64_t phase;         // one parity bit per barrier id
   int* dbg;
+  int* status;
+  long long watchdog;
   long long* prof;        // wait-cycle counters of this role (CTA 0, one thread per role) or nullptr
   bool dead;
   int tile;
@@ -217,7 +224,7 @@ struct Sync {             // lives in registers (never escapes by address)
     return parity;
   }
   __device__ __forceinline__ void slow(int id, uint32_t parity) {
-    if (!dead) dead = slow_wait_impl(addr(id), parity, id, tile, dbg, prof);
+    if (!dead) dead = slow_wait_impl(addr(id), parity, id, tile, dbg, prof, status, watchdog);
   }
   __device__ __forceinline__ void wait(int id) {
     const uint32_t parity = take_parity(id);
@@ -279,10 +286,16 @@ __device__ __forceinline__ void pe_coord(float x, int n_freqs, float* s, float* 
   }
 }
 
-__device__ __forceinline__ uint32_t relu_h2(uint32_t h2) {
-  __half2 v = *reinterpret_cast<__half2*>(&h2);
-  v = __hmax2(v, __float2half2_rn(0.f));
-  return *reinterpret_cast<uint32_t*>(&v);
+// relu + round-to-nearest fp16 pair, saturating at +-65504 instead of producing inf (one F2FP instruction)
+__device__ __forceinline__ uint32_t pack_relu_sat_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  __half2 x = *reinterpret_cast<__half2*>(&a), y = *reinterpret_cast<__half2*>(&b);
+  x = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&x);
 }
 
 // swizzled byte offsets of the 8 16-byte units of this thread's row inside a chunk
@@ -391,6 +404,7 @@ __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t sme
   for (int it = 0; it < P.n_iter; ++it) {
     sy.tile = it;
     for (int b = 0; b < P.n_fills; ++b) {
+      if (P.fault && it == 0 && b == 3) return;      // test hook: starve the ring -> the issuer's wait must trip the watchdog
       sy.wait(B_WEMPTY + slot);           // every CTA of the cluster has consumed this slot
       if (leader && !sy.dead) {
         const uint32_t bytes = (uint32_t)P.fill_bytes[b];
@@ -594,7 +608,7 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
 template <bool ADD_BIAS, bool SIGMA, bool GOUT>
 __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __restrict__ bias, uint32_t dst_chunk,
                                             const RowAddr& ra, int unit0, const float* alpha_w_smem, float* sigma_acc,
-                                            float* gout, unsigned char* gimg) {
+                                            float* gout, unsigned char* gimg, uint32_t& amax) {
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -625,7 +639,10 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
   for (int u = 0; u < 4; ++u) {
     uint32_t pk[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pk[i] = relu_h2(pack_h2(f[8 * u + 2 * i], f[8 * u + 2 * i + 1]));
+    for (int i = 0; i < 4; ++i) {
+      pk[i] = pack_relu_sat_h2(f[8 * u + 2 * i], f[8 * u + 2 * i + 1]);
+      amax = hmax2_u32(amax, pk[i]);          // running maximum of the stored halves: fp16-range check at the tile end
+    }
     st_shared_v4(dst_chunk + ra.unit[unit0 + u], pk[0], pk[1], pk[2], pk[3]);
     if (gimg != nullptr) st_global_v4(gimg + ra.unit[unit0 + u], pk[0], pk[1], pk[2], pk[3]);   // training stash image
   }
@@ -637,7 +654,8 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
 template <int MODE>
 __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst0, int n_chunks,
                                           const RowAddr& ra, int jj, int lane, Sync& sy, int free_bar0, int ready_bar0,
-                                          const float* alpha_smem, float* sigma_acc, float* gout0, unsigned char* gimg0) {
+                                          const float* alpha_smem, float* sigma_acc, float* gout0, unsigned char* gimg0,
+                                          uint32_t& amax) {
 #pragma unroll 1
   for (int cp = 0; cp < n_chunks; cp += 2) {
     uint32_t v0[32], v1[32];
@@ -653,8 +671,8 @@ __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const f
       float* g = (MODE == 2 && gout0) ? gout0 + col : nullptr;
       const float* aw = (MODE == 1) ? alpha_smem + col : nullptr;
       unsigned char* gi = gimg0 ? gimg0 + c * IMG_BYTES : nullptr;
-      if (add_bias) epi_store32<true, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi);
-      else epi_store32<false, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi);
+      if (add_bias) epi_store32<true, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi, amax);
+      else epi_store32<false, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi, amax);
       fence_async_smem();
       tc_fence_before();
       if (ready_bar0 >= 0) warp_arrive(sy.addr(ready_bar0 + c), lane);
@@ -688,11 +706,12 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 #define SLOT(s) (simg ? simg + (s) * IMG_BYTES : nullptr)
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
     float sig = 0.f;
+    uint32_t amax = 0u;                                  // running max of every fp16 activation this thread stored
     for (int l = 0; l < 8; ++l) {
       sy.wait(B_ACC_FULL + (l & 1));
       tc_fence_after();
-      if (l == 7) epi_layer<1>(add_bias, lane_addr + 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28));
-      else epi_layer<0>(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l));
+      if (l == 7) epi_layer<1>(add_bias, lane_addr + 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28), amax);
+      else epi_layer<0>(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l), amax);
     }
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
@@ -701,17 +720,17 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
       tc_fence_after();
     if (P.a.endpoint)
       epi_layer<2>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
-                   valid ? grow + INRF_RAW_BASE + P.C : nullptr, SLOT(IS_V));
+                   valid ? grow + INRF_RAW_BASE + P.C : nullptr, SLOT(IS_V), amax);
     else
-      epi_layer<0>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V));
+      epi_layer<0>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V), amax);
     warp_arrive(sy.addr(B_V_READY), lane);
     // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ---------------------------------
     sy.wait(B_ACC_FULL + 1);
       tc_fence_after();
-    epi_layer<0>(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS));
+    epi_layer<0>(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS), amax);
     // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
     if (sem)
-      epi_layer<0>(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1));
+      epi_layer<0>(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1), amax);
 #undef SLOT
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
@@ -752,6 +771,11 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
         }
       }
     }
+    // fp16 range: a stored activation at the saturation value 65504 (0x7bff) means the tile left the range the
+    // tensor-core path can represent; report it (next API call returns INRF_ERANGE) instead of passing inf on
+    if (valid && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {
+      if (atomicCAS(P.dbg + 8, 0, 1) == 0) status_raise(P.status, DST_F16_ACT, 0, (int)tile, blockIdx.x);
+    }
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");     // s_sig may be rewritten by the next tile
     warp_arrive(sy.addr(B_TAIL_DONE), lane);
@@ -772,12 +796,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   Sync sy;
   sy.bar0 = smem_base + SM_BAR;
   sy.dbg = P.dbg;
+  sy.status = P.status;
+  sy.watchdog = P.watchdog;
   sy.prof = nullptr;
   sy.dead = false;
   sy.tile = -1;
   sy.phase = 0;
   if ((smem_base & 1023u) != 0) {                    // SWIZZLE_128B atoms need 1024 B alignment
-    if (threadIdx.x == 0 && atomicCAS(P.dbg, 0, 2) == 0) P.dbg[1] = (int)smem_base;
+    if (threadIdx.x == 0 && atomicCAS(P.dbg, 0, 2) == 0) status_raise(P.status, DST_SMEM_ALIGN, (int)smem_base);
     return;                                            // same for every CTA of the launch
   }
   if (threadIdx.x == 0) {
@@ -882,8 +908,16 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   int* dbg = nullptr;
   INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, tc::g_dbg));
   P.dbg = dbg;
+  P.status = status_flag_dev();
+  if (P.status == nullptr) return INRF_ECUDA;
+  static const long long wd_env = getenv("INRF_TC_WATCHDOG_CYCLES") ? atoll(getenv("INRF_TC_WATCHDOG_CYCLES")) : 3000000000LL;
+  static int faults_left = getenv("INRF_TC_FAULT") ? atoi(getenv("INRF_TC_FAULT")) : 0;   // test hook: fault the first n launches
+  P.watchdog = wd_env > 0 ? wd_env : 3000000000LL;
+  P.fault = faults_left > 0 ? 1 : 0;
+  if (faults_left > 0) --faults_left;
   static const bool checked = getenv("INRF_TC_CHECK") != nullptr && getenv("INRF_TC_CHECK")[0] == '1';
-  if (checked) INRF_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(int), st));
+  // the abort / claim words are per launch: a tripped watchdog must not poison later launches
+  INRF_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(int), st));
   int dev = 0, sms = 148;
   INRF_CUDA(cudaGetDevice(&dev));
   INRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -926,12 +960,9 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
       }
     }
   }
-  if (checked) {      // debug mode: synchronise and surface watchdog records as errors
-    int h[16];
+  if (checked) {      // debug mode (INRF_TC_CHECK=1): synchronise and report this launch's status record right away
     INRF_CUDA(cudaStreamSynchronize(st));
-    INRF_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h[0] == 1) { set_error("mlp_tc watchdog: barrier %d stuck (warp %d, tile %d, cta %d, parity %d)", h[1], h[2], h[3], h[4], h[5]); return INRF_ECUDA; }
-    if (h[0] == 2) { set_error("mlp_tc: dynamic shared memory base 0x%x is not 1024-byte aligned", h[1]); return INRF_ECUDA; }
+    return status_poll();
   }
   return INRF_OK;
 }

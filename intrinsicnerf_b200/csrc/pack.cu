@@ -132,7 +132,20 @@ int make_tc_program(int variant, int n_classes, TcProgram* p) {
 // ---------------------------------------------------------------------------------
 struct PackParams {
   NetLayout L;
+  int* status;     // deferred status record (common.cuh)
 };
+
+// fp32 -> fp16 (RN) for a tensor-core operand; a finite value beyond +-65504 saturates and is reported.
+// `tiny` counts non-zero values below 2^-17: there fp16 is subnormal with fewer than 8 significant bits (or zero).
+__device__ __forceinline__ __half to_operand_half(float v, bool& overflow, int* tiny = nullptr) {
+  __half h = __float2half_rn(v);
+  if (__hisinf(h) && isfinite(v)) {
+    overflow = true;
+    h = __float2half_rn(v > 0.f ? 65504.f : -65504.f);
+  }
+  if (tiny != nullptr && v != 0.f && fabsf(v) < 7.62939453125e-06f) ++*tiny;
+  return h;
+}
 
 __global__ void k_pack_f32(const float* __restrict__ flat, unsigned char* __restrict__ packed, PackParams P) {
   int l = blockIdx.y;
@@ -209,12 +222,13 @@ __global__ void k_pack_tc_blocks(const float* __restrict__ flat, unsigned char* 
   const TcBlock b = prog.blk[blockIdx.x];
   __half* dst = reinterpret_cast<__half*>(packed + P.L.tc_blocks + b.byte_off);
   const float* comp = reinterpret_cast<const float*>(packed + P.L.comp);
+  bool overflow = false;
   if (b.kind == 3) {
     // no-swizzle K-major core matrices: 8 rows x 8 halves = 128 B contiguous; K halves 128 B apart
     // (LBO), 8-row groups 256 B apart (SBO).  bias = hi + lo + lo2 in three fp16 columns.
     for (int r = threadIdx.x; r < 128; r += blockDim.x) {
       float bv = (b.layer < 0) ? comp[128 * W_HID + b.n0 + r] : flat[P.L.flat_b[b.layer] + b.n0 + r];
-      __half hi = __float2half_rn(bv);
+      __half hi = to_operand_half(bv, overflow);
       float r1 = bv - __half2float(hi);
       __half lo = __float2half_rn(r1);
       __half lo2 = __float2half_rn(r1 - __half2float(lo));
@@ -223,8 +237,10 @@ __global__ void k_pack_tc_blocks(const float* __restrict__ flat, unsigned char* 
         dst[((r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2) >> 1] = v;
       }
     }
+    if (__syncthreads_or(overflow) && threadIdx.x == 0) status_raise(P.status, DST_F16_WEIGHT, blockIdx.x);
     return;
   }
+  int tiny = 0, nonzero = 0;
   for (int e = threadIdx.x; e < b.rows * 64; e += blockDim.x) {
     int r = e >> 6, kk = e & 63;
     float v = 0.f;
@@ -242,8 +258,18 @@ __global__ void k_pack_tc_blocks(const float* __restrict__ flat, unsigned char* 
     // UMMA K-major SWIZZLE_128B: 8-row atom = 1024 B, row = 128 B, 16 B unit index ^ (row & 7)
     int unit = kk >> 3, within = kk & 7;
     int off_bytes = (r >> 3) * 1024 + (r & 7) * 128 + ((unit ^ (r & 7)) << 4) + within * 2;
-    dst[off_bytes >> 1] = __float2half_rn(v);
+    dst[off_bytes >> 1] = to_operand_half(v, overflow, &tiny);
+    nonzero += (v != 0.f);
   }
+  if (__syncthreads_or(overflow) && threadIdx.x == 0) status_raise(P.status, DST_F16_WEIGHT, blockIdx.x, 0);
+  // a block whose weights mostly sit below fp16's normal range would silently lose the layer: report it as well
+  __shared__ int s_cnt[2];
+  if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) { tiny += __shfl_xor_sync(0xffffffffu, tiny, o); nonzero += __shfl_xor_sync(0xffffffffu, nonzero, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], tiny); atomicAdd(&s_cnt[1], nonzero); }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt[0] * 4 > s_cnt[1]) status_raise(P.status, DST_F16_WEIGHT, blockIdx.x, 1);
 }
 
 int pack_weights(const float* flat, int variant, int n_classes, void* packed, int64_t packed_bytes, cudaStream_t st) {
@@ -254,6 +280,8 @@ int pack_weights(const float* flat, int variant, int n_classes, void* packed, in
   TcProgram prog;
   rc = make_tc_program(variant, n_classes, &prog);
   if (rc) return rc;
+  P.status = status_flag_dev();
+  if (P.status == nullptr) return INRF_ECUDA;
   unsigned char* out = static_cast<unsigned char*>(packed);
   k_pack_f32<<<dim3(32, P.L.n_layers), 256, 0, st>>>(flat, out, P);
   INRF_LAUNCH_CHECK();

@@ -172,12 +172,14 @@ struct DxParams {
   int64_t M;
   const unsigned int* amax_bits;
   int* dbg;
+  int* status;                   // deferred status record (common.cuh)
 };
 enum { DXB_FULL = 0, DXB_EMPTY = DX_NS, DXB_ACC_FULL = 2 * DX_NS, DXB_ACC_EMPTY = 2 * DX_NS + 2, DXB_COUNT = 2 * DX_NS + 4 };
 
 #define TTC_WAIT(addr, par, code)                                          \
   do {                                                                     \
-    if (!dead && !mbar_wait((addr), (par))) { dead = true; if (atomicCAS(P.dbg, 0, (code)) == 0) { P.dbg[1] = blockIdx.x; P.dbg[2] = threadIdx.x; } } \
+    if (!dead && !mbar_wait((addr), (par))) { dead = true; if (atomicCAS(P.dbg, 0, (code)) == 0) { P.dbg[1] = blockIdx.x; P.dbg[2] = threadIdx.x; \
+      status_raise(P.status, DST_WATCHDOG, (code), threadIdx.x >> 5, -1, blockIdx.x, 2); } } \
   } while (0)
 
 __global__ void __launch_bounds__(DX_THREADS, 1) k_gemm_dx(const __grid_constant__ DxParams P) {
@@ -320,6 +322,7 @@ struct DwParams {
   int n_items, n_tiles, n_splits, pad;
   const unsigned int* amax_bits;
   int* dbg;
+  int* status;                   // deferred status record (common.cuh)
   float* part;                   // [n_items][n_splits][128][DW_PART_LD] split-K partial accumulators
   DwItem item[DW_MAX_ITEMS];
 };
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_gemm_dw(const __grid_constant
 __global__ void __launch_bounds__(256) k_dw_reduce(const __grid_constant__ DwParams P) {
   const DwItem& I = P.item[blockIdx.x];
   const float inv = 1.f / grad_scale(P.amax_bits);
+  bool bad = false;               // a non-finite partial sum: some fp16 gradient image overflowed upstream
   const float* part = P.part + (int64_t)blockIdx.x * P.n_splits * 128 * DW_PART_LD;
   const int64_t sstride = (int64_t)128 * DW_PART_LD;
   for (int ri = 0; ri < I.n_rect; ++ri) {
@@ -430,6 +434,7 @@ __global__ void __launch_bounds__(256) k_dw_reduce(const __grid_constant__ DwPar
       const float* p = part + (int64_t)(R.row0 + r) * DW_PART_LD + R.col0 + c;
       float acc = 0.f;
       for (int sp = 0; sp < P.n_splits; ++sp) acc += p[sp * sstride];
+      if (!isfinite(acc)) bad = true;
       R.dst[(int64_t)r * R.ld + c] += acc * inv;
     }
     if (R.bias != nullptr) {
@@ -437,10 +442,12 @@ __global__ void __launch_bounds__(256) k_dw_reduce(const __grid_constant__ DwPar
         const float* p = part + (int64_t)(R.row0 + r) * DW_PART_LD + 256;
         float acc = 0.f;
         for (int sp = 0; sp < P.n_splits; ++sp) acc += p[sp * sstride];
+        if (!isfinite(acc)) bad = true;
         R.bias[r] += acc * inv;
       }
     }
   }
+  if (__syncthreads_or(bad) && threadIdx.x == 0 && atomicCAS(P.dbg + 4, 0, 1) == 0) status_raise(P.status, DST_F16_GRAD, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -526,7 +533,9 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   INRF_CUDA(cudaGetSymbolAddress((void**)&dbg, ttc::g_dbg));
   INRF_CUDA(cudaMemsetAsync(ws, 0, WS_HEAD + WS_COMP, st));
   static const bool checked = getenv("INRF_TC_CHECK") != nullptr && getenv("INRF_TC_CHECK")[0] == '1';
-  if (checked) INRF_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(int), st));
+  INRF_CUDA(cudaMemsetAsync(dbg, 0, 8 * sizeof(int), st));      // per-launch claim words
+  int* status = status_flag_dev();
+  if (status == nullptr) return INRF_ECUDA;
   int dev = 0, sms = 148;
   INRF_CUDA(cudaGetDevice(&dev));
   INRF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -546,7 +555,7 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   auto begin = [&](int N, ImgRef mask, ImgRef out) {
     DxParams& g = G[ng];
     memset(&g, 0, sizeof(g));
-    g.N = N; g.mask = mask; g.out = out; g.b = blob + prog.bytes; g.M = a.M; g.amax_bits = amax; g.dbg = dbg; g.n_tiles = (int)T;
+    g.N = N; g.mask = mask; g.out = out; g.b = blob + prog.bytes; g.M = a.M; g.amax_bits = amax; g.dbg = dbg; g.status = status; g.n_tiles = (int)T;
   };
   auto add = [&](ImgRef src, int kind, int layer, int out0, int in0) {
     DxParams& g = G[ng];
@@ -593,7 +602,7 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   // ---- dW: one launch, one item per (GEMM, 128 output rows) --------------------------------------------
   DwParams D;                              // 9 KB launch table, rebuilt per call (pointers depend on the caller's buffers)
   memset(&D, 0, sizeof(D));
-  D.n_tiles = (int)T; D.amax_bits = amax; D.dbg = dbg; D.part = part;
+  D.n_tiles = (int)T; D.amax_bits = amax; D.dbg = dbg; D.status = status; D.part = part;
   float* gf = a.grad_flat;
   auto item = [&](ImgRef az, ImgRef x, int n_x, int N) -> DwItem& {
     DwItem& it = D.item[D.n_items++];
@@ -641,11 +650,9 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   INRF_LAUNCH_CHECK();
   k_unfold_comp<<<16 + 256, 256, 0, st>>>(a.flat, L, dcomp, gf);
   INRF_LAUNCH_CHECK();
-  if (checked) {
-    int h[8];
+  if (checked) {      // debug mode (INRF_TC_CHECK=1): synchronise and report this call's status record right away
     INRF_CUDA(cudaStreamSynchronize(st));
-    INRF_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    if (h[0] != 0) { set_error("mlp_bwd_tc watchdog: wait %d stuck (cta %d, thread %d)", h[0], h[1], h[2]); return INRF_ECUDA; }
+    return status_poll();
   }
   return INRF_OK;
 }

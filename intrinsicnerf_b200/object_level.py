@@ -301,6 +301,19 @@ class _FrameWriter:
     def __init__(self, device):
         self.stream = torch.cuda.Stream(device=device)
         self.pending = None
+        self._pinned = {}          # (plane name, shape, dtype) -> two pinned host buffers used alternately
+
+    def _host_buffer(self, key, t):
+        """Pinned staging buffer for plane `key`, reused across frames.  Two per plane: one is being written to disk
+        (previous frame) while the other receives this frame's copy.  device='cpu' is explicit because the reference's
+        entry point sets a CUDA default tensor type (run_nerf.py:1129) and pinning needs a CPU tensor."""
+        k = (key, tuple(t.shape), t.dtype)
+        slot = self._pinned.setdefault(k, [None, None, 0])
+        i = slot[2]
+        if slot[i] is None:
+            slot[i] = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        slot[2] = 1 - i
+        return slot[i]
 
     def submit(self, planes, names):
         """planes: {name: device uint8/uint16 tensor}; names: {name: file path}.  Returns immediately."""
@@ -312,7 +325,7 @@ class _FrameWriter:
             for k, path in names.items():
                 t = planes[k]
                 t.record_stream(self.stream)
-                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h = self._host_buffer(k, t)
                 h.copy_(t, non_blocking=True)
                 host[path] = h
             done = torch.cuda.Event()

@@ -20,6 +20,13 @@ def default_precision():
     return _DEFAULT_PRECISION
 
 
+def poll_status():
+    """Report (raise) what kernels enqueued so far have recorded: a tripped barrier watchdog (InrfError) or a value
+    outside the fp16 range of the tensor-core path (InrfRangeError).  The hot entry points poll on entry without
+    synchronising; call this after a stream/device synchronise to check everything launched before it."""
+    check(_lib.lib().inrf_poll_status())
+
+
 def _prec(p):
     if p is None:
         return _DEFAULT_PRECISION
