@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the IntrinsicNeRF ray-marching hot path on B200.
 
-Contract (see the task brief): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON
-line.  A step = one full 800x800 synthetic Blender-'chair' view (640 000 rays, 64 coarse + 128
-fine samples, two 8x256 intrinsic MLPs) rendered per GPU (weak scaling: every rank renders its own
-pose; rays shard by image, there is no data-path collective).
+Contract (task brief): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line (rank 0).
 
-  value      rays/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        rays/s through the public API (object_level.render with host rays): pinned-host
-             rays -> H2D -> render -> D2H of the six maps, every step
-  roofline   tensor-pipe fraction of the dominant kernel (k_mlp_tc, fine pass launch), algorithmic
-             FLOPs (1 318 912 FLOP/sample) / CUDA-event time / measured bf16 peak
-  cpu_baseline  the CPU oracle (torch fp32 port of the reference algorithm) on a bounded ray sample
+The job (identical for every N: strong scaling).  One step = ``--views`` (default 24) synthetic 800x800 Blender-'chair'
+views of the 100-pose orbit of BASELINE config 4 (pose_spherical(theta, -30, 4), theta in linspace(-180, 180, 101)[:-1],
+every (100/views)-th pose), 64 coarse + 128 fine samples, two 8x256 intrinsic MLPs (BASELINE config 2 per view; the 100
+views of config 4 scaled to 24 so that one N=1 step stays at a few seconds).  Views are sharded by image over the ranks
+(reference loop: object_level/run_nerf.py:142-186 render_path); every finished frame's per-ray record (13 fp32 = 52
+B/ray) is all-gathered over NCCL INSIDE the timed region, on NCCL's stream, while the rank renders its next view.
 
-``--impl reference`` times the reference algorithm's CPU implementation (the oracle port: the
-reference itself lives in /root/reference, which does not exist on the GPU box) on the host cores.
+  value        rays/s of the whole job (all ranks), rays resident in HBM, CUDA events, max over ranks
+  e2e          the same job through the public API with host buffers: per view pinned-host rays -> H2D ->
+               object_level.render(rays=...) -> D2H of the six maps
+  roofline     tensor-pipe fraction of the dominant kernel (fine-pass k_mlp_tc launch), algorithmic FLOPs
+               (1 318 912 FLOP/sample) / CUDA-event time / measured bf16 peak
+  cpu_baseline the UNMODIFIED reference render() (oracle/_ref staged copy or /root/reference) on the host cores, bounded
+               sample (N=1 only): all-core row + the as-shipped 1-thread row + BASELINE config 1
+  config5      BASELINE config 5 at N ranks: SSR training step (1024 rays sharded over the ranks, render + backward +
+               gradient all-reduce + Adam)
+
+``--impl reference`` times the unmodified reference render() on the host cores (rank 0 only; other ranks exit).
 """
 import argparse
+import contextlib
 import json
 import math
 import os
@@ -35,6 +42,7 @@ N_SAMPLES, N_IMPORTANCE = 64, 128
 FLOP_PER_SAMPLE = 1318912                       # SURVEY 8d, object network, GEMMs only
 FLOP_PER_RAY = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * FLOP_PER_SAMPLE
 BYTES_PER_RAY = 144                             # 44 B in + 100 B out
+METRIC = "rays/sec (64+128 samples)"
 
 
 def peaks():
@@ -44,6 +52,24 @@ def peaks():
         return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def measured_traffic():
+    """DRAM bytes per MLP row of the dominant kernel from the tracked ncu summary (profiles/mlp_tc_traffic.json,
+    written by tools/summarize_profiles.py from an `ncu --set full` capture); None when no capture is tracked."""
+    p = os.path.join(ROOT, "profiles", "mlp_tc_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p))
+
+
+def workload_config(args, world):
+    """The `config` object - identical in the product arm and the reference arm."""
+    return {"workload": "blender_chair_800x800_64+128", "H": H, "W": W, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE,
+            "net": "2 x NeRF(D=8,W=256,skips=[4]) intrinsic heads", "views_per_step": args.views,
+            "rays_per_step": args.views * H * W,
+            "parallelism": f"views sharded by image over {world} rank(s); per-view record all-gather (NCCL) inside the timed region",
+            "l2": "no explicit flush: every view streams 28 MB of rays and the per-chunk scratch is far larger than the 126 MB L2"}
 
 
 class ClockSampler:
@@ -84,94 +110,211 @@ class ClockSampler:
         return out
 
 
-def synthetic_rays(rank, device):
-    """[H*W, 11] rays of a Blender-style view: pose_spherical(theta_rank, -30, 4) (load_blender.py:29-34),
-    camera_angle_x of the 'chair' scene, near 2, far 6 - generated on the device by inrf_get_rays."""
-    from intrinsicnerf_b200 import ops
-    theta = math.radians(-180.0 + 360.0 * (rank % 100) / 100.0)
+def view_pose(v, n_views):
+    """c2w [3,4] of view v of the job: pose_spherical(theta, -30, 4) (load_blender.py:29-34) on the 100-pose orbit."""
+    idx = (v * 100) // n_views
+    theta = math.radians(-180.0 + 360.0 * idx / 100.0)
     phi = math.radians(-30.0)
     ct, st, cp, sp = math.cos(theta), math.sin(theta), math.cos(phi), math.sin(phi)
     trans = torch.tensor([[1., 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 4.0], [0, 0, 0, 1]])
     rphi = torch.tensor([[1., 0, 0, 0], [0, cp, -sp, 0], [0, sp, cp, 0], [0, 0, 0, 1]])
     rth = torch.tensor([[ct, 0, -st, 0], [0, 1., 0, 0], [st, 0, ct, 0], [0, 0, 0, 1]])
     flip = torch.tensor([[-1., 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])
-    c2w = (flip @ rth @ rphi @ trans)[:3, :4]
+    return (flip @ rth @ rphi @ trans)[:3, :4]
+
+
+def intrinsics():
     f = 0.5 * W / math.tan(0.5 * 0.6911112070083618)
-    K = [[f, 0.0, 0.5 * W], [0.0, f, 0.5 * H], [0.0, 0.0, 1.0]]
-    return ops.get_rays_packed(H, W, K, c2w, 2.0, 6.0, device)
+    return [[f, 0.0, 0.5 * W], [0.0, f, 0.5 * H], [0.0, 0.0, 1.0]]
 
 
-def cpu_baseline(n_rays=2048, seconds_cap=40.0):
-    """The oracle's render_rays on the host cores.  The thread count is probed (all cores, then
-    halving) on a small batch and the fastest setting is used for the timed sample - many-core hosts
-    are slower with every core on these GEMM sizes."""
-    from oracle import nerf_oracle as orc
-    ncpu = os.cpu_count() or 1
-    coarse, fine = orc.seeded_nets("object")
-    rays = orc.blender_rays(64, 64)[:n_rays].contiguous()
-    probe = {}
-    with torch.no_grad():
-        t = ncpu
-        while t >= 8 or t == ncpu:
-            torch.set_num_threads(t)
-            orc.render_rays(rays[:128], coarse, fine, white_bkgd=True)
-            t0 = time.perf_counter()
-            orc.render_rays(rays[:256], coarse, fine, white_bkgd=True)
-            probe[t] = 256 / (time.perf_counter() - t0)
-            if t <= 8:
-                break
-            t //= 2
-        threads = max(probe, key=probe.get)
-        torch.set_num_threads(threads)
-        orc.render_rays(rays[:256], coarse, fine, white_bkgd=True)          # warm-up
-        t0 = time.perf_counter()
-        done = 0
-        for i in range(0, rays.shape[0], 512):
-            orc.render_rays(rays[i:i + 512], coarse, fine, white_bkgd=True)
-            done += min(512, rays.shape[0] - i)
-            if time.perf_counter() - t0 > seconds_cap:
-                break
-        dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "rays/s", "cores": threads, "kind": "port", "host_cpus": ncpu,
-            "thread_probe_rays_per_s": {str(k): round(v, 1) for k, v in probe.items()},
-            "sample": f"{done} rays of a 64x64 Blender view, 64+128 samples, oracle.render_rays, torch {torch.__version__} CPU"}
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference render() on the host cores
+# --------------------------------------------------------------------------------------------------------------------
+def reference_rows(n_rays=1024, probe=True, extra_rows=True):
+    """All-core timing of reference render() on a ray sample of the 800x800 view (+ the two single-thread rows of
+    BASELINE.md section 3 in subprocesses).  Returns (rays_per_s, cpu_baseline dict, timer(fn) for repeated steps)."""
+    from oracle import ref_bench as rb
+    from oracle import refshim
+    with contextlib.redirect_stdout(sys.stderr):             # the reference prints while it builds its networks
+        rn, kw = rb.build(N_IMPORTANCE)
+        ncpu = os.cpu_count() or 1
+        if probe:
+            threads, table = rb.probe_threads(rn, kw, H, W)
+        else:
+            threads, table = ncpu, {}
+            torch.set_num_threads(threads)
+        rb.time_sample(rn, kw, H, W, 128)                    # warm-up
+        dt, n = rb.time_sample(rn, kw, H, W, n_rays)
+    base = {"value": n / dt, "unit": "rays/s", "cores": threads, "kind": "reference", "host_cpus": ncpu,
+            "thread_probe_rays_per_s": {str(k): round(v, 1) for k, v in table.items()},
+            "sample": f"{n} rays (regular sub-grid) of the 800x800 view, 64+128 samples, the unmodified reference "
+                      f"render(rays=...) from {os.path.relpath(refshim.REF_ROOT, ROOT) if refshim.REF_ROOT.startswith(ROOT) else refshim.REF_ROOT}, "
+                      f"torch {torch.__version__} CPU, {threads} threads"}
+    if extra_rows:
+        rows = {}
+        for row, rays in (("config1", 1024), ("as_shipped", 256)):
+            r = rb.row_subprocess(row, rays)
+            rows[row] = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in r.items() if k in ("rays_per_s", "rays", "threads", "what", "error")}
+        base["rows"] = rows
+
+    def one_step():
+        with contextlib.redirect_stdout(sys.stderr):
+            d, m = rb.time_sample(rn, kw, H, W, n_rays)
+        return m / d
+    return base, one_step
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm's CPU implementation (oracle port), rank 0 only."""
+    """--impl reference: rank 0 alone times the unmodified reference; each step = one render() of a bounded ray sample."""
     if rank != 0:
         return
-    steps = []
-    base = None
+    base, one_step = reference_rows(n_rays=1024)
+    vals = []
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(n_rays=1024, seconds_cap=30.0)
+        v = one_step()
         if i >= args.warmup:
-            steps.append(base["value"])
-    v = sum(steps) / len(steps)
+            vals.append(v)
+    v = sum(vals) / len(vals)
     base["value"] = v
-    out = {"impl": "reference", "metric": "rays/sec (64+128 samples)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 1024 / v, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "blender_chair_800x800_64+128", "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE,
-                      "net": "2 x NeRF(D=8,W=256,skips=[4]) intrinsic heads",
-                      "sample": "bounded 1024-ray sample of the workload per step (cost is exactly linear in rays)"},
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, reference seed 20220414; pose_spherical Blender camera)",
+           "config": workload_config(args, world),
+           "step_sample": "each step renders a bounded 1024-ray sample of the workload (cost is exactly linear in rays)",
            "cpu_baseline": base, "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
-def run_room0(args, rank, local, world, dev, dist):
-    """Secondary line (not the headline): the SSR fork's renderer on Replica-shaped input.  One step = 8 frames of
-    320x240 (614 400 rays) through SSRRenderer-equivalent calls; `value` device-resident via inrf_render_fwd,
-    `e2e` through SSRRenderer.render_rays with host rays and D2H of rgb / depth / semantic logits."""
+# --------------------------------------------------------------------------------------------------------------------
+# shared timing helpers
+# --------------------------------------------------------------------------------------------------------------------
+class Timer:
+    def __init__(self, dev, dist):
+        self.dev, self.dist = dev, dist
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        """Total milliseconds of `steps` calls (CUDA events per step, summed), max over ranks."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in ev:
+            s.record()
+            fn()
+            e.record()
+        self.barrier()
+        t = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], device=self.dev, dtype=torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: SSR training step at N ranks
+# --------------------------------------------------------------------------------------------------------------------
+def make_ssr_trainer(dev, C, training):
     import intrinsicnerf_b200 as inrf
-    from intrinsicnerf_b200 import ops, ssr
-    C, Hh, Ww, frames = 28, 240, 320, 8
-    flop_per_ray = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * 2 * (692224 + 128 * C)          # SURVEY 8d, SSR network
+    from intrinsicnerf_b200 import ssr
     torch.manual_seed(20220414)
     mk = lambda: inrf.Semantic_NeRF(True, C, D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27,  # noqa: E731
                                     use_viewdirs=True).to(dev)
     coarse, fine = mk(), mk()
+
+    class T(ssr.SSRRenderer):
+        pass
+    t = T()
+    t.N_samples, t.N_importance = N_SAMPLES, N_IMPORTANCE
+    t.perturb, t.raw_noise_std, t.training = (1.0, 1.0, True) if training else (0.0, 0.0, False)   # SSR_room0_config.yaml:29,34
+    t.white_bkgd, t.enable_semantic, t.num_valid_semantic_class, t.endpoint_feat = False, True, C, False
+    t.netchunk = t.chunk = 76800
+    t.ssr_net_coarse, t.ssr_net_fine = coarse, fine
+    t.embed_fn, _ = ssr.get_embedder(10, 0, scalar_factor=10)
+    t.embeddirs_fn, _ = ssr.get_embedder(4, 0, scalar_factor=1)
+    return t, coarse, fine
+
+
+def train_step_record(dev, dist, rank, world, steps=20, warmup=5, n_rays=1024, C=28):
+    """One SSR training step (SSR/training/trainer.py:851-1010 `step`): 1024 rays = 512 pixels + one neighbour each,
+    perturb=1, raw_noise_std=1; render coarse+fine in training mode, photometric + semantic + intrinsic losses on the
+    full batch, backward, gradient all-reduce, Adam.  At N ranks the rays are sharded (parallel.ray_shard), the rendered
+    maps are all-gathered with a gradient (the losses pair ray i with ray i+N/2), and one flat all-reduce sums the
+    gradients of both networks."""
+    from intrinsicnerf_b200 import ops, parallel, ssr
+    t, coarse, fine = make_ssr_trainer(dev, C, training=True)
+    if dist is not None:
+        for m in (coarse, fine):
+            parallel.broadcast_weights(m, 0)
+    g = torch.Generator().manual_seed(7)
+    Hh, Ww = 240, 320
+    pix = torch.randint(0, Hh * Ww, (n_rays // 2,), generator=g)
+    nb = (pix + torch.randint(0, 3, (n_rays // 2,), generator=g) - 1).clamp(0, Hh * Ww - 1)      # a neighbour per pixel (rays.py:153-172)
+    pose = torch.eye(4)
+    rays_all = ssr.rays_for_batch(torch.cat([pix, nb]).to(dev), pose, Hh, Ww, Ww / 2, Ww / 2, (Ww - 1) / 2, (Hh - 1) / 2, 0.1, 10.0)
+    gt = torch.rand(n_rays, 3, generator=g).to(dev)
+    labels = torch.randint(0, C, (n_rays,), generator=g).to(dev)
+    a, b = parallel.ray_shard(n_rays, rank, world)
+    rays = rays_all[a:b].contiguous()
+    nets = [coarse, fine]
+    opt = torch.optim.Adam([p for m in nets for p in m.parameters()], lr=5e-4)
+    ce = torch.nn.functional.cross_entropy
+    keys = ("rgb_fine", "rgb_coarse", "albedo_fine", "shading_fine", "residual_fine", "albedo_coarse", "shading_coarse",
+            "residual_coarse", "sem_logits_fine", "sem_logits_coarse")
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = t.render_rays(rays)
+        m = parallel.gather_maps_for_loss({k: out[k] for k in keys}, n_rays) if dist is not None else out
+        loss = ((m["rgb_fine"] - gt) ** 2).mean() + ((m["rgb_coarse"] - gt) ** 2).mean() \
+            + 0.04 * (ce(m["sem_logits_fine"], labels) + ce(m["sem_logits_coarse"], labels))
+        for sfx in ("fine", "coarse"):
+            terms = ops.intrinsic_losses(None, m["albedo_" + sfx], m["shading_" + sfx], m["residual_" + sfx], gt, labels.float(), None, "ssr")
+            loss = loss + terms[1:7].sum() * 0.01
+        loss.backward()
+        if dist is not None:
+            parallel.allreduce_gradients(nets)
+        opt.step()
+        return loss
+
+    tm = Timer(dev, dist)
+    l0 = ops.launch_count()
+    ms = tm.timed(step, steps, warmup)
+    launches = (ops.launch_count() - l0) / (steps + warmup)
+    torch.cuda.synchronize()
+    ops.poll_status()
+    flop = n_rays * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * 2 * (692224 + 128 * C) * 3          # fwd + dX + dW (SURVEY 8d)
+    per = ms / steps
+    pk = peaks()
+    n_grad = sum(p.numel() for m_ in nets for p in m_.parameters())
+    return {"workload": "replica_room0_train_step_1024rays_64+128_C28", "n_gpus": world, "ms_per_step": per,
+            "rays_per_s": n_rays / (per * 1e-3), "rays_per_step": n_rays, "rays_per_rank": b - a,
+            "algorithmic_tflops": flop / (per * 1e-3) / 1e12,
+            "frac_of_sustained_bf16": flop / (per * 1e-3) / 1e12 / ((pk["bf16_sustained"] or pk["bf16_tflops"]) * world),
+            "libinrf_launches_per_step": launches,
+            "collectives": None if dist is None else
+            f"all_gather of {len(keys)} rendered maps (~{n_rays * (3 * 8 + 2 * C) * 4 // 1024} KB, autograd) + one all_reduce of "
+            f"{n_grad} fp32 gradients ({n_grad * 4 / 1e6:.1f} MB)",
+            "includes": "ray sampling excluded; render (training mode, in-kernel stash) + losses + backward + all-reduce + Adam"}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# secondary workloads (not the headline): Replica room_0 shape, eval render and training step
+# --------------------------------------------------------------------------------------------------------------------
+def run_room0(args, rank, local, world, dev, dist):
+    """BASELINE config 3.  One step = 8 frames of 320x240 (614 400 rays) per rank through the SSR renderer; `value`
+    device-resident via inrf_render_fwd, `e2e` through SSRRenderer.render_rays with host rays and D2H of rgb / depth /
+    semantic logits."""
+    from intrinsicnerf_b200 import ops, ssr
+    C, Hh, Ww, frames = 28, 240, 320, 8
+    flop_per_ray = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * 2 * (692224 + 128 * C)          # SURVEY 8d, SSR network
+    t, coarse, fine = make_ssr_trainer(dev, C, training=False)
     poses = torch.eye(4).repeat(frames, 1, 1)
     for i in range(frames):
         a = math.radians(45.0 * i + 5.0 * rank)
@@ -180,16 +323,6 @@ def run_room0(args, rank, local, world, dev, dist):
     n_rays = rays_dev.shape[0]
     rays_host = rays_dev.cpu().pin_memory()
     pc, pf = coarse.packed(), fine.packed()
-
-    class T(ssr.SSRRenderer):
-        pass
-    t = T()
-    t.N_samples, t.N_importance, t.perturb, t.raw_noise_std, t.training = N_SAMPLES, N_IMPORTANCE, 0.0, 0.0, False
-    t.white_bkgd, t.enable_semantic, t.num_valid_semantic_class, t.endpoint_feat = False, True, C, False
-    t.netchunk = t.chunk = 76800
-    t.ssr_net_coarse, t.ssr_net_fine = coarse, fine
-    t.embed_fn, _ = ssr.get_embedder(10, 0, scalar_factor=10)
-    t.embeddirs_fn, _ = ssr.get_embedder(4, 0, scalar_factor=1)
     chunks = [(i, min(i + 76800, n_rays)) for i in range(0, n_rays, 76800)]
 
     def step_device():
@@ -207,50 +340,34 @@ def run_room0(args, rank, local, world, dev, dist):
             dst.copy_(d[k].reshape(n_rays, -1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for s_, e_ in ev:
-            s_.record()
-            fn()
-            e_.record()
-        barrier()
-        tt = torch.tensor([sum(s_.elapsed_time(e_) for s_, e_ in ev)], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
+    tm = Timer(dev, dist)
     with torch.no_grad():
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ms_dev = timed(step_device, args.steps, max(3, args.warmup))
+        l0 = ops.launch_count()
+        ms_dev = tm.timed(step_device, args.steps, max(3, args.warmup))
+        launches = (ops.launch_count() - l0) * args.steps // (args.steps + max(3, args.warmup))
         clocks = sampler.stop() if rank == 0 else None
         e2e_steps = max(2, args.steps // 2)
-        ms_e2e = timed(step_e2e, e2e_steps, 1)
+        ms_e2e = tm.timed(step_e2e, e2e_steps, 1)
+    torch.cuda.synchronize()
+    ops.poll_status()
     if rank == 0:
         pk = peaks()
         value = n_rays * world * args.steps / (ms_dev * 1e-3)
-        out = {"metric": "rays/sec (64+128 samples)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        out = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f16 operands (RN) x f32 accumulate on tcgen05; everything else f32",
                "data": "synthetic (random-init weights, reference seed 20220414; Replica-shaped cameras)",
                "config": {"workload": "replica_room0_320x240_64+128_C28", "frames_per_step_per_gpu": frames, "rays_per_step_per_gpu": n_rays,
                           "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "net": "2 x Semantic_NeRF(D=8,W=256,skips=[4], C=28)",
-                          "parallelism": f"rays sharded by image, dp{world}, no data-path collective",
+                          "parallelism": f"frames sharded by image, dp{world}, no data-path collective",
                           "l2": "no explicit flush: per-step working set >> 126 MB L2"},
                "e2e": {"value": n_rays * world * e2e_steps / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(n_rays * 44),
                        "d2h_bytes_per_step": int(n_rays * (4 + C) * 4),
-                       "api": "SSRRenderer.render_rays(host rays) + D2H of rgb_fine, depth_fine, sem_logits_fine (raw_* materialised as the API requires)"},
-               "gpu_launches": 8 * len(chunks) * args.steps,
+                       "api": "SSRRenderer.render_rays(host rays) + D2H of rgb_fine, depth_fine, sem_logits_fine"},
+               "gpu_launches": launches,
                "roofline": {"bound": "tensor", "kernel": "k_mlp_tc (whole step)", "achieved": value / world * flop_per_ray / 1e12,
                             "peak": pk["bf16_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": value / world * flop_per_ray / 1e12 / (pk["bf16_sustained"] or pk["bf16_tflops"]), "traffic": None,
@@ -261,6 +378,34 @@ def run_room0(args, rank, local, world, dev, dist):
         dist.destroy_process_group()
 
 
+def run_room0_train(args, rank, local, world, dev, dist):
+    """BASELINE config 5 as its own line: metric = rays/s of the SSR training step (1024 rays per step over all ranks)."""
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rec = train_step_record(dev, dist, rank, world, steps=max(20, args.steps), warmup=max(5, args.warmup))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        pk = peaks()
+        out = {"metric": "rays/sec (64+128 samples), training step", "value": rec["rays_per_s"], "unit": "rays/s", "n_gpus": world,
+               "steps": max(20, args.steps), "warmup": max(5, args.warmup), "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands x f32 accumulate (tcgen05) forward and backward; Adam in f32",
+               "data": "synthetic (random-init weights, seed 20220414; Replica-shaped camera; random targets)",
+               "config": {"workload": rec["workload"], "rays_per_step": rec["rays_per_step"], "n_samples": N_SAMPLES,
+                          "n_importance": N_IMPORTANCE, "net": "2 x Semantic_NeRF(D=8,W=256,skips=[4], C=28)",
+                          "parallelism": f"rays sharded over {world} rank(s); " + (rec["collectives"] or "no collective"),
+                          "l2": "working set (stash 5.25 KB/sample x 262 144 samples = 1.4 GB per step) >> 126 MB L2"},
+               "e2e": None, "gpu_launches": int(rec["libinrf_launches_per_step"] * max(20, args.steps)),
+               "roofline": {"bound": "tensor", "kernel": "training step (forward + dX + dW GEMMs)", "achieved": rec["algorithmic_tflops"],
+                            "peak": (pk["bf16_sustained"] or pk["bf16_tflops"]) * world, "unit": "TFLOP/s", "frac": rec["frac_of_sustained_bf16"],
+                            "traffic": None, "peak_source": pk["source"] + ", sustained bf16 x ranks; 3 x forward FLOPs (SURVEY 8d)"},
+               "clocks": clocks, "cpu_baseline": None, "config5": rec}
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,11 +413,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
-    ap.add_argument("--chunk", type=int, default=160000, help="rays per inrf_render_fwd call (bounds the raw scratch)")
+    ap.add_argument("--views", type=int, default=24, help="800x800 views per step (the whole job, fixed for every N)")
+    ap.add_argument("--chunk", type=int, default=160000, help="rays per inrf_render_fwd call (bounds the scratch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="chair", choices=["chair", "room0"],
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--workload", default="chair", choices=["chair", "room0", "room0_train"],
                     help="chair: the BASELINE headline config (default). room0: BASELINE config 3 - Replica room_0 shape "
-                         "(320x240 frames, Semantic_NeRF with 28 classes, near 0.1 / far 10, PE scale 10), 8 frames per step")
+                         "(320x240 frames, Semantic_NeRF with 28 classes, near 0.1 / far 10, PE scale 10), 8 frames per step. "
+                         "room0_train: BASELINE config 5 - the SSR training step")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -291,12 +439,15 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import intrinsicnerf_b200 as inrf
-    from intrinsicnerf_b200 import object_level as ol, ops
+    from intrinsicnerf_b200 import object_level as ol, ops, parallel
     ops.set_default_precision(args.precision)
 
     if args.workload == "room0":
         return run_room0(args, rank, local, world, dev, dist)
-    # random-init weights of the reference architecture, reference seed (run_nerf.py:1130)
+    if args.workload == "room0_train":
+        return run_room0_train(args, rank, local, world, dev, dist)
+
+    # random-init weights of the reference architecture, reference seed (run_nerf.py:1130); identical on every rank
     torch.manual_seed(20220414)
     mk = lambda: inrf.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(dev)  # noqa: E731
     coarse, fine = mk(), mk()
@@ -304,113 +455,129 @@ def main():
     embeddirs_fn, _ = ol.get_embedder(4, 0)
     kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=ol._FusedQuery(embed_fn, embeddirs_fn, 65536),
               N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=0., white_bkgd=True, raw_noise_std=0.)
-    rays_dev = synthetic_rays(rank, dev)
-    rays_host = rays_dev.cpu().pin_memory()
-    n_rays = rays_dev.shape[0]
+    V = args.views
+    rounds = (V + world - 1) // world                      # views per rank (the last round may be padded with an idle rank)
+    mine = parallel.image_shard(V, rank, world)            # views rank, rank+world, ...
+    K = intrinsics()
+    n_rays = H * W
+    rays_dev = [ops.get_rays_packed(H, W, K, view_pose(v, V), 2.0, 6.0, dev) for v in mine]
     pc, pf = coarse.packed(), fine.packed()
     chunks = [(i, min(i + args.chunk, n_rays)) for i in range(0, n_rays, args.chunk)]
-    launches_per_step = 8 * len(chunks)
+    rec_w = 13
+    rec_local = [torch.zeros(n_rays, rec_w, device=dev) for _ in range(rounds)]
+    rec_all = [torch.empty(world, n_rays, rec_w, device=dev) for _ in range(rounds)] if world > 1 else None
 
     def step_device():
-        for a, b in chunks:
-            ops.render_chunk(rays_dev[a:b], pc, pf, white_bkgd=True, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE)
+        """The job on this rank: render my views; after each view start the all-gather of its records (NCCL stream)
+        and go on rendering; wait for every gather before the step ends."""
+        works = []
+        for k in range(rounds):
+            if k < len(rays_dev):
+                for a, b in chunks:
+                    o = ops.render_chunk(rays_dev[k][a:b], pc, pf, white_bkgd=True, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE)
+                    rec_local[k][a:b].copy_(o["rec_fine"])
+            if world > 1:
+                works.append(dist.all_gather_into_tensor(rec_all[k].view(world * n_rays, rec_w), rec_local[k], async_op=True))
+        for w_ in works:
+            w_.wait()
 
-    o_host, d_host = rays_host[:, 0:3].contiguous().pin_memory(), rays_host[:, 3:6].contiguous().pin_memory()
+    # e2e: host rays in, host maps out, through object_level.render
+    rays_host = [(r[:, 0:3].contiguous().cpu().pin_memory(), r[:, 3:6].contiguous().cpu().pin_memory()) for r in rays_dev]
     out_host = [torch.empty(n_rays, c, pin_memory=True) for c in (3, 1, 1, 3, 1, 3)]
-    Kmat = [[1111.111, 0, W / 2], [0, 1111.111, H / 2], [0, 0, 1]]
 
     def step_e2e():
-        ro, rd = o_host.to(dev, non_blocking=True), d_host.to(dev, non_blocking=True)
-        with torch.no_grad():
-            res = ol.render(H, W, Kmat, chunk=args.chunk, rays=(ro, rd), ndc=False, near=2., far=6., use_viewdirs=True, **kw)
-        for dst, src in zip(out_host, res[:6]):
-            dst.copy_(src.reshape(n_rays, -1), non_blocking=True)
+        for o_h, d_h in rays_host:
+            ro, rd = o_h.to(dev, non_blocking=True), d_h.to(dev, non_blocking=True)
+            with torch.no_grad():
+                res = ol.render(H, W, K, chunk=args.chunk, rays=(ro, rd), ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+            for dst, src in zip(out_host, res[:6]):
+                dst.copy_(src.reshape(n_rays, -1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for s, e in ev:
-            s.record()
-            fn()
-            e.record()
-        barrier()
-        ms = sum(s.elapsed_time(e) for s, e in ev)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    tm = Timer(dev, dist)
+    warm = max(3, args.warmup)
     with torch.no_grad():
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ms_dev = timed(step_device, args.steps, max(3, args.warmup))
+        l0 = ops.launch_count()
+        ms_dev = tm.timed(step_device, args.steps, warm)
+        launches = (ops.launch_count() - l0) * args.steps // (args.steps + warm)      # this rank's kernels inside the timed steps
         clocks = sampler.stop() if rank == 0 else None
-        ms_e2e = timed(step_e2e, max(2, args.steps // 2), 1)
-        e2e_steps = max(2, args.steps // 2)
+        e2e_steps = max(2, args.steps // 4)
+        ms_e2e = tm.timed(step_e2e, e2e_steps, 1)
 
         # dominant kernel alone: fine-pass launch of k_mlp_tc (or the fp32 kernel) on one chunk
-        a, b = chunks[0]
-        o = ops.render_chunk(rays_dev[a:b], pc, pf, white_bkgd=True, want_z=True)
-        zf = o["z_fine"]
-        n_k = 5
-        for _ in range(2):
-            ops.mlp_forward_rays(pf, 0, 0, rays_dev[a:b], zf)
-        torch.cuda.synchronize()
-        ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ks.record()
-        for _ in range(n_k):
-            ops.mlp_forward_rays(pf, 0, 0, rays_dev[a:b], zf)
-        ke.record()
-        torch.cuda.synchronize()
-        k_ms = ks.elapsed_time(ke) / n_k
-        k_flops = (b - a) * (N_SAMPLES + N_IMPORTANCE) * FLOP_PER_SAMPLE
+        k_ms = k_flops = None
+        if rays_dev:
+            a, b = chunks[0]
+            o = ops.render_chunk(rays_dev[0][a:b], pc, pf, white_bkgd=True, want_z=True)
+            zf = o["z_fine"]
+            n_k = 5
+            for _ in range(2):
+                ops.mlp_forward_rays(pf, 0, 0, rays_dev[0][a:b], zf)
+            torch.cuda.synchronize()
+            ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ks.record()
+            for _ in range(n_k):
+                ops.mlp_forward_rays(pf, 0, 0, rays_dev[0][a:b], zf)
+            ke.record()
+            torch.cuda.synchronize()
+            k_ms = ks.elapsed_time(ke) / n_k
+            k_flops = (b - a) * (N_SAMPLES + N_IMPORTANCE) * FLOP_PER_SAMPLE
+    torch.cuda.synchronize()
+    ops.poll_status()                                         # a tripped watchdog / fp16-range record would invalidate the run
+    config5 = None
+    if not args.no_config5:
+        config5 = train_step_record(dev, dist, rank, world)
 
+    comm = None
+    if world > 1:
+        lt = torch.tensor([launches], device=dev, dtype=torch.float64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+        comm = {"collective": "all_gather_into_tensor", "backend": "nccl", "calls_per_step": rounds,
+                "bytes_per_call_per_rank": n_rays * rec_w * 4, "received_bytes_per_step_per_rank": rounds * (world - 1) * n_rays * rec_w * 4,
+                "overlap": "async on NCCL's stream behind the next view's render; waited for inside the timed region"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     pk = peaks()
-    total_rays = n_rays * world * args.steps
-    value = total_rays / (ms_dev * 1e-3)
-    e2e_val = n_rays * world * e2e_steps / (ms_e2e * 1e-3)
+    job_rays = V * n_rays
+    value = job_rays * args.steps / (ms_dev * 1e-3)
+    e2e_val = job_rays * e2e_steps / (ms_e2e * 1e-3)
     ach_tf = k_flops / (k_ms * 1e-3) / 1e12
     kernel_name = "k_mlp_tc" if args.precision == "tc" else "k_mlp_fp32"
+    tr = measured_traffic()
+    rows = (chunks[0][1] - chunks[0][0]) * (N_SAMPLES + N_IMPORTANCE)
     out = {
-        "metric": "rays/sec (64+128 samples)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f16 operands (RN) x f32 accumulate on tcgen05; sigma head, PE, compositing, resampling in f32" if args.precision == "tc" else "f32",
         "data": "synthetic (random-init weights, reference seed 20220414; pose_spherical Blender camera)",
-        "config": {"workload": "blender_chair_800x800_64+128", "rays_per_step_per_gpu": n_rays, "n_samples": N_SAMPLES,
-                   "n_importance": N_IMPORTANCE, "net": "2 x NeRF(D=8,W=256,skips=[4]) intrinsic heads", "chunk_rays": args.chunk,
-                   "parallelism": f"rays sharded by image, dp{world}, no data-path collective",
-                   "l2": "no explicit flush: the per-step working set (raw tensors, ~5.9 GB) is >> the 126 MB L2"},
-        "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": int(n_rays * 24), "d2h_bytes_per_step": int(n_rays * 48),
-                "api": "object_level.render(rays=(o,d) from pinned host) + D2H of rgb,disp,acc,albedo,shading,residual"},
-        "gpu_launches": launches_per_step * args.steps,
+        "config": workload_config(args, world),
+        "impl_detail": {"chunk_rays": args.chunk, "views_per_rank": len(mine), "ms_per_view": ms_dev / args.steps / max(1, rounds)},
+        "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": int(len(mine) * n_rays * 24), "d2h_bytes_per_step": int(len(mine) * n_rays * 48),
+                "bytes_are": "per rank (rank 0)", "steps": e2e_steps,
+                "api": "per view: object_level.render(rays=(o,d) copied from pinned host) + D2H of rgb,disp,acc,albedo,shading,residual"},
+        "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": kernel_name, "achieved": ach_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": ach_tf / pk["bf16_tflops"],
-                     # DRAM bytes per launch: ncu --set full of the same kernel (profiles/r01e_prof_mlp_tc_raw.md):
-                     # (35.1 MB read + 282.7 MB written) / 7 680 000 rows = 41.4 B/row vs 48 B/row algorithmic (44 raw + 4 z)
-                     "traffic": (b - a) * (N_SAMPLES + N_IMPORTANCE) * 41.4, "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)",
-                     "kernel_ms": k_ms, "launch_rows": (b - a) * (N_SAMPLES + N_IMPORTANCE),
+                     "traffic": (tr["bytes_per_row"] * rows) if tr else None, "traffic_source": tr["source"] if tr else None,
+                     "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)",
+                     "kernel_ms": k_ms, "launch_rows": rows,
                      "whole_step_frac": value / world * FLOP_PER_RAY / 1e12 / (pk["bf16_sustained"] or pk["bf16_tflops"]),
                      "hbm_frac_algorithmic": value / world * BYTES_PER_RAY / 1e9 / pk["hbm_gbs"]},
-        "clocks": clocks,
+        "clocks": clocks, "comm": comm, "config5": config5,
     }
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline()
-    elif not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"], _ = reference_rows(n_rays=2048)
+        except Exception as e:                                # the staged reference is test infrastructure: say so, keep the line
+            out["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    else:
         out["cpu_baseline"] = None
     print(json.dumps(out), flush=True)
     if dist is not None:

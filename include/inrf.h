@@ -70,6 +70,10 @@ int inrf_version(void);
  * synchronised its stream, it reports everything enqueued so far); it clears the record.              */
 int inrf_poll_status(void);
 
+/* Number of CUDA kernels this library has launched in the calling process so far (all devices, all streams;
+ * memsets and copies are not kernels).  bench.py reports the difference across its timed region.          */
+int64_t inrf_launch_count(void);
+
 /* ---------------------------------------------------------------------------------
  * Weights
  * --------------------------------------------------------------------------------- */

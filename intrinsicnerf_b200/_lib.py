@@ -36,6 +36,7 @@ _SIGS = {
     "inrf_last_error_string": (C.c_char_p, []),
     "inrf_version": (i32, []),
     "inrf_poll_status": (i32, []),
+    "inrf_launch_count": (i64, []),
     "inrf_flat_param_count": (i64, [i32, i32]),
     "inrf_packed_bytes": (i64, [i32, i32]),
     "inrf_pack_weights": (i32, [p, i32, i32, p, i64, p]),

@@ -3,6 +3,7 @@
 
 namespace inrf {
 const char* last_error();
+long long launch_count();
 int pack_weights(const float* flat, int variant, int n_classes, void* packed, int64_t packed_bytes, cudaStream_t st);
 int launch_embed(const float* x, int64_t M, int L, float scale, float* out, cudaStream_t st);
 int launch_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S, int lindisp, float* z, cudaStream_t st);
@@ -70,6 +71,7 @@ extern "C" {
 const char* inrf_last_error_string(void) { return last_error(); }
 int inrf_version(void) { return 200; }
 int inrf_poll_status(void) { return status_poll(); }
+int64_t inrf_launch_count(void) { return launch_count(); }
 #define INRF_POLL() do { int rc__ = status_poll(); if (rc__) return rc__; } while (0)
 
 int64_t inrf_flat_param_count(int variant, int n_classes) {

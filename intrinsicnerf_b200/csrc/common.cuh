@@ -28,7 +28,8 @@ int cuda_fail(cudaError_t e, const char* what);
     cudaError_t e__ = (call);                                       \
     if (e__ != cudaSuccess) return ::inrf::cuda_fail(e__, #call);   \
   } while (0)
-#define INRF_LAUNCH_CHECK() INRF_CUDA(cudaGetLastError())
+void note_launch();                      // counts kernel launches (inrf_launch_count: the bench's gpu_launches claim)
+#define INRF_LAUNCH_CHECK() do { ::inrf::note_launch(); INRF_CUDA(cudaGetLastError()); } while (0)
 
 // ---------------------------------------------------------------------------------
 // Deferred device status (status.cu).  Kernels cannot return codes, and no hot entry point may
@@ -52,6 +53,7 @@ int status_poll();                      // INRF_OK, or INRF_ECUDA / INRF_ERANGE 
 __device__ __forceinline__ void status_raise(int* flag, int code, int a = 0, int b = 0, int c = 0, int d = 0, int e = 0) {
   if (flag == nullptr) return;
   volatile int* f = flag;
+  if (f[0] != 0) return;                  // an earlier record the host has not consumed yet wins
   f[1] = a; f[2] = b; f[3] = c; f[4] = d; f[5] = e;
   __threadfence_system();
   f[0] = code;

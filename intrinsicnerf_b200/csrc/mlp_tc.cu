@@ -773,7 +773,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     }
     // fp16 range: a stored activation at the saturation value 65504 (0x7bff) means the tile left the range the
     // tensor-core path can represent; report it (next API call returns INRF_ERANGE) instead of passing inf on
-    if (valid && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {
+    if (valid && !sy.dead && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {   // (an abandoned launch computes garbage)
       if (atomicCAS(P.dbg + 8, 0, 1) == 0) status_raise(P.status, DST_F16_ACT, 0, (int)tile, blockIdx.x);
     }
     tc_fence_before();
@@ -944,6 +944,7 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   INRF_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+  note_launch();
   if (prof_env) {
     static const char* bar_names[] = {"WFULL0","WFULL1","WFULL2","WFULL3","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3","F_READY","F_FREE",
       "A_READY0","A_READY1","A_READY2","A_READY3","H_FREE","ACC_FULL0","ACC_FULL1","V_READY",

@@ -1,8 +1,13 @@
 // Deferred device status: a 64-byte pinned, device-mapped record per device (see common.cuh).
 #include "common.cuh"
+#include <atomic>
 #include <mutex>
 
 namespace inrf {
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 static std::mutex g_mu;
 static int* g_host[64];

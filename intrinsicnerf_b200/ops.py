@@ -27,6 +27,11 @@ def poll_status():
     check(_lib.lib().inrf_poll_status())
 
 
+def launch_count():
+    """Kernels launched by libinrf.so in this process so far (inrf_launch_count)."""
+    return int(_lib.lib().inrf_launch_count())
+
+
 def _prec(p):
     if p is None:
         return _DEFAULT_PRECISION
