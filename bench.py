@@ -131,51 +131,35 @@ def intrinsics():
 # --------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the unmodified reference render() on the host cores
 # --------------------------------------------------------------------------------------------------------------------
-def reference_rows(n_rays=1024, probe=True, extra_rows=True):
-    """All-core timing of reference render() on a ray sample of the 800x800 view (+ the two single-thread rows of
-    BASELINE.md section 3 in subprocesses).  Returns (rays_per_s, cpu_baseline dict, timer(fn) for repeated steps)."""
+def reference_rows(n_rays=1024, steps=1, warmup=0, extra_rows=True):
+    """The unmodified reference render() on the host cores (oracle/ref_bench.py, each row in its own interpreter with
+    CUDA hidden): the all-core row on a ray sample of the 800x800 view (`steps` timed renders), plus the two
+    single-thread rows of BASELINE.md section 3.  Returns (cpu_baseline dict, per-step rays/s list)."""
     from oracle import ref_bench as rb
-    from oracle import refshim
-    with contextlib.redirect_stdout(sys.stderr):             # the reference prints while it builds its networks
-        rn, kw = rb.build(N_IMPORTANCE)
-        ncpu = os.cpu_count() or 1
-        if probe:
-            threads, table = rb.probe_threads(rn, kw, H, W)
-        else:
-            threads, table = ncpu, {}
-            torch.set_num_threads(threads)
-        rb.time_sample(rn, kw, H, W, 128)                    # warm-up
-        dt, n = rb.time_sample(rn, kw, H, W, n_rays)
-    base = {"value": n / dt, "unit": "rays/s", "cores": threads, "kind": "reference", "host_cpus": ncpu,
-            "thread_probe_rays_per_s": {str(k): round(v, 1) for k, v in table.items()},
-            "sample": f"{n} rays (regular sub-grid) of the 800x800 view, 64+128 samples, the unmodified reference "
-                      f"render(rays=...) from {os.path.relpath(refshim.REF_ROOT, ROOT) if refshim.REF_ROOT.startswith(ROOT) else refshim.REF_ROOT}, "
-                      f"torch {torch.__version__} CPU, {threads} threads"}
+    r = rb.row_subprocess("all_cores", n_rays, steps=steps, warmup=warmup)
+    if "error" in r:
+        raise RuntimeError("reference arm failed: " + r["error"])
+    root = r["reference_root"]
+    base = {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["threads"], "kind": "reference", "host_cpus": r["host_cpus"],
+            "thread_probe_rays_per_s": r["thread_probe_rays_per_s"],
+            "sample": f"{r['rays']} rays (regular sub-grid) of the 800x800 view, 64+128 samples, the unmodified reference "
+                      f"render(rays=...) from {os.path.relpath(root, ROOT) if root.startswith(ROOT) else root}, "
+                      f"torch {r['torch']} CPU, {r['threads']} threads, CUDA hidden from the process"}
     if extra_rows:
         rows = {}
         for row, rays in (("config1", 1024), ("as_shipped", 256)):
-            r = rb.row_subprocess(row, rays)
-            rows[row] = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in r.items() if k in ("rays_per_s", "rays", "threads", "what", "error")}
+            x = rb.row_subprocess(row, rays)
+            rows[row] = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in x.items() if k in ("rays_per_s", "rays", "threads", "what", "error")}
         base["rows"] = rows
-
-    def one_step():
-        with contextlib.redirect_stdout(sys.stderr):
-            d, m = rb.time_sample(rn, kw, H, W, n_rays)
-        return m / d
-    return base, one_step
+    return base, r["per_step"]
 
 
 def run_reference(args, rank, world):
     """--impl reference: rank 0 alone times the unmodified reference; each step = one render() of a bounded ray sample."""
     if rank != 0:
         return
-    base, one_step = reference_rows(n_rays=1024)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v = one_step()
-        if i >= args.warmup:
-            vals.append(v)
-    v = sum(vals) / len(vals)
+    base, per_step = reference_rows(n_rays=1024, steps=args.steps, warmup=args.warmup)
+    v = sum(per_step) / len(per_step)
     base["value"] = v
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 1024 / v, "higher_is_better": True,
@@ -574,7 +558,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         try:
-            out["cpu_baseline"], _ = reference_rows(n_rays=2048)
+            out["cpu_baseline"], _ = reference_rows(n_rays=2048, steps=2, warmup=1)
         except Exception as e:                                # the staged reference is test infrastructure: say so, keep the line
             out["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     else:

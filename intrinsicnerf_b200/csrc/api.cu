@@ -33,10 +33,30 @@ static int run_mlp(const MlpArgs& a, int precision, cudaStream_t st) {
 
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
-struct WsPlan { int64_t z_c, w_c, zmid, zs, z_f, raw_c, raw_f, total; };
+struct WsPlan { int64_t z_c, w_c, zmid, zs, z_f, raw_c, raw_f, ring, total; };
+
+// Fused renderer (two launches per chunk, no raw tensor): tensor-core precision, 32 | S for both passes, no endpoint
+// feature, and - when there is a fine pass - the reference's 64 + 128 samples with deterministic u.  Everything else
+// (caller wants raw / weights, random u, strict fp32) takes the stage-by-stage path.  INRF_NO_FUSE=1 forces that path.
+static bool can_fuse(const InrfRenderCfg& c, bool wants_raw_or_weights, bool random_u) {
+  static const bool off = getenv("INRF_NO_FUSE") != nullptr && getenv("INRF_NO_FUSE")[0] == '1';
+  if (off || c.precision != INRF_PREC_TC || c.endpoint_feat || wants_raw_or_weights) return false;
+  if ((c.n_samples & 31) || ((c.n_samples + c.n_importance) & 31)) return false;
+  if (c.n_importance > 0 && (random_u || c.n_samples != 64 || c.n_importance != 128)) return false;
+  return true;
+}
+
+static WsPlan plan_ws_fused(const InrfRenderCfg& c, int64_t N, bool own_z_f) {
+  WsPlan p{};
+  int64_t o = 0;
+  p.ring = o; o = align256(o + mlp_tc_ring_bytes(c.n_classes));
+  p.z_f = o; if (own_z_f && c.n_importance > 0) o = align256(o + N * (c.n_samples + c.n_importance) * 4);
+  p.total = o;
+  return p;
+}
 
 static WsPlan plan_ws(const InrfRenderCfg& c, int64_t N, bool own_raw_c, bool own_raw_f, bool own_z_f) {
-  WsPlan p;
+  WsPlan p{};
   int64_t o = 0;
   const int Sc = c.n_samples, Sf = c.n_importance, St = Sc + Sf;
   p.z_c = o; o = align256(o + N * Sc * 4);
@@ -281,7 +301,9 @@ int64_t inrf_render_workspace_bytes(const InrfRenderCfg* cfg, int64_t N) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   if (N < 0) { set_error("negative ray count"); return INRF_EINVAL; }
-  return plan_ws(*cfg, N, true, true, true).total + 256;
+  // worst case over the paths inrf_render_fwd may take (the stage path with its own raw tensors is the larger one)
+  const int64_t a = plan_ws(*cfg, N, true, true, true).total, b = plan_ws_fused(*cfg, N, true).total;
+  return (a > b ? a : b) + 256;
 }
 
 int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, const void* packed_fine,
@@ -299,11 +321,29 @@ int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, con
   const int Sc = c.n_samples, Sf = c.n_importance, St = Sc + Sf;
   if (Sf > 0) INRF_CHECK_ARG(rec_fine && (u || u_det), "fine pass needs rec_fine and u or u_det");
   cudaStream_t st = (cudaStream_t)stream;
-  WsPlan p = plan_ws(c, N, raw_coarse == nullptr, raw_fine == nullptr, z_fine == nullptr);
+  const bool fused = can_fuse(c, raw_coarse != nullptr || raw_fine != nullptr || weights_fine != nullptr, u != nullptr);
+  WsPlan p = fused ? plan_ws_fused(c, N, z_fine == nullptr) : plan_ws(c, N, raw_coarse == nullptr, raw_fine == nullptr, z_fine == nullptr);
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
   int64_t usable = workspace_bytes - (int64_t)(base - reinterpret_cast<uintptr_t>(workspace));
   if (usable < p.total) { set_error("workspace too small: %lld < %lld", (long long)usable, (long long)p.total); return INRF_EWORKSPACE; }
   auto F = [&](int64_t off) { return reinterpret_cast<float*>(base + off); };
+  if (fused) {
+    // coarse launch: depths generated in the front end, rows composited by the back-end warp, which also resamples
+    // and writes the merged depths of the fine pass; fine launch: composited the same way.  No raw tensor exists.
+    float* z_f = z_fine ? z_fine : F(p.z_f);
+    MlpArgs a{};
+    a.packed = packed_coarse; a.variant = c.variant; a.n_classes = c.n_classes; a.endpoint = 0;
+    a.pe_scale = c.pe_scalar_factor; a.rays = rays; a.z = nullptr; a.S = Sc; a.M = N * Sc; a.raw = nullptr;
+    FuseArgs f{};
+    f.white_bkgd = c.white_bkgd; f.lindisp = c.lindisp; f.t_vals = t_vals; f.t_rand = t_rand; f.noise = noise_coarse;
+    f.rec = rec_coarse; f.n_importance = Sf; f.u_det = u_det; f.z_out = Sf > 0 ? z_f : nullptr; f.z_std = z_std; f.ring = F(p.ring);
+    if ((rc = launch_mlp_tc(a, st, &f))) return rc;
+    if (Sf == 0) return INRF_OK;
+    a.packed = packed_fine ? packed_fine : packed_coarse;
+    a.z = z_f; a.S = St; a.M = N * St;
+    f.t_vals = nullptr; f.t_rand = nullptr; f.noise = noise_fine; f.rec = rec_fine; f.n_importance = 0; f.z_out = nullptr; f.z_std = nullptr;
+    return launch_mlp_tc(a, st, &f);
+  }
   float* z_c = F(p.z_c);
   float* w_c = F(p.w_c);
   float* zmid = F(p.zmid);

@@ -49,6 +49,26 @@ enum DevStatusCode {
 int* status_flag_dev();                 // device-visible pointer of the current device's record (nullptr: error set)
 int status_poll();                      // INRF_OK, or INRF_ECUDA / INRF_ERANGE with the message set; clears the record
 #ifdef __CUDACC__
+// coarse sample depths (run_nerf.py:464-486; trainer.py:730-746) - shared by k_coarse_z and the fused kernel's front end
+__device__ __forceinline__ float coarse_depth(float nearv, float farv, float t, int lindisp) {
+  if (!lindisp) return __fadd_rn(__fmul_rn(nearv, __fsub_rn(1.f, t)), __fmul_rn(farv, t));
+  float a = __fmul_rn(__fdiv_rn(1.f, nearv), __fsub_rn(1.f, t));
+  float b = __fmul_rn(__fdiv_rn(1.f, farv), t);
+  return __fdiv_rn(1.f, __fadd_rn(a, b));
+}
+// depth of sample s of a ray; t_rand_s: this sample's stratified-jitter draw (ignored when jitter == false)
+__device__ __forceinline__ float coarse_z_sample(float nearv, float farv, const float* __restrict__ t_vals, int s, int S, int lindisp,
+                                                 bool jitter, float t_rand_s) {
+  float zc = coarse_depth(nearv, farv, t_vals[s], lindisp);
+  if (jitter) {
+    float zl = s > 0 ? coarse_depth(nearv, farv, t_vals[s - 1], lindisp) : zc;
+    float zr = s < S - 1 ? coarse_depth(nearv, farv, t_vals[s + 1], lindisp) : zc;
+    float lower = s > 0 ? __fmul_rn(0.5f, __fadd_rn(zc, zl)) : zc;
+    float upper = s < S - 1 ? __fmul_rn(0.5f, __fadd_rn(zr, zc)) : zc;
+    zc = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand_s));
+  }
+  return zc;
+}
 // one writer per launch is elected by the caller (a device-side atomicCAS on its own claim word)
 __device__ __forceinline__ void status_raise(int* flag, int code, int a = 0, int b = 0, int c = 0, int d = 0, int e = 0) {
   if (flag == nullptr) return;
@@ -201,7 +221,24 @@ struct MlpBwdArgs {
   float* grad_flat;          // [flat_count], accumulated into (+=)
 };
 int launch_mlp_bwd_fp32(const MlpBwdArgs& a, cudaStream_t st);
-int launch_mlp_tc(const MlpArgs& a, cudaStream_t st);
+// In-kernel compositing / resampling of the fused renderer (mlp_tc.cu back-end warp; api.cu: inrf_render_fwd).
+// With a FuseArgs the tensor-core kernel does not write raw rows to HBM: the rows of the tile in flight go through a
+// small L2-resident ring and one warp composites them (raw2outputs, run_nerf.py:359-412) into per-ray records, and -
+// coarse pass - resamples (sample_pdf + sort, run_nerf.py:499-503) into the fine pass's depths.
+struct FuseArgs {
+  int white_bkgd, lindisp;
+  const float* t_vals;       // coarse pass, depths generated in-kernel (MlpArgs.z == nullptr): linspace(0,1,S)
+  const float* t_rand;       // [N,S] stratified jitter or nullptr
+  const float* noise;        // [N,S] sigma noise (already scaled) or nullptr
+  float* rec;                // [N, 13 + C] per-ray records
+  int n_importance;          // > 0: coarse pass also resamples (requires S == 64, n_importance == 128, deterministic u)
+  const float* u_det;        // [n_importance] = linspace(0,1,n_importance)
+  float* z_out;              // [N, S + n_importance] merged, ascending depths of the fine pass
+  float* z_std;              // [N]
+  float* ring;               // scratch: mlp_tc_ring_bytes(n_classes) (rows of two tiles per CTA)
+};
+int64_t mlp_tc_ring_bytes(int n_classes);
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse = nullptr);
 struct TcBwdArgs {
   const void* packed;        // packed blob (composed views' matrix, fp32 sections)
   const float* flat;         // canonical flat parameters

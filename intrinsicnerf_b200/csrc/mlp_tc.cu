@@ -69,7 +69,9 @@ enum {
   B_ACC_FULL,                  // [2] accumulator (TMEM columns parity*256 ..) complete
   B_V_READY = B_ACC_FULL + 2,  // relu(views') written (256 threads)
   B_SMALL_FULL, B_SEM2_FULL, B_TAIL_DONE,
-  B_COUNT
+  B_RAW_READY,                 // [2] fused mode: the raw rows of a tile are in ring slot (it & 1) (8 epilogue warps)
+  B_RAW_FREE = B_RAW_READY + 2,  // [2] the back-end warp has consumed the slot
+  B_COUNT = B_RAW_FREE + 2
 };
 static_assert(B_COUNT <= 40, "barrier area");
 
@@ -83,6 +85,8 @@ struct Params {
   int out_ch, C, sem_rows;
   int bias_mma;                   // 1: accumulators are initialised with the bias by an MMA (default)
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
+  int fuse;                       // 1: composite (and resample) in-kernel, CTAs walk CONTIGUOUS tiles (whole rays per CTA)
+  FuseArgs f;
   int* dbg;                       // [16] per-launch abort / claim words (device, cleared before every launch)
   int* status;                    // pinned host record the next API call reads (common.cuh: status_raise)
   long long watchdog;             // cycles a blocking barrier wait may take before the launch is abandoned
@@ -298,6 +302,269 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&x);
 }
 
+// tile walked by this CTA in iteration `it`.  Fused mode: contiguous runs (n_iter is a multiple of the tiles per ray
+// group, so every ray is completed by the CTA that started it); otherwise interleaved.
+__device__ __forceinline__ int64_t tile_of(const Params& P, int it) {
+  return P.fuse ? (int64_t)blockIdx.x * P.n_iter + it : (int64_t)it * gridDim.x + blockIdx.x;
+}
+// depth of sample s of ray n: the caller's array, or (coarse pass of the fused renderer) generated here
+__device__ __forceinline__ float sample_depth(const Params& P, int64_t n, int s) {
+  if (P.a.z != nullptr) return __ldg(P.a.z + n * P.a.S + s);
+  const float* ray = P.a.rays + n * 11;
+  const bool jit = P.f.t_rand != nullptr;
+  return coarse_z_sample(__ldg(ray + 6), __ldg(ray + 7), P.f.t_vals, s, P.a.S, P.f.lindisp, jit, jit ? __ldg(P.f.t_rand + n * P.a.S + s) : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// ray back end (fused renderer): one warp turns the raw rows of the previous tile - handed over through a small
+// global ring that stays in L2 - into per-ray records while the tensor pipe works on the next tile.
+//   compositing  raw2outputs, run_nerf.py:359-412 / model_utils.py:39-116 - same arithmetic, in the same order, as
+//                k_raw2outputs (stages.cu): lane l owns samples l, l+32, ...; 32-sample segments with a running carry
+//   resampling   sample_pdf + sort(cat(z, z_samples)) + std, run_nerf.py:499-503,519 - the arithmetic of k_zmid,
+//                k_sample_pdf and k_merge_sorted with the 63-entry cdf, the bins and both sorted lists held in
+//                registers and searched with warp shuffles (no shared memory: the CTA has none left)
+// ------------------------------------------------------------------------------------------
+constexpr unsigned FULLMASK = 0xffffffffu;
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+struct RayState {             // per-lane state of the ray the back-end warp is compositing
+  float carry;                // prod (1 - alpha + 1e-10) over the segments already seen
+  float acc[12];              // rgb3 albedo3 shading residual3 depth acc, this lane's samples
+  float ex[4];                // semantic logits, channel lane + 32 i
+  float zc[2], wc[2];         // coarse pass with resampling (S == 64): depth / weight of samples lane, lane + 32
+};
+
+// searchsorted-style fetches from tables spread over the warp (entry k lives in lane k & 31 of register k >> 5)
+__device__ __forceinline__ float fetch2(float r0, float r1, int k) {
+  const float a = __shfl_sync(FULLMASK, r0, k & 31), b = __shfl_sync(FULLMASK, r1, k & 31);
+  return (k < 32) ? a : b;
+}
+__device__ __forceinline__ float fetch4(const float* r, int k) {
+  const float a = __shfl_sync(FULLMASK, r[0], k & 31), b = __shfl_sync(FULLMASK, r[1], k & 31);
+  const float c = __shfl_sync(FULLMASK, r[2], k & 31), d = __shfl_sync(FULLMASK, r[3], k & 31);
+  return (k < 64) ? ((k < 32) ? a : b) : ((k < 96) ? c : d);
+}
+
+// coarse ray finished: z_samples = sample_pdf(z_mid, weights[1:-1], 128, det) ; z_out = sort(cat(z, z_samples)) ; z_std
+__device__ __noinline__ void resample_ray(const Params& P, int64_t ray, const RayState& rs, int lane) {
+  // pdf weights i = 0..61 <-> coarse weights i+1 (k_sample_pdf with weights + 1, B = 63)
+  const float w_lo = __shfl_down_sync(FULLMASK, rs.wc[0], 1), w_32 = __shfl_sync(FULLMASK, rs.wc[1], 0);
+  const float pw0 = (lane == 31) ? w_32 : w_lo;                        // i = lane
+  const float pw1 = __shfl_down_sync(FULLMASK, rs.wc[1], 1);           // i = lane + 32 (valid for lane < 30)
+  float part = __fadd_rn(pw0, 1e-5f);
+  if (lane + 32 < 62) part += __fadd_rn(pw1, 1e-5f);
+  const float total = wsum(part);
+  // cdf: fp64 inclusive scan rounded per element (ATen's CPU cumsum), cdf[0] = 0
+  double p0 = (double)__fdiv_rn(__fadd_rn(pw0, 1e-5f), total);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const double q = __shfl_up_sync(FULLMASK, p0, o); if (lane >= o) p0 += q; }
+  const float cv0 = (float)(0.0 + p0);                                  // cdf[lane + 1]
+  const double carry = __shfl_sync(FULLMASK, p0, 31);
+  double p1 = (lane + 32 < 62) ? (double)__fdiv_rn(__fadd_rn(pw1, 1e-5f), total) : 0.0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const double q = __shfl_up_sync(FULLMASK, p1, o); if (lane >= o) p1 += q; }
+  const float cv1 = (float)(carry + p1);                                // cdf[lane + 33] (lane < 30)
+  // bins = z_mid[k] = .5 (z[k+1] + z[k]), k = 0..62
+  const float z_lo = __shfl_down_sync(FULLMASK, rs.zc[0], 1), z_32 = __shfl_sync(FULLMASK, rs.zc[1], 0);
+  const float zm0 = __fmul_rn(0.5f, __fadd_rn((lane == 31) ? z_32 : z_lo, rs.zc[0]));             // k = lane
+  const float zm1 = __fmul_rn(0.5f, __fadd_rn(__shfl_down_sync(FULLMASK, rs.zc[1], 1), rs.zc[1])); // k = lane + 32 (lane < 31)
+  auto cdf_at = [&](int k) { const float v = fetch2(cv0, cv1, (k - 1) & 63); return k == 0 ? 0.f : v; };
+  const int B = 63;
+  float smp[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float u = __ldg(P.f.u_det + lane + 32 * r);
+    int lo = 0, hi = B;
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {                                    // searchsorted(cdf, u, right=True)
+      const bool act = lo < hi;
+      const int mid = act ? (lo + hi) >> 1 : 0;
+      const float v = cdf_at(mid);
+      if (act) { if (v <= u) lo = mid + 1; else hi = mid; }
+    }
+    const int below = max(lo - 1, 0), above = min(lo, B - 1);
+    const float c0 = cdf_at(below), c1 = cdf_at(above);
+    const float b0 = fetch2(zm0, zm1, below), b1 = fetch2(zm0, zm1, above);
+    float denom = __fsub_rn(c1, c0);
+    if (denom < 1e-5f) denom = 1.f;
+    const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
+    smp[r] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+  }
+  // z_std = std(z_samples, unbiased=False)
+  if (P.f.z_std != nullptr) {
+    float sm = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sm += smp[r];
+    const float mean = wsum(sm) / 128.f;
+    float q = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { const float d = smp[r] - mean; q += d * d; }
+    q = wsum(q);
+    if (lane == 0) P.f.z_std[ray] = sqrtf(q / 128.f);
+  }
+  // merge: both lists ascending (depths by construction, samples because u and the cdf are) -> final position =
+  // own index + rank in the other list (ties: depths first), exactly k_merge_sorted's fast path
+  float* zo = P.f.z_out + ray * 192;
+  bool ok = true;
+  {
+    const float a_next0 = (lane == 31) ? z_32 : z_lo;
+    ok = ok && (rs.zc[0] <= a_next0);
+    if (lane < 31) ok = ok && (rs.zc[1] <= __shfl_down_sync(FULLMASK, rs.zc[1], 1)); else (void)__shfl_down_sync(FULLMASK, rs.zc[1], 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float nxt = __shfl_down_sync(FULLMASK, smp[r], 1);
+      const float wrap = (r < 3) ? __shfl_sync(FULLMASK, smp[r < 3 ? r + 1 : 3], 0) : 0.f;
+      if (lane < 31) ok = ok && (smp[r] <= nxt);
+      else if (r < 3) ok = ok && (smp[r] <= wrap);
+    }
+  }
+  if (__all_sync(FULLMASK, ok)) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {                                       // depths: index i, rank = #(samples < x)
+      const float x = rs.zc[g];
+      int lo = 0, hi = 128;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const bool act = lo < hi;
+        const int mid = act ? (lo + hi) >> 1 : 0;
+        const float v = fetch4(smp, mid);
+        if (act) { if (v < x) lo = mid + 1; else hi = mid; }
+      }
+      zo[lane + 32 * g + lo] = x;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                                       // samples: index j, rank = #(depths <= x)
+      const float x = smp[r];
+      int lo = 0, hi = 64;
+#pragma unroll
+      for (int it = 0; it < 7; ++it) {
+        const bool act = lo < hi;
+        const int mid = act ? (lo + hi) >> 1 : 0;
+        const float v = fetch2(rs.zc[0], rs.zc[1], mid);
+        if (act) { if (v <= x) lo = mid + 1; else hi = mid; }
+      }
+      zo[lane + 32 * r + lo] = x;
+    }
+    return;
+  }
+  // general case (NaN weights, non-monotone input): rank sort over all 192 values, NaNs last, ties by source index
+  float v[6] = {rs.zc[0], rs.zc[1], smp[0], smp[1], smp[2], smp[3]};
+  int rank[6] = {0, 0, 0, 0, 0, 0};
+  for (int sr = 0; sr < 6; ++sr) {
+    for (int sl = 0; sl < 32; ++sl) {
+      const float y = __shfl_sync(FULLMASK, v[sr], sl);
+      const int yi = sr * 32 + sl;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        const float x = v[e];
+        const int xi = e * 32 + lane;
+        const bool xn = x != x, yn = y != y;
+        const bool less = yn ? (xn && yi < xi) : (xn || y < x || (y == x && yi < xi));
+        rank[e] += less ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 6; ++e) zo[rank[e]] = v[e];
+}
+
+template <bool SAMPLER>
+__device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, int lane, RayState& rs) {
+  const int slot = it & 1;
+  const int64_t tile = tile_of(P, it);
+  sy.tile = (int)tile;
+  sy.wait(B_RAW_READY + slot);
+  const float* ring = P.f.ring + ((size_t)blockIdx.x * 2 + slot) * TILE_M * P.out_ch;   // plain (coherent) loads: written by this CTA
+  const int S = P.a.S;
+  for (int q = 0; q < 4; ++q) {
+    const int64_t m0 = tile * TILE_M + q * 32;
+    if (m0 >= P.a.M) break;                             // 32 | S | M: a segment is entirely inside or outside the batch
+    const int64_t ray = m0 / S;
+    const int s0 = (int)(m0 - ray * S), s = s0 + lane;
+    if (s0 == 0) {
+      rs.carry = 1.f;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rs.acc[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rs.ex[i] = 0.f;
+    }
+    const float* rp = P.a.rays + ray * 11;
+    const float dx = __ldg(rp + 3), dy = __ldg(rp + 4), dz = __ldg(rp + 5);
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float zs = sample_depth(P, ray, s);
+    float znext = __shfl_down_sync(FULLMASK, zs, 1);
+    if (lane == 31 && s + 1 < S) znext = sample_depth(P, ray, s + 1);
+    float dist = (s + 1 < S) ? __fsub_rn(znext, zs) : 1e10f;
+    dist = __fmul_rn(dist, dnorm);
+    const float* row = ring + (size_t)(q * 32 + lane) * P.out_ch;
+    float c[INRF_RAW_BASE];
+#pragma unroll
+    for (int i = 0; i < INRF_RAW_BASE; ++i) c[i] = row[i];
+    float sig = c[3];
+    if (P.f.noise != nullptr) sig = __fadd_rn(sig, __ldg(P.f.noise + ray * S + s));
+    const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(fmaxf(sig, 0.f), dist)));
+    float p = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(FULLMASK, p, o); if (lane >= o) p *= t; }
+    float excl = __shfl_up_sync(FULLMASK, p, 1);
+    if (lane == 0) excl = 1.f;
+    const float T = rs.carry * excl;
+    rs.carry *= __shfl_sync(FULLMASK, p, 31);
+    const float w = alpha * T;
+    rs.acc[0] += w * c[0]; rs.acc[1] += w * c[1]; rs.acc[2] += w * c[2];
+    rs.acc[3] += w * c[4]; rs.acc[4] += w * c[5]; rs.acc[5] += w * c[6];
+    rs.acc[6] += w * c[7];
+    rs.acc[7] += w * c[8]; rs.acc[8] += w * c[9]; rs.acc[9] += w * c[10];
+    rs.acc[10] += w * zs;
+    rs.acc[11] += w;
+    if (SAMPLER) {
+      if (s0 == 0) { rs.zc[0] = zs; rs.wc[0] = w; } else { rs.zc[1] = zs; rs.wc[1] = w; }
+    }
+    if (P.C > 0) {                                       // semantic logits: lanes stride over channels, weights by shuffle
+      for (int j = 0; j < 32; ++j) {
+        const float wj = __shfl_sync(FULLMASK, w, j);
+        const float* rj = ring + (size_t)(q * 32 + j) * P.out_ch + INRF_RAW_BASE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = lane + 32 * i;
+          if (e < P.C) rs.ex[i] += wj * rj[e];
+        }
+      }
+    }
+    if (s0 + 32 == S) {                                  // ray complete: record (k_raw2outputs' epilogue)
+      float a[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) a[i] = wsum(rs.acc[i]);
+      const float accw = a[11];
+      const float bg = P.f.white_bkgd ? (1.f - accw) : 0.f;
+      float* r = P.f.rec + ray * (INRF_REC_BASE + P.C);
+      if (lane == 0) {
+        r[0] = a[0] + bg; r[1] = a[1] + bg; r[2] = a[2] + bg;
+        const float depth = a[10];
+        const float ratio = depth / accw;                // 0/0 -> NaN, kept (appendix A8)
+        const float mx = (ratio != ratio) ? ratio : fmaxf(1e-10f, ratio);
+        r[3] = 1.f / mx;
+        r[4] = accw;
+        r[5] = a[3] + bg; r[6] = a[4] + bg; r[7] = a[5] + bg;
+        r[8] = a[6] + bg;
+        r[9] = a[7]; r[10] = a[8]; r[11] = a[9];          // residual: no background (A9)
+        r[12] = depth;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = lane + 32 * i;
+        if (e < P.C) r[INRF_REC_BASE + e] = P.f.white_bkgd ? rs.ex[i] + (1.f - accw) : rs.ex[i];   // model_utils.py:113-114
+      }
+      if (SAMPLER) resample_ray(P, ray, rs, lane);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(sy.addr(B_RAW_FREE + slot));
+}
+
 // swizzled byte offsets of the 8 16-byte units of this thread's row inside a chunk
 struct RowAddr {
   uint32_t unit[8];
@@ -305,11 +572,15 @@ struct RowAddr {
 
 template <bool STASH>
 __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
+  RayState rs;                                           // fused mode, warp 0 of the front end only
+  rs.carry = 1.f;
+  const bool backend = P.fuse && row < 32;
+  const bool sampler = P.f.n_importance > 0;
   RowAddr ra;
 #pragma unroll
   for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
   for (int it = 0; it < P.n_iter; ++it) {
-    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: rows clamp, stores are masked
+    const int64_t tile = tile_of(P, it);                        // may run past the end: rows clamp, stores are masked
     sy.tile = (int)tile;
     int64_t m = tile * TILE_M + row;
     if (m >= P.a.M) m = P.a.M - 1;
@@ -320,7 +591,7 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
       if (P.a.rays != nullptr) {
         const int64_t n = m / P.a.S;
         const float* ray = P.a.rays + n * 11;
-        const float zv = __ldg(P.a.z + m);
+        const float zv = sample_depth(P, n, (int)(m - n * P.a.S));
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           x[i] = __fadd_rn(__ldg(ray + i), __fmul_rn(__ldg(ray + 3 + i), zv));   // o + d z (run_nerf.py:488)
@@ -383,6 +654,9 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
     for (int u = 0; u < 4; ++u) st_shared_v4(smem_base + SM_DIR + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     fence_async_smem();
     warp_arrive(sy.addr(B_F_READY), row & 31);
+    if (backend && it > 0) {                     // composite (and resample) the previous tile while this one is in the pipe
+      if (sampler) ray_backend<true>(P, sy, it - 1, row, rs); else ray_backend<false>(P, sy, it - 1, row, rs);
+    }
     if (STASH && tile * TILE_M < P.a.M) {        // training: the same operand images go to the stash
       unsigned char* g = P.a.stash_img + (tile * IMG_STASH_SLOTS + IS_PE) * (int64_t)IMG_BYTES;
 #pragma unroll
@@ -391,6 +665,9 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
 #pragma unroll
       for (int u = 0; u < 4; ++u) st_global_v4(g + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     }
+  }
+  if (backend && P.n_iter > 0) {                 // the last tile of this CTA
+    if (sampler) ray_backend<true>(P, sy, P.n_iter - 1, row, rs); else ray_backend<false>(P, sy, P.n_iter - 1, row, rs);
   }
 }
 
@@ -696,11 +973,13 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 #pragma unroll
   for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
   for (int it = 0; it < P.n_iter; ++it) {
-    const int64_t tile = (int64_t)it * gridDim.x + blockIdx.x;   // may run past the end: stores are masked
+    const int64_t tile = tile_of(P, it);                        // may run past the end: stores are masked
     sy.tile = (int)tile;
     const int64_t m = tile * TILE_M + row;
-    const bool valid = m < P.a.M;
-    float* grow = P.a.raw + (valid ? m : 0) * P.out_ch;
+    const bool valid = P.fuse ? true : (m < P.a.M);             // fused: every row of the ring slot is written
+    // raw row destination: the caller's [M, out_ch] tensor, or (fused) this tile's slot of the L2-resident ring
+    float* grow = P.fuse ? P.f.ring + (((size_t)blockIdx.x * 2 + (it & 1)) * TILE_M + row) * P.out_ch
+                         : P.a.raw + (m < P.a.M ? m : 0) * P.out_ch;
     // training: image slot 0 of this tile in the stash (tiles past the end of the batch are not stored)
     unsigned char* simg = (STASH && tile * TILE_M < P.a.M) ? P.a.stash_img + tile * IMG_STASH_SLOTS * (int64_t)IMG_BYTES : nullptr;
 #define SLOT(s) (simg ? simg + (s) * IMG_BYTES : nullptr)
@@ -735,6 +1014,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
     if (sem) sy.wait(B_SEM2_FULL);
+    if (P.fuse) sy.wait(B_RAW_FREE + (it & 1));           // the back-end warp is done with this slot (two tiles ago)
     tc_fence_after();
     __syncwarp();
     asm volatile("bar.sync 1, 256;" ::: "memory");     // both sigma partials of every row are in smem
@@ -773,7 +1053,11 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     }
     // fp16 range: a stored activation at the saturation value 65504 (0x7bff) means the tile left the range the
     // tensor-core path can represent; report it (next API call returns INRF_ERANGE) instead of passing inf on
-    if (valid && !sy.dead && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {   // (an abandoned launch computes garbage)
+    if (P.fuse) {                                          // hand the rows to the back-end warp (release: CTA scope)
+      __threadfence_block();
+      warp_arrive(sy.addr(B_RAW_READY + (it & 1)), lane);
+    }
+    if (m < P.a.M && !sy.dead && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {   // (an abandoned launch computes garbage)
       if (atomicCAS(P.dbg + 8, 0, 1) == 0) status_raise(P.status, DST_F16_ACT, 0, (int)tile, blockIdx.x);
     }
     tc_fence_before();
@@ -815,6 +1099,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     mbar_init(sy.addr(B_V_READY), 8);
     mbar_init(sy.addr(B_SMALL_FULL), 1); mbar_init(sy.addr(B_SEM2_FULL), 1);
     mbar_init(sy.addr(B_TAIL_DONE), 8);
+    for (int k = 0; k < 2; ++k) { mbar_init(sy.addr(B_RAW_READY + k), 8); mbar_init(sy.addr(B_RAW_FREE + k), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
@@ -840,7 +1125,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   const uint32_t tmem = *tmem_slot;
 
   // "free"-type barriers start released: the first wait must pass on a fresh barrier
-  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (1ull << B_TAIL_DONE);
+  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (1ull << B_TAIL_DONE) | (3ull << B_RAW_FREE);
   sy.phase = released;
 
   if (P.prof != nullptr && blockIdx.x == 0) {
@@ -871,8 +1156,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
 
 }  // namespace tc
 
-int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
+int64_t mlp_tc_ring_bytes(int n_classes) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (int64_t)sms * 2 * tc::TILE_M * raw_channels(n_classes, 0) * (int64_t)sizeof(float);
+}
+
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   if (a.M == 0) return INRF_OK;
+  if (fuse != nullptr) {
+    if (a.rays == nullptr || a.S <= 0 || (a.S & 31) || a.endpoint || a.stash_img || fuse->rec == nullptr || fuse->ring == nullptr ||
+        (a.z == nullptr && fuse->t_vals == nullptr)) {
+      set_error("internal: fused tensor-core launch needs ray addressing, S %% 32 == 0, no endpoint feature, rec and ring");
+      return INRF_EINVAL;
+    }
+    if (fuse->n_importance > 0 && (a.S != 64 || fuse->n_importance != 128 || fuse->u_det == nullptr || fuse->z_out == nullptr)) {
+      set_error("internal: the in-kernel resampler implements 64 + 128 samples with deterministic u");
+      return INRF_EINVAL;
+    }
+  }
   NetLayout L;
   int rc = make_layout(a.variant, a.n_classes, &L);
   if (rc) return rc;
@@ -924,10 +1226,26 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st) {
   static const int cl_env = getenv("INRF_TC_CLUSTER") ? atoi(getenv("INRF_TC_CLUSTER")) : 2;
   const int64_t tiles = (a.M + tc::TILE_M - 1) / tc::TILE_M;
   int cl = (cl_env == 1) ? 1 : 2;     // default: 2-CTA clusters share every weight fetch (multicast)
-  if (tiles < cl) cl = 1;
-  int grid = (int)(tiles < sms ? tiles : sms);
-  grid = grid / cl * cl;                       // whole clusters only
-  P.n_iter = (int)((tiles + grid - 1) / grid);
+  P.fuse = fuse != nullptr ? 1 : 0;
+  if (fuse != nullptr) P.f = *fuse; else memset(&P.f, 0, sizeof(P.f));
+  int grid;
+  if (fuse == nullptr) {
+    if (tiles < cl) cl = 1;
+    grid = (int)(tiles < sms ? tiles : sms);
+    grid = grid / cl * cl;                       // whole clusters only
+    P.n_iter = (int)((tiles + grid - 1) / grid);
+  } else {
+    // contiguous runs of whole ray groups per CTA: lcm(S, 128) rows = unit_tiles tiles hold a whole number of rays, so
+    // the back-end warp's running transmittance never crosses a CTA boundary
+    int g = a.S, h = tc::TILE_M;
+    while (h) { const int t = g % h; g = h; h = t; }
+    const int unit_tiles = a.S / g;                                  // lcm(S,128)/128
+    const int64_t units = (tiles + unit_tiles - 1) / unit_tiles;
+    if (units < cl) cl = 1;
+    grid = (int)(units < sms ? units : sms);
+    grid = grid / cl * cl;
+    P.n_iter = (int)((units + grid - 1) / grid) * unit_tiles;
+  }
   void (*kern)(tc::Params) = a.stash_img ? (cl == 2 ? tc::k_mlp_tc<2, true> : tc::k_mlp_tc<1, true>)
                                          : (cl == 2 ? tc::k_mlp_tc<2, false> : tc::k_mlp_tc<1, false>);
   INRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));

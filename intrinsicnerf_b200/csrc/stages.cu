@@ -43,13 +43,6 @@ __global__ void k_embed(const float* __restrict__ x, int64_t M, int L, float sca
 // ---------------------------------------------------------------------------------
 // coarse sample depths (run_nerf.py:464-486; trainer.py:730-746)
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ float coarse_depth(float nearv, float farv, float t, int lindisp) {
-  if (!lindisp) return __fadd_rn(__fmul_rn(nearv, __fsub_rn(1.f, t)), __fmul_rn(farv, t));
-  float a = __fmul_rn(__fdiv_rn(1.f, nearv), __fsub_rn(1.f, t));
-  float b = __fmul_rn(__fdiv_rn(1.f, farv), t);
-  return __fdiv_rn(1.f, __fadd_rn(a, b));
-}
-
 __global__ void k_coarse_z(const float* __restrict__ rays, const float* __restrict__ t_vals,
                            const float* __restrict__ t_rand, int64_t N, int S, int lindisp, float* __restrict__ z) {
   int64_t total = N * S;
@@ -57,15 +50,7 @@ __global__ void k_coarse_z(const float* __restrict__ rays, const float* __restri
     int64_t n = i / S;
     int s = (int)(i - n * S);
     float nearv = rays[n * 11 + 6], farv = rays[n * 11 + 7];
-    float zc = coarse_depth(nearv, farv, t_vals[s], lindisp);
-    if (t_rand != nullptr) {
-      float zl = s > 0 ? coarse_depth(nearv, farv, t_vals[s - 1], lindisp) : zc;
-      float zr = s < S - 1 ? coarse_depth(nearv, farv, t_vals[s + 1], lindisp) : zc;
-      float lower = s > 0 ? __fmul_rn(0.5f, __fadd_rn(zc, zl)) : zc;
-      float upper = s < S - 1 ? __fmul_rn(0.5f, __fadd_rn(zr, zc)) : zc;
-      zc = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[i]));
-    }
-    z[i] = zc;
+    z[i] = coarse_z_sample(nearv, farv, t_vals, s, S, lindisp, t_rand != nullptr, t_rand != nullptr ? t_rand[i] : 0.f);
   }
 }
 

@@ -119,11 +119,18 @@ def probe_threads(rn, kw, H, W):
     return best, out
 
 
-def row_subprocess(row, n_rays):
-    """Single-thread rows: OMP/MKL = 1 exported before the interpreter (and torch) start."""
-    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
-    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--row", row, "--rays", str(n_rays)], env=env, cwd=ROOT,
-                         capture_output=True, text=True, timeout=900)
+def row_subprocess(row, n_rays, steps=1, warmup=0):
+    """Every row runs in its own interpreter: CUDA is hidden (CUDA_VISIBLE_DEVICES="") so that the reference's
+    `device = "cuda" if available` (run_nerf.py:27) picks the CPU on the GPU box too, and the single-thread rows get
+    OMP/MKL = 1 exported before torch starts (what run_nerf.py:2-3 does when it is the entry point)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    if row != "all_cores":
+        env.update(OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    else:
+        env.pop("OMP_NUM_THREADS", None)
+        env.pop("MKL_NUM_THREADS", None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--row", row, "--rays", str(n_rays), "--steps", str(steps),
+                          "--warmup", str(warmup)], env=env, cwd=ROOT, capture_output=True, text=True, timeout=1800)
     for line in out.stdout.splitlines()[::-1]:
         if line.startswith("{"):
             return json.loads(line)
@@ -132,10 +139,29 @@ def row_subprocess(row, n_rays):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--row", required=True, choices=["config1", "as_shipped"])
+    ap.add_argument("--row", required=True, choices=["config1", "as_shipped", "all_cores"])
     ap.add_argument("--rays", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=0)
     a = ap.parse_args()
+    import contextlib
     import torch
+    if a.row == "all_cores":
+        # the headline reference row: all host cores (best thread count by probe), `steps` renders of the ray sample
+        with contextlib.redirect_stdout(sys.stderr):
+            rn, kw = build(128)
+            threads, table = probe_threads(rn, kw, 800, 800)
+            per_step = []
+            for i in range(a.warmup + a.steps):
+                dt, n = time_sample(rn, kw, 800, 800, a.rays)
+                if i >= a.warmup:
+                    per_step.append(n / dt)
+        from oracle import refshim
+        print(json.dumps({"row": a.row, "rays_per_s": sum(per_step) / len(per_step), "per_step": per_step, "rays": n, "threads": threads,
+                          "host_cpus": os.cpu_count(), "thread_probe_rays_per_s": {str(k): round(v, 1) for k, v in table.items()},
+                          "what": f"render(800, 800, K, rays={n} of the view), 64 + 128", "torch": torch.__version__,
+                          "reference_root": refshim.REF_ROOT, "cuda_visible": torch.cuda.is_available()}))
+        return
     torch.set_num_threads(1)
     if a.row == "config1":
         rn, kw = build(0)

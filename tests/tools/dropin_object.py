@@ -98,6 +98,7 @@ with tempfile.TemporaryDirectory() as base:
     ok_ckpt = False
     if ckpts:
         ck = torch.load(os.path.join(exp, ckpts[-1]), map_location="cpu")
+        rh.NeRF = RefNeRF          # the reference class resolves its own name (super(NeRF, self)) in run_nerf_helpers' globals
         ref_net = RefNeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
         ref_net.load_state_dict(ck["network_fine_state_dict"], strict=True)
         import intrinsicnerf_b200 as inrf

@@ -65,6 +65,9 @@ with tempfile.TemporaryDirectory() as base:
     t.train_Ts = t.test_Ts = Ts
     # ---------------------------------------------------------------------------------------------------------------------
     t.create_ssr()                                 # dropin: our Semantic_NeRF modules + Adam, the reference's attribute names
+    with torch.no_grad():                          # start from an opaque field (default init renders acc ~ 0.002: nothing to learn from in 24 steps)
+        for net in (t.ssr_net_coarse, t.ssr_net_fine):
+            net.alpha_linear.bias += 1.0
     t.init_rays()                                  # reference code; its create_rays name is bound to ours
     losses = []
     import builtins
@@ -94,6 +97,7 @@ with tempfile.TemporaryDirectory() as base:
     ok_ckpt = False
     if ckpts:
         ck = torch.load(os.path.join(ck_dir, ckpts[-1]), map_location="cpu")
+        sn.Semantic_NeRF = RefSemanticNeRF     # the reference class resolves its own name (super(Semantic_NeRF, self)) in its module
         ref_net = RefSemanticNeRF(enable_semantic=True, num_semantic_classes=C, D=8, W=256, input_ch=63, output_ch=5, skips=[4],
                                   input_ch_views=27, use_viewdirs=True)
         ref_net.load_state_dict(ck["network_fine_state_dict"], strict=True)
