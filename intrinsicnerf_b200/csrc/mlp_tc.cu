@@ -70,7 +70,7 @@ enum {
   B_V_READY = B_ACC_FULL + 2,  // relu(views') written (256 threads)
   B_SMALL_FULL, B_SEM2_FULL, B_TAIL_DONE,
   B_RAW_READY,                 // [2] fused mode: the raw rows of a tile are in ring slot (it & 1) (8 epilogue warps)
-  B_RAW_FREE = B_RAW_READY + 2,  // [2] the back-end warp has consumed the slot
+  B_RAW_FREE = B_RAW_READY + 2,  // [2] both back-end warps have consumed the slot
   B_COUNT = B_RAW_FREE + 2
 };
 static_assert(B_COUNT <= 40, "barrier area");
@@ -471,8 +471,10 @@ __device__ __noinline__ void resample_ray(const Params& P, int64_t ray, const Ra
   for (int e = 0; e < 6; ++e) zo[rank[e]] = v[e];
 }
 
+// `which` = 0 / 1: front-end warps 0 and 2 share the work by ray parity (a ray is always handled by one warp, so its
+// running transmittance stays in that warp's registers)
 template <bool SAMPLER>
-__device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, int lane, RayState& rs) {
+__device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, int lane, RayState& rs, int which) {
   const int slot = it & 1;
   const int64_t tile = tile_of(P, it);
   sy.tile = (int)tile;
@@ -483,6 +485,7 @@ __device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, i
     const int64_t m0 = tile * TILE_M + q * 32;
     if (m0 >= P.a.M) break;                             // 32 | S | M: a segment is entirely inside or outside the batch
     const int64_t ray = m0 / S;
+    if ((int)(ray & 1) != which) continue;
     const int s0 = (int)(m0 - ray * S), s = s0 + lane;
     if (s0 == 0) {
       rs.carry = 1.f;
@@ -572,9 +575,11 @@ struct RowAddr {
 
 template <bool STASH>
 __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
-  RayState rs;                                           // fused mode, warp 0 of the front end only
+  RayState rs;                                           // fused mode, warps 0 and 2 of the front end only
   rs.carry = 1.f;
-  const bool backend = P.fuse && row < 32;
+  const bool backend = P.fuse && (row < 32 || (row >= 64 && row < 96));
+  const int which = row >= 64 ? 1 : 0;
+  const int blane = row & 31;
   const bool sampler = P.f.n_importance > 0;
   RowAddr ra;
 #pragma unroll
@@ -655,7 +660,7 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
     fence_async_smem();
     warp_arrive(sy.addr(B_F_READY), row & 31);
     if (backend && it > 0) {                     // composite (and resample) the previous tile while this one is in the pipe
-      if (sampler) ray_backend<true>(P, sy, it - 1, row, rs); else ray_backend<false>(P, sy, it - 1, row, rs);
+      if (sampler) ray_backend<true>(P, sy, it - 1, blane, rs, which); else ray_backend<false>(P, sy, it - 1, blane, rs, which);
     }
     if (STASH && tile * TILE_M < P.a.M) {        // training: the same operand images go to the stash
       unsigned char* g = P.a.stash_img + (tile * IMG_STASH_SLOTS + IS_PE) * (int64_t)IMG_BYTES;
@@ -667,7 +672,7 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
     }
   }
   if (backend && P.n_iter > 0) {                 // the last tile of this CTA
-    if (sampler) ray_backend<true>(P, sy, P.n_iter - 1, row, rs); else ray_backend<false>(P, sy, P.n_iter - 1, row, rs);
+    if (sampler) ray_backend<true>(P, sy, P.n_iter - 1, blane, rs, which); else ray_backend<false>(P, sy, P.n_iter - 1, blane, rs, which);
   }
 }
 
@@ -1053,16 +1058,18 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     }
     // fp16 range: a stored activation at the saturation value 65504 (0x7bff) means the tile left the range the
     // tensor-core path can represent; report it (next API call returns INRF_ERANGE) instead of passing inf on
-    if (P.fuse) {                                          // hand the rows to the back-end warp (release: CTA scope)
-      __threadfence_block();
-      warp_arrive(sy.addr(B_RAW_READY + (it & 1)), lane);
-    }
     if (m < P.a.M && !sy.dead && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {   // (an abandoned launch computes garbage)
       if (atomicCAS(P.dbg + 8, 0, 1) == 0) status_raise(P.status, DST_F16_ACT, 0, (int)tile, blockIdx.x);
     }
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");     // s_sig may be rewritten by the next tile
     warp_arrive(sy.addr(B_TAIL_DONE), lane);
+    if (P.fuse) {
+      // hand the rows to the back-end warps AFTER releasing the tensor pipe: the fence waits for the ring stores to
+      // be visible, which would otherwise sit on the tile-to-tile critical path
+      __threadfence_block();
+      warp_arrive(sy.addr(B_RAW_READY + (it & 1)), lane);
+    }
   }
 }
 
@@ -1099,7 +1106,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     mbar_init(sy.addr(B_V_READY), 8);
     mbar_init(sy.addr(B_SMALL_FULL), 1); mbar_init(sy.addr(B_SEM2_FULL), 1);
     mbar_init(sy.addr(B_TAIL_DONE), 8);
-    for (int k = 0; k < 2; ++k) { mbar_init(sy.addr(B_RAW_READY + k), 8); mbar_init(sy.addr(B_RAW_FREE + k), 1); }
+    for (int k = 0; k < 2; ++k) { mbar_init(sy.addr(B_RAW_READY + k), 8); mbar_init(sy.addr(B_RAW_FREE + k), 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {

@@ -230,7 +230,10 @@ class SSRRenderer:
         import numpy as np
         from .object_level import imwrite
         try:
-            from imgviz import depth2rgb
+            import imgviz
+            if getattr(imgviz, "__version__", None) is None:       # a stubbed module (test harnesses) is not an install
+                raise ImportError("imgviz stub")
+            depth2rgb = imgviz.depth2rgb
         except ImportError:
             depth2rgb = None
         H, W = int(self.H_scaled), int(self.W_scaled)

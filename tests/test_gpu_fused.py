@@ -27,6 +27,7 @@ def _same(a, b):
 
 def _both(rays, pc, pf, **kw):
     from intrinsicnerf_b200 import ops
+    torch.cuda.synchronize()
     n0 = ops.launch_count()
     fused = ops.render_chunk(rays, pc, pf, want_z=True, **kw)
     n_fused = ops.launch_count() - n0
@@ -81,9 +82,10 @@ def test_coarse_only_and_unusual_sample_counts(dev):
     from intrinsicnerf_b200 import ops
     coarse, fine, _, _ = build_nets("object")
     rays = orc.blender_rays(32, 32)[:500].contiguous().to(dev)
+    pc = coarse.packed()                                  # (packs on first use: 4 launches that are not part of a render)
     for S in (64, 32, 96, 128):
         n0 = ops.launch_count()
-        f = ops.render_chunk(rays, coarse.packed(), None, white_bkgd=True, n_samples=S, n_importance=0)
+        f = ops.render_chunk(rays, pc, None, white_bkgd=True, n_samples=S, n_importance=0)
         assert ops.launch_count() - n0 == 1, S
         raw = ops.mlp_forward_rays(coarse.packed(), 0, 0, rays, ops.coarse_z(rays, S))
         rec, _ = ops.raw2outputs_rec(raw, ops.coarse_z(rays, S), rays[:, 3:6].contiguous(), None, True)

@@ -19,8 +19,21 @@ def rel_err(a, b, floor=1e-3):
     return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
 
 
-def build_nets(variant="object", n_classes=0, opaque=True, device="cuda"):
-    """Our modules with the reference's seeded init (+ optional 'opaque' tweak), and the same
+def apply_regime(net, regime):
+    """Weight regimes of SURVEY section 7-1 (same as tests/golden/make_golden.py:apply_regime)."""
+    with torch.no_grad():
+        if regime == "opaque":
+            net.alpha_linear.bias += 1.0
+            net.pts_linears[7].weight *= 3.0
+        elif regime == "trained_like":
+            net.pts_linears[7].weight *= 6.0
+            net.alpha_linear.weight *= 30.0
+        elif regime != "default":
+            raise ValueError(regime)
+
+
+def build_nets(variant="object", n_classes=0, opaque=True, device="cuda", regime=None):
+    """Our modules with the reference's seeded init (+ optional 'opaque' tweak / a named weight regime), and the same
     weights as oracle parameter dicts on the CPU."""
     import intrinsicnerf_b200 as inrf
     torch.manual_seed(SEED)
@@ -30,11 +43,10 @@ def build_nets(variant="object", n_classes=0, opaque=True, device="cuda"):
         mk = lambda: inrf.Semantic_NeRF(n_classes > 0, n_classes, D=8, W=256, input_ch=63, output_ch=5, skips=[4],  # noqa: E731
                                         input_ch_views=27, use_viewdirs=True)
     coarse, fine = mk(), mk()
-    if opaque:
-        with torch.no_grad():
-            for net in (coarse, fine):
-                net.alpha_linear.bias += 1.0
-                net.pts_linears[7].weight *= 3.0
+    if regime is None:
+        regime = "opaque" if opaque else "default"
+    for net in (coarse, fine):
+        apply_regime(net, regime)
     pc = {k: v.detach().clone() for k, v in coarse.state_dict().items()}
     pf = {k: v.detach().clone() for k, v in fine.state_dict().items()}
     return coarse.to(device), fine.to(device), pc, pf
