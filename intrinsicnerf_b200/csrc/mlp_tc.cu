@@ -796,17 +796,22 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
   I.probe(-1);                          // first fill of the first tile (layer-0 bias)
   for (int it = 0; it < P.n_iter; ++it) {
     sy.tile = it;
-    sy.wait(B_TAIL_DONE);               // previous tile's accumulators drained
+    // The two 256-column accumulators swap roles every tile: A0 (even layers, views', the narrow heads) is the
+    // accumulator the PREVIOUS tile used for its odd layers and albedo1|shading1, which is fully drained as soon as
+    // that tile's albedo2/shading2 MMAs have been issued - so layer 0 of this tile runs while the previous tile's
+    // epilogue warps are still reading the narrow heads out of its own A0 and writing the rows (the tile tail).
+    const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;
     sy.wait(B_F_READY);                 // gamma(x), gamma(d) of this tile
-    // ---- trunk layer 0: K = 64 (gamma(x)) -> accumulator 0 ---------------------------------------
+    // ---- trunk layer 0: K = 64 (gamma(x)) -> accumulator A0 --------------------------------------
     {
-      const bool init = I.bias(256, 0, -1);
-      I.fill_mma<4>(PE, 256, 0, !init, -1);
+      const bool init = I.bias(256, A0, -1);
+      I.fill_mma<4>(PE, 256, A0, !init, -1);
       I.commit(B_ACC_FULL + 0);
     }
+    sy.wait(B_TAIL_DONE);               // previous tile's narrow-head / logit columns (in this tile's A1) have been read
     // ---- trunk layers 1..7 ------------------------------------------------------------------------
     for (int l = 1; l < 8; ++l) {
-      const uint32_t acc = (l & 1) * 256;
+      const uint32_t acc = (l & 1) ? A1 : A0;
       bool first = !I.bias(256, acc, l == 5 ? -1 : B_A_READY + 0);
       if (l == 5) {                      // skip connection: [gamma(x), h] -> K = 64 + 256
         I.fill_mma<4>(PE, 256, acc, first, B_A_READY + 0);
@@ -818,46 +823,47 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
       }
       I.commit(B_ACC_FULL + (l & 1));
     }
-    // ---- views' [| sem1] on the trunk output -> accumulator 0 (drained since layer 6) ---------------
+    // ---- views' [| sem1] on the trunk output -> accumulator A0 (drained since layer 6) --------------
     {
-      bool first = !I.bias(nv, 0, B_A_READY + 0);
-      for (int c = 0; c < 4; ++c) {       // all four waits also prove layer 7's accumulator (1) is drained
-        I.fill_mma<4>(H + c * CHUNK, nv, 0, first, c < 3 ? B_A_READY + c + 1 : -1);
+      bool first = !I.bias(nv, A0, B_A_READY + 0);
+      for (int c = 0; c < 4; ++c) {       // all four waits also prove layer 7's accumulator (A1) is drained
+        I.fill_mma<4>(H + c * CHUNK, nv, A0, first, c < 3 ? B_A_READY + c + 1 : -1);
         first = false;
       }
-      I.fill_mma<2>(DIR, 128, 0, false, -1);
+      I.fill_mma<2>(DIR, 128, A0, false, -1);
       I.commit(B_ACC_FULL + 0);
     }
-    // ---- albedo1 | shading1 on the trunk output -> accumulator 1 ------------------------------------
+    // ---- albedo1 | shading1 on the trunk output -> accumulator A1 -----------------------------------
     {
-      bool first = !I.bias(256, 256, -1);
+      bool first = !I.bias(256, A1, -1);
       for (int c = 0; c < 4; ++c) {
-        I.fill_mma<4>(H + c * CHUNK, 256, 256, first, -1);
+        I.fill_mma<4>(H + c * CHUNK, 256, A1, first, -1);
         first = false;
       }
       I.commit(B_H_FREE);                // last reader of the trunk output: relu(albedo1|shading1) may land in H
       I.commit(B_ACC_FULL + 1);
     }
-    // ---- residual head on relu(views'): 16 x 128 -> accumulator 0 cols [0,16) ------------------------
+    // ---- residual head on relu(views'): 16 x 128 -> accumulator A0 cols [0,16) -----------------------
     sy.wait(B_V_READY);
     {
       I.acquire();
       const uint32_t b_addr = I.slot_addr();
-      I.mma<4>(V, b_addr, 16, 0, true);
-      I.mma<4>(V + CHUNK, b_addr + 2048, 16, 0, false);
+      I.mma<4>(V, b_addr, 16, A0, true);
+      I.mma<4>(V + CHUNK, b_addr + 2048, 16, A0, false);
       I.release();
       I.advance();
       I.probe(-1);
     }
     I.commit(B_F_FREE);                  // PE | DIR | V region may be rewritten by the front end
-    // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> accumulator 0 cols [16,32) ------
+    // ---- albedo2 / shading2 on relu(albedo1 | shading1): 16 x 256 -> accumulator A0 cols [16,32) -----
+    //      (its four A_READY waits also prove that A1 is drained: the next tile's layer 0 may overwrite it)
     {
       I.acquire();
       const uint32_t b_addr = I.slot_addr();
       for (int c = 0; c < 4; ++c) {
         sy.wait(B_A_READY + c);
         tc_fence_after();
-        I.mma<4>(H + c * CHUNK, b_addr + 2048 * c, 16, 16, c == 0);
+        I.mma<4>(H + c * CHUNK, b_addr + 2048 * c, 16, A0 + 16, c == 0);
       }
       I.release();
       I.advance();
@@ -865,14 +871,15 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
     }
     if (sem) I.commit(B_H_FREE);         // relu(sem1) may overwrite H chunks 0,1
     I.commit(B_SMALL_FULL);
-    // ---- semantic logits on relu(sem1): C x 128 -> accumulator 1 cols [0, sem_rows) -------------------
+    // ---- semantic logits on relu(sem1): C x 128 -> accumulator A0 cols [32, 32 + sem_rows) (the views' | sem1
+    //      columns there were drained by the V / sem1 epilogues) ---------------------------------------------
     if (sem) {
       I.acquire();
       const uint32_t b_addr = I.slot_addr();
       for (int c = 0; c < 2; ++c) {
         sy.wait(B_A_READY + c);
         tc_fence_after();
-        I.mma<4>(H + c * CHUNK, b_addr + (uint32_t)(P.sem_rows * 128 * c), P.sem_rows, 256, c == 0);
+        I.mma<4>(H + c * CHUNK, b_addr + (uint32_t)(P.sem_rows * 128 * c), P.sem_rows, A0 + 32, c == 0);
       }
       I.release();
       I.advance();
@@ -991,11 +998,12 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
     float sig = 0.f;
     uint32_t amax = 0u;                                  // running max of every fp16 activation this thread stored
+    const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;   // accumulator roles swap every tile (see issuer)
     for (int l = 0; l < 8; ++l) {
       sy.wait(B_ACC_FULL + (l & 1));
       tc_fence_after();
-      if (l == 7) epi_layer<1>(add_bias, lane_addr + 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28), amax);
-      else epi_layer<0>(add_bias, lane_addr + (l & 1) * 256, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l), amax);
+      if (l == 7) epi_layer<1>(add_bias, lane_addr + A1, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28), amax);
+      else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l), amax);
     }
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
@@ -1003,18 +1011,18 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     sy.wait(B_ACC_FULL + 0);
       tc_fence_after();
     if (P.a.endpoint)
-      epi_layer<2>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
+      epi_layer<2>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
                    valid ? grow + INRF_RAW_BASE + P.C : nullptr, SLOT(IS_V), amax);
     else
-      epi_layer<0>(add_bias, lane_addr + 0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V), amax);
+      epi_layer<0>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V), amax);
     warp_arrive(sy.addr(B_V_READY), lane);
     // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ---------------------------------
     sy.wait(B_ACC_FULL + 1);
       tc_fence_after();
-    epi_layer<0>(add_bias, lane_addr + 256, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS), amax);
+    epi_layer<0>(add_bias, lane_addr + A1, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS), amax);
     // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
     if (sem)
-      epi_layer<0>(add_bias, lane_addr + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1), amax);
+      epi_layer<0>(add_bias, lane_addr + A0 + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1), amax);
 #undef SLOT
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
@@ -1025,7 +1033,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     asm volatile("bar.sync 1, 256;" ::: "memory");     // both sigma partials of every row are in smem
     if (jj == 0) {
       uint32_t v[32];
-      tmem_ld32(lane_addr + 0, v);
+      tmem_ld32(lane_addr + A0, v);
       tmem_ld_wait();
       if (valid) {
         float res[3], alb[3], sh;
@@ -1047,7 +1055,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     } else if (sem) {
       for (int c0 = 0; c0 < P.C; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(lane_addr + 256 + c0, v);
+        tmem_ld32(lane_addr + A0 + 32 + c0, v);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll

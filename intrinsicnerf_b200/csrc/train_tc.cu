@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256) k_dw_reduce(const __grid_constant__ DwPar
   for (int ri = 0; ri < I.n_rect; ++ri) {
     const DwRect R = I.r[ri];
     const int total = R.nrows * R.ncols;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < total; e += blockDim.x * gridDim.y) {   // grid.y slices every rectangle
       const int r = e / R.ncols, c = e - r * R.ncols;
       const float* p = part + (int64_t)(R.row0 + r) * DW_PART_LD + R.col0 + c;
       float acc = 0.f;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) k_dw_reduce(const __grid_constant__ DwPar
       R.dst[(int64_t)r * R.ld + c] += acc * inv;
     }
     if (R.bias != nullptr) {
-      for (int r = threadIdx.x; r < R.nrows; r += blockDim.x) {
+      for (int r = blockIdx.y * blockDim.x + threadIdx.x; r < R.nrows; r += blockDim.x * gridDim.y) {
         const float* p = part + (int64_t)(R.row0 + r) * DW_PART_LD + 256;
         float acc = 0.f;
         for (int sp = 0; sp < P.n_splits; ++sp) acc += p[sp * sstride];
@@ -646,7 +646,7 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   INRF_CUDA(cudaFuncSetAttribute(k_gemm_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
   k_gemm_dw<<<dim3(D.n_items, splits), DW_THREADS, DW_SMEM, st>>>(D);
   INRF_LAUNCH_CHECK();
-  k_dw_reduce<<<D.n_items, 256, 0, st>>>(D);
+  k_dw_reduce<<<dim3(D.n_items, 16), 256, 0, st>>>(D);      // (item, slice): ~450 CTAs instead of ~28
   INRF_LAUNCH_CHECK();
   k_unfold_comp<<<16 + 256, 256, 0, st>>>(a.flat, L, dcomp, gf);
   INRF_LAUNCH_CHECK();

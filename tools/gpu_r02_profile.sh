@@ -1,0 +1,12 @@
+#!/bin/bash
+# round-2 ncu evidence: launch list of a one-view bench step, full capture of a FUSED fine-pass k_mlp_tc launch, training launch list
+mkdir -p gpurun_out
+rm -f gpurun_out/*.ncu-rep gpurun_out/launches*.csv
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+  python bench.py --views 1 --steps 1 --warmup 3 --no-cpu-baseline --no-config5 > gpurun_out/bench_under_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mlp_tc -s 3 -c 1 -o gpurun_out/prof_mlp_tc_fused_fine \
+  python tests/tools/profile_target.py 40000 tc > gpurun_out/prof_target.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_train.csv \
+  python tests/tools/train_target.py > gpurun_out/train_under_ncu.log 2>&1
+INRF_TC_PAIR=1 timeout 300 python tests/tools/tc_perf.py 160000 > gpurun_out/tc_perf_pair.log 2>&1
+ls -la gpurun_out | head -40; grep TC_PERF gpurun_out/tc_perf_pair.log
