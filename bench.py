@@ -273,11 +273,44 @@ def train_step_record(dev, dist, rank, world, steps=20, warmup=5, n_rays=1024, C
     launches = (ops.launch_count() - l0) / (steps + warmup)
     torch.cuda.synchronize()
     ops.poll_status()
+    # the same step replayed from a CUDA graph (one rank: no collective inside): what is left when the ~150 launches of
+    # the step (ours + PyTorch's loss / Adam kernels) cost no host time
+    ms_graph = None
+    if dist is None:
+        try:
+            opt_g = torch.optim.Adam([p for m in nets for p in m.parameters()], lr=5e-4, capturable=True)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+
+            def gstep():
+                opt_g.zero_grad(set_to_none=False)
+                out = t.render_rays(rays)
+                loss = ((out["rgb_fine"] - gt) ** 2).mean() + ((out["rgb_coarse"] - gt) ** 2).mean() \
+                    + 0.04 * (ce(out["sem_logits_fine"], labels) + ce(out["sem_logits_coarse"], labels))
+                for sfx in ("fine", "coarse"):
+                    terms = ops.intrinsic_losses(None, out["albedo_" + sfx], out["shading_" + sfx], out["residual_" + sfx], gt, labels.float(), None, "ssr")
+                    loss = loss + terms[1:7].sum() * 0.01
+                loss.backward()
+                opt_g.step()
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    gstep()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gstep()
+            ms_graph = tm.timed(graph.replay, steps, warmup) / steps
+            torch.cuda.synchronize()
+            ops.poll_status()
+        except Exception as e:                                 # capture is an optimisation: report why it was not possible
+            ms_graph = f"capture failed: {type(e).__name__}: {e}"[:200]
     flop = n_rays * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * 2 * (692224 + 128 * C) * 3          # fwd + dX + dW
     per = ms / steps
     pk = peaks()
     n_grad = sum(p.numel() for m_ in nets for p in m_.parameters())
     return {"workload": "replica_room0_train_step_1024rays_64+128_C28", "n_gpus": world, "ms_per_step": per,
+            "ms_per_step_cuda_graph": ms_graph,
             "rays_per_s": n_rays / (per * 1e-3), "rays_per_step": n_rays, "rays_per_rank": b - a,
             "algorithmic_tflops": flop / (per * 1e-3) / 1e12,
             "frac_of_sustained_bf16": flop / (per * 1e-3) / 1e12 / ((pk["bf16_sustained"] or pk["bf16_tflops"]) * world),

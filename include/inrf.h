@@ -198,6 +198,25 @@ int inrf_merge_sorted(const float* z_a, const float* z_b, int64_t N, int Sa, int
 int inrf_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S,
                   int lindisp, float* z, void* stream);
 
+/* Training-mode draws generated INSIDE the stage kernels.  The reference draws
+ * t_rand = torch.rand(N,Sc) (run_nerf.py:478), u = torch.rand(N,Sf) (run_nerf_helpers.py:414) and
+ * noise = torch.randn(N,S) * raw_noise_std (run_nerf.py:387) with three generator launches per pass; here a draw is
+ * Philox4x32-10(key = seed, counter = (element index, tensor id)) evaluated where it is consumed: U[0,1) with 24 bits
+ * for t_rand / u, Box-Muller N(0,1) * noise_std for the sigma noise.  The same (seed, element) always gives the same
+ * number, so inrf_raw2outputs_bwd_rng regenerates the forward's noise.  `fine_pass` selects the noise tensor
+ * (coarse / fine pass of one step use different streams of the same seed).  Everything else as the non-_rng entries. */
+int inrf_coarse_z_rng(const float* rays, const float* t_vals, uint64_t seed, int64_t N, int S, int lindisp, float* z,
+                      void* stream);
+int inrf_sample_pdf_rng(const float* bins, const float* weights, int ld_w, uint64_t seed, int64_t N, int B,
+                        int n_samples, float* samples, void* stream);
+int inrf_raw2outputs_rng(const float* raw, const float* z, const float* rays_d, int ld_rays_d, float noise_std,
+                         uint64_t seed, int fine_pass, int64_t N, int S, int n_classes, int endpoint_feat,
+                         int white_bkgd, float* rec, float* weights, void* stream);
+int inrf_raw2outputs_bwd_rng(const float* raw, const float* z, const float* rays_d, int ld_rays_d, float noise_std,
+                             uint64_t seed, int fine_pass, int64_t N, int S, int n_classes, int endpoint_feat,
+                             int white_bkgd, const float* grad_rec, const float* grad_weights, float* grad_raw,
+                             void* stream);
+
 /* Pinhole ray generation + packing of render() for a full image (run_nerf_helpers.py:359-368
  * get_rays, run_nerf.py:100-128 with use_viewdirs=True, ndc=False): pixel (i=column, j=row) ->
  * dir = ((i-cx)/fx, -(j-cy)/fy, -1), d = R dir, o = t, viewdir = d/|d|.
@@ -252,6 +271,28 @@ int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, con
                     const float* noise_fine, float* rec_coarse, float* rec_fine, float* z_std,
                     float* raw_coarse, float* raw_fine, float* z_fine, float* weights_fine,
                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The same renderer for a whole frame (or a pixel range of it) WITHOUT a ray table: render() called with c2w
+ * (run_nerf.py:100-103 get_rays, :113-128 packing) and SSRTrainer.render_path over create_rays' rows generate the
+ * rays of a frame from (H, W, K, c2w); here the kernels do that per pixel - ray n of the call is pixel pix0 + n
+ * (row-major), bit-identical to inrf_get_rays / inrf_rays_from_pixels - so the 44 B/ray table is never written or
+ * read.  Deterministic rendering only (no jitter / noise / random u: the frame drivers render with perturb = 0), and
+ * only configurations the fused kernel covers (INRF_PREC_TC, sample counts multiples of 32, 64 + 128 when there is a
+ * fine pass, no endpoint feature); anything else returns INRF_EUNSUPPORTED and the caller uses inrf_get_rays +
+ * inrf_render_fwd.  Outputs as inrf_render_fwd.                                                                  */
+typedef struct InrfCamera {
+  int32_t H, W;
+  float fx, fy, cx, cy;
+  float c2w[12];           /* row-major 3x4 camera-to-world */
+  float near_, far_;
+  int32_t convention;      /* INRF_CAM_OPENGL / INRF_CAM_OPENCV */
+  int32_t euclidean;       /* depth_type "euclidean": unit camera-frame directions */
+  int32_t reserved[4];
+} InrfCamera;
+int inrf_render_fwd_camera(const InrfCamera* cam, int64_t pix0, int64_t N, const void* packed_coarse,
+                           const void* packed_fine, const InrfRenderCfg* cfg, const float* t_vals,
+                           const float* u_det, float* rec_coarse, float* rec_fine, float* z_std, float* z_fine,
+                           void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Reflectance clustering (object_level/cluster.py, SSR/training/cluster.py)

@@ -25,6 +25,13 @@ class RenderCfg(C.Structure):
                 ("reserved", C.c_int32 * 7)]
 
 
+class Camera(C.Structure):
+    """InrfCamera (include/inrf.h)."""
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("c2w", C.c_float * 12), ("near_", C.c_float), ("far_", C.c_float), ("convention", C.c_int32),
+                ("euclidean", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
 class FramePlanes(C.Structure):
     """InrfFramePlanes (include/inrf.h): nullable output planes of inrf_frame_finish."""
     _fields_ = [(n, C.c_void_p) for n in ("rgb8", "albedo8", "shading8", "residual8", "label8", "vis_label8", "entropy8",
@@ -57,12 +64,17 @@ _SIGS = {
     "inrf_invert_cdf": (i32, [p, p, p, i64, i32, i32, p, p, p]),
     "inrf_merge_sorted": (i32, [p, p, i64, i32, i32, p, p, p]),
     "inrf_coarse_z": (i32, [p, p, p, i64, i32, i32, p, p]),
+    "inrf_coarse_z_rng": (i32, [p, p, C.c_uint64, i64, i32, i32, p, p]),
+    "inrf_sample_pdf_rng": (i32, [p, p, i32, C.c_uint64, i64, i32, i32, p, p]),
+    "inrf_raw2outputs_rng": (i32, [p, p, p, i32, f32, C.c_uint64, i32, i64, i32, i32, i32, i32, p, p, p]),
+    "inrf_raw2outputs_bwd_rng": (i32, [p, p, p, i32, f32, C.c_uint64, i32, i64, i32, i32, i32, i32, p, p, p, p]),
     "inrf_get_rays": (i32, [i32, i32, f32, f32, f32, f32, C.POINTER(C.c_float), f32, f32, p, p]),
     "inrf_intrinsic_loss_fwd": (i32, [p, i32, p, i32, p, i32, p, i32, p, p, p, i64, i32, p, p]),
     "inrf_intrinsic_loss_bwd": (i32, [p, i32, p, i32, p, i32, p, i32, p, p, p, i64, i32, p, p, p, p, p, p]),
     "inrf_rays_from_pixels": (i32, [p, i64, i32, i32, f32, f32, f32, f32, C.POINTER(C.c_float), i32, i32, f32, f32, p, p]),
     "inrf_render_workspace_bytes": (i64, [C.POINTER(RenderCfg), i64]),
     "inrf_render_fwd": (i32, [p, i64, p, p, C.POINTER(RenderCfg)] + [p] * 13 + [p, i64, p]),
+    "inrf_render_fwd_camera": (i32, [C.POINTER(Camera), i64, i64, p, p, C.POINTER(RenderCfg)] + [p] * 7 + [i64, p]),
     "inrf_mapping_color": (i32, [p, i64, f32, p, p]),
     "inrf_nearest_anchor": (i32, [p, i64, p, i64, i32, f32, p, p]),
     "inrf_dest_color": (i32, [p, i64, p, p, i64, p, i64, f32, p, p, p]),

@@ -6,14 +6,16 @@ const char* last_error();
 long long launch_count();
 int pack_weights(const float* flat, int variant, int n_classes, void* packed, int64_t packed_bytes, cudaStream_t st);
 int launch_embed(const float* x, int64_t M, int L, float scale, float* out, cudaStream_t st);
-int launch_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S, int lindisp, float* z, cudaStream_t st);
+int launch_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S, int lindisp, float* z, cudaStream_t st,
+                    Rng rng = Rng{});
 int launch_raw2outputs(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise, int64_t N,
-                       int S, int n_classes, int endpoint, int white_bkgd, float* rec, float* weights, cudaStream_t st);
+                       int S, int n_classes, int endpoint, int white_bkgd, float* rec, float* weights, cudaStream_t st, Rng rng = Rng{});
 int launch_raw2outputs_bwd(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise, int64_t N,
                            int S, int n_classes, int endpoint, int white_bkgd, const float* grec, const float* gweights,
-                           float* graw, cudaStream_t st);
+                           float* graw, cudaStream_t st, Rng rng = Rng{});
 int launch_sample_pdf(const float* bins, const float* weights, int ld_w, const float* cdf_in, const float* u,
-                      const float* u_det, int64_t N, int B, int n_samples, float* samples, int64_t* inds, float* cdf_out, cudaStream_t st);
+                      const float* u_det, int64_t N, int B, int n_samples, float* samples, int64_t* inds, float* cdf_out, cudaStream_t st,
+                      Rng rng = Rng{});
 int launch_merge_sorted(const float* za, const float* zb, int64_t N, int Sa, int Sb, float* zout, float* zstd, cudaStream_t st);
 int launch_zmid(const float* z, int64_t N, int S, float* zmid, cudaStream_t st);
 int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int opencv, int euclidean,
@@ -80,6 +82,27 @@ static int check_cfg(const InrfRenderCfg* c) {
   if (c->variant == INRF_NET_SSR && c->lindisp) { set_error("SSR renderer samples linearly in depth only (trainer.py:732)"); return INRF_EUNSUPPORTED; }
   if (!(c->pe_scalar_factor > 0.f)) { set_error("pe_scalar_factor must be positive"); return INRF_EINVAL; }
   return INRF_OK;
+}
+
+// The fused renderer: coarse launch (depths generated in the front end, rows composited by the back-end warps, which
+// also resample and write the merged depths of the fine pass), then the fine launch, composited the same way.  No raw
+// tensor exists.  `a` carries the ray addressing (table or camera).
+static int render_fused(MlpArgs a, int64_t N, const void* packed_coarse, const void* packed_fine, const InrfRenderCfg& c,
+                        const float* t_vals, const float* u_det, const float* t_rand, const float* noise_coarse,
+                        const float* noise_fine, float* rec_coarse, float* rec_fine, float* z_std, float* z_f, float* ring,
+                        cudaStream_t st) {
+  const int Sc = c.n_samples, Sf = c.n_importance, St = Sc + Sf;
+  a.packed = packed_coarse; a.variant = c.variant; a.n_classes = c.n_classes; a.endpoint = 0;
+  a.pe_scale = c.pe_scalar_factor; a.z = nullptr; a.S = Sc; a.M = N * Sc; a.raw = nullptr;
+  FuseArgs f{};
+  f.white_bkgd = c.white_bkgd; f.lindisp = c.lindisp; f.t_vals = t_vals; f.t_rand = t_rand; f.noise = noise_coarse;
+  f.rec = rec_coarse; f.n_importance = Sf; f.u_det = u_det; f.z_out = Sf > 0 ? z_f : nullptr; f.z_std = z_std; f.ring = ring;
+  int rc = launch_mlp_tc(a, st, &f);
+  if (rc || Sf == 0) return rc;
+  a.packed = packed_fine ? packed_fine : packed_coarse;
+  a.z = z_f; a.S = St; a.M = N * St;
+  f.t_vals = nullptr; f.t_rand = nullptr; f.noise = noise_fine; f.rec = rec_fine; f.n_importance = 0; f.z_out = nullptr; f.z_std = nullptr;
+  return launch_mlp_tc(a, st, &f);
 }
 
 }  // namespace inrf
@@ -328,21 +351,10 @@ int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, con
   if (usable < p.total) { set_error("workspace too small: %lld < %lld", (long long)usable, (long long)p.total); return INRF_EWORKSPACE; }
   auto F = [&](int64_t off) { return reinterpret_cast<float*>(base + off); };
   if (fused) {
-    // coarse launch: depths generated in the front end, rows composited by the back-end warp, which also resamples
-    // and writes the merged depths of the fine pass; fine launch: composited the same way.  No raw tensor exists.
-    float* z_f = z_fine ? z_fine : F(p.z_f);
     MlpArgs a{};
-    a.packed = packed_coarse; a.variant = c.variant; a.n_classes = c.n_classes; a.endpoint = 0;
-    a.pe_scale = c.pe_scalar_factor; a.rays = rays; a.z = nullptr; a.S = Sc; a.M = N * Sc; a.raw = nullptr;
-    FuseArgs f{};
-    f.white_bkgd = c.white_bkgd; f.lindisp = c.lindisp; f.t_vals = t_vals; f.t_rand = t_rand; f.noise = noise_coarse;
-    f.rec = rec_coarse; f.n_importance = Sf; f.u_det = u_det; f.z_out = Sf > 0 ? z_f : nullptr; f.z_std = z_std; f.ring = F(p.ring);
-    if ((rc = launch_mlp_tc(a, st, &f))) return rc;
-    if (Sf == 0) return INRF_OK;
-    a.packed = packed_fine ? packed_fine : packed_coarse;
-    a.z = z_f; a.S = St; a.M = N * St;
-    f.t_vals = nullptr; f.t_rand = nullptr; f.noise = noise_fine; f.rec = rec_fine; f.n_importance = 0; f.z_out = nullptr; f.z_std = nullptr;
-    return launch_mlp_tc(a, st, &f);
+    a.rays = rays;
+    return render_fused(a, N, packed_coarse, packed_fine, c, t_vals, u_det, t_rand, noise_coarse, noise_fine, rec_coarse, rec_fine,
+                        z_std, z_fine ? z_fine : F(p.z_f), F(p.ring), st);
   }
   float* z_c = F(p.z_c);
   float* w_c = F(p.w_c);
@@ -370,6 +382,73 @@ int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, con
   a.z = z_f; a.S = St; a.M = N * St; a.raw = raw_f;
   if ((rc = run_mlp(a, c.precision, st))) return rc;
   return launch_raw2outputs(raw_f, z_f, rays + 3, 11, noise_fine, N, St, c.n_classes, a.endpoint, c.white_bkgd, rec_fine, weights_fine, st);
+}
+
+/* ---- training-mode draws generated inside the stage kernels (no generator launch, no [N,S] tensors) -------------------- */
+int inrf_coarse_z_rng(const float* rays, const float* t_vals, uint64_t seed, int64_t N, int S, int lindisp, float* z, void* stream) {
+  INRF_CHECK_ARG(N >= 0 && S > 0 && (N == 0 || (rays && t_vals && z)), "null pointer / bad size");
+  return launch_coarse_z(rays, t_vals, nullptr, N, S, lindisp, z, (cudaStream_t)stream, Rng{seed, RNG_T_RAND, 1.f, 1});
+}
+
+int inrf_sample_pdf_rng(const float* bins, const float* weights, int ld_w, uint64_t seed, int64_t N, int B, int n_samples,
+                        float* samples, void* stream) {
+  INRF_CHECK_ARG(N >= 0 && n_samples > 0 && (N == 0 || (bins && weights && samples)), "null pointer / bad size");
+  INRF_CHECK_ARG(ld_w >= B - 1, "ld_w smaller than the number of weights per ray");
+  return launch_sample_pdf(bins, weights, ld_w, nullptr, nullptr, nullptr, N, B, n_samples, samples, nullptr, nullptr,
+                           (cudaStream_t)stream, Rng{seed, RNG_U, 1.f, 1});
+}
+
+int inrf_raw2outputs_rng(const float* raw, const float* z, const float* rays_d, int ld_rays_d, float noise_std, uint64_t seed,
+                         int fine_pass, int64_t N, int S, int n_classes, int endpoint_feat, int white_bkgd, float* rec,
+                         float* weights, void* stream) {
+  INRF_CHECK_ARG(N >= 0 && S > 0 && (N == 0 || (raw && z && rays_d && rec)), "null pointer / bad size");
+  INRF_CHECK_ARG(ld_rays_d >= 3, "ld_rays_d < 3");
+  INRF_CHECK_SUPPORTED(n_classes >= 0 && n_classes <= MAX_CLASSES, "n_classes out of range");
+  return launch_raw2outputs(raw, z, rays_d, ld_rays_d, nullptr, N, S, n_classes, endpoint_feat ? 1 : 0, white_bkgd, rec, weights,
+                            (cudaStream_t)stream, Rng{seed, (unsigned)(fine_pass ? RNG_NOISE_FINE : RNG_NOISE_COARSE), noise_std, noise_std > 0.f});
+}
+
+int inrf_raw2outputs_bwd_rng(const float* raw, const float* z, const float* rays_d, int ld_rays_d, float noise_std, uint64_t seed,
+                             int fine_pass, int64_t N, int S, int n_classes, int endpoint_feat, int white_bkgd,
+                             const float* grad_rec, const float* grad_weights, float* grad_raw, void* stream) {
+  INRF_CHECK_ARG(N >= 0 && S > 0 && (N == 0 || (raw && z && rays_d && grad_rec && grad_raw)), "null pointer / bad size");
+  INRF_CHECK_ARG(ld_rays_d >= 3, "ld_rays_d < 3");
+  INRF_CHECK_SUPPORTED(n_classes >= 0 && n_classes <= MAX_CLASSES, "n_classes out of range");
+  return launch_raw2outputs_bwd(raw, z, rays_d, ld_rays_d, nullptr, N, S, n_classes, endpoint_feat ? 1 : 0, white_bkgd, grad_rec,
+                                grad_weights, grad_raw, (cudaStream_t)stream,
+                                Rng{seed, (unsigned)(fine_pass ? RNG_NOISE_FINE : RNG_NOISE_COARSE), noise_std, noise_std > 0.f});
+}
+
+int inrf_render_fwd_camera(const InrfCamera* cam, int64_t pix0, int64_t N, const void* packed_coarse, const void* packed_fine,
+                           const InrfRenderCfg* cfg, const float* t_vals, const float* u_det, float* rec_coarse, float* rec_fine,
+                           float* z_std, float* z_fine, void* workspace, int64_t workspace_bytes, void* stream) {
+  INRF_POLL();
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  const InrfRenderCfg& c = *cfg;
+  INRF_CHECK_ARG(cam != nullptr && cam->H > 0 && cam->W > 0 && cam->fx != 0.f && cam->fy != 0.f, "bad camera");
+  INRF_CHECK_ARG(cam->convention == INRF_CAM_OPENGL || cam->convention == INRF_CAM_OPENCV, "unknown camera convention");
+  INRF_CHECK_ARG(N >= 0 && pix0 >= 0 && pix0 + N <= (int64_t)cam->H * cam->W, "pixel range outside the frame");
+  if (N == 0) return INRF_OK;
+  INRF_CHECK_ARG(packed_coarse && t_vals && rec_coarse && workspace, "null pointer");
+  if (c.n_importance > 0) INRF_CHECK_ARG(rec_fine && u_det, "fine pass needs rec_fine and u_det");
+  if (!can_fuse(c, false, false)) {
+    set_error("inrf_render_fwd_camera: this configuration is not rendered by the fused kernel (needs INRF_PREC_TC, 32 | samples, "
+              "64 + 128 when there is a fine pass, no endpoint feature); generate the rays (inrf_get_rays) and call inrf_render_fwd");
+    return INRF_EUNSUPPORTED;
+  }
+  WsPlan p = plan_ws_fused(c, N, z_fine == nullptr);
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  int64_t usable = workspace_bytes - (int64_t)(base - reinterpret_cast<uintptr_t>(workspace));
+  if (usable < p.total) { set_error("workspace too small: %lld < %lld", (long long)usable, (long long)p.total); return INRF_EWORKSPACE; }
+  MlpArgs a{};
+  a.cam_on = 1; a.cam_H = cam->H; a.cam_W = cam->W; a.cam_pix0 = pix0;
+  a.cam.fx = cam->fx; a.cam.fy = cam->fy; a.cam.cx = cam->cx; a.cam.cy = cam->cy; a.cam.nearv = cam->near_; a.cam.farv = cam->far_;
+  a.cam.opencv = cam->convention == INRF_CAM_OPENCV; a.cam.euclidean = cam->euclidean != 0;
+  for (int i = 0; i < 12; ++i) a.cam.m[i] = cam->c2w[i];
+  return render_fused(a, N, packed_coarse, packed_fine, c, t_vals, u_det, nullptr, nullptr, nullptr, rec_coarse, rec_fine, z_std,
+                      z_fine ? z_fine : reinterpret_cast<float*>(base + p.z_f), reinterpret_cast<float*>(base + p.ring),
+                      (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -173,6 +173,68 @@ struct TcProgram {
 };
 int make_tc_program(int variant, int n_classes, TcProgram* prog);
 
+// Counter-based random numbers for the training-mode draws (stratified jitter run_nerf.py:472-486,
+// u of sample_pdf run_nerf_helpers.py:414, sigma noise run_nerf.py:385-387): Philox4x32-10 keyed by the caller's seed,
+// counter = (element index, stream id), so a draw is a pure function of (seed, which tensor, which element) - the
+// backward pass regenerates the forward's noise instead of reading it back, and no generator kernel is launched.
+struct Rng { unsigned long long seed; unsigned int stream; float scale; int on; };
+enum { RNG_T_RAND = 1, RNG_U = 2, RNG_NOISE_COARSE = 3, RNG_NOISE_FINE = 4 };
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ uint4 rng_bits(const Rng& g, long long i) {
+  return philox4x32_10(make_uint4((unsigned int)i, (unsigned int)((unsigned long long)i >> 32), g.stream, 0u),
+                       make_uint2((unsigned int)g.seed, (unsigned int)(g.seed >> 32)));
+}
+// U[0,1) with 24 random bits (what torch.rand produces for float32)
+__device__ __forceinline__ float rng_uniform(const Rng& g, long long i) { return (float)(rng_bits(g, i).x >> 8) * 5.9604644775390625e-08f; }
+// N(0,1) * scale (Box-Muller on two of the four words)
+__device__ __forceinline__ float rng_normal(const Rng& g, long long i) {
+  const uint4 b = rng_bits(g, i);
+  const float u1 = (float)((b.x >> 8) + 1u) * 5.9604644775390625e-08f;      // (0,1]
+  const float u2 = (float)(b.y >> 8) * 5.9604644775390625e-08f;
+  return g.scale * sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+#endif
+
+// Pinhole camera of one frame (get_rays + render()'s packing, run_nerf_helpers.py:359-368 / run_nerf.py:100-128;
+// SSR: rays.py:48-84): the ray record of pixel p is a pure function of it, so kernels can generate rays instead
+// of reading a [N,11] table.
+struct Cam { float fx, fy, cx, cy, m[12], nearv, farv; int opencv, euclidean; };
+#ifdef __CUDACC__
+// ray record o3 d3 near far viewdir3 of flat pixel p = row * W + column (the arithmetic of k_get_rays, stages.cu)
+__device__ __forceinline__ void cam_ray(const Cam& c, int H, int W, int64_t p, float* o) {
+  if (p < 0) p = 0;
+  if (p >= (int64_t)H * W) p = (int64_t)H * W - 1;
+  const int j = (int)(p / W), i = (int)(p - (int64_t)j * W);
+  float dx = __fdiv_rn(__fsub_rn((float)i, c.cx), c.fx);
+  float dy = __fdiv_rn(__fsub_rn((float)j, c.cy), c.fy);
+  float dz = 1.f;
+  if (!c.opencv) { dy = -dy; dz = -1.f; }          // OpenGL: x right, y up, camera looks along -z
+  if (c.euclidean) {                                 // depth_type == "euclidean": unit camera-frame directions
+    const float inv = __fdiv_rn(1.f, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+    dx = __fmul_rn(dx, inv); dy = __fmul_rn(dy, inv); dz = __fmul_rn(dz, inv);
+  }
+  float d[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)      // torch.sum(dirs[..., None, :] * c2w[:3, :3], -1): ((x*m0 + y*m1) + z*m2)
+    d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.m[4 * r]), __fmul_rn(dy, c.m[4 * r + 1])), __fmul_rn(dz, c.m[4 * r + 2]));
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+  o[0] = c.m[3]; o[1] = c.m[7]; o[2] = c.m[11];
+  o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
+  o[6] = c.nearv; o[7] = c.farv;
+  o[8] = __fdiv_rn(d[0], nrm); o[9] = __fdiv_rn(d[1], nrm); o[10] = __fdiv_rn(d[2], nrm);
+}
+#endif
+
 // ---------------------------------------------------------------------------------
 // launchers implemented in the .cu files
 // ---------------------------------------------------------------------------------
@@ -185,6 +247,10 @@ struct MlpArgs {
   const float* viewdirs;     // [M,3] or null
   // addressing mode C: rows already embedded (NeRF.forward's own input), [M,90] = gamma(x) | gamma(d)
   const float* emb;
+  // addressing mode B': rays generated from a camera (fused tensor-core renderer only): ray n = pixel cam_pix0 + n
+  int cam_on, cam_H, cam_W;
+  int64_t cam_pix0;
+  Cam cam;
   // addressing mode B: rays + depths
   const float* rays;         // [N,11] or null
   const float* z;            // [N,S]

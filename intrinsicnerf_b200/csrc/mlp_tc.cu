@@ -307,12 +307,21 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
 __device__ __forceinline__ int64_t tile_of(const Params& P, int it) {
   return P.fuse ? (int64_t)blockIdx.x * P.n_iter + it : (int64_t)it * gridDim.x + blockIdx.x;
 }
+// ray record n (o3 d3 near far viewdir3): read from the caller's table or generated from the frame's camera
+__device__ __forceinline__ void get_ray(const Params& P, int64_t n, float* r) {
+  if (P.a.cam_on) { cam_ray(P.a.cam, P.a.cam_H, P.a.cam_W, P.a.cam_pix0 + n, r); return; }
+  const float* ray = P.a.rays + n * 11;
+#pragma unroll
+  for (int i = 0; i < 11; ++i) r[i] = __ldg(ray + i);
+}
 // depth of sample s of ray n: the caller's array, or (coarse pass of the fused renderer) generated here
 __device__ __forceinline__ float sample_depth(const Params& P, int64_t n, int s) {
   if (P.a.z != nullptr) return __ldg(P.a.z + n * P.a.S + s);
-  const float* ray = P.a.rays + n * 11;
+  float nearv, farv;
+  if (P.a.cam_on) { nearv = P.a.cam.nearv; farv = P.a.cam.farv; }
+  else { nearv = __ldg(P.a.rays + n * 11 + 6); farv = __ldg(P.a.rays + n * 11 + 7); }
   const bool jit = P.f.t_rand != nullptr;
-  return coarse_z_sample(__ldg(ray + 6), __ldg(ray + 7), P.f.t_vals, s, P.a.S, P.f.lindisp, jit, jit ? __ldg(P.f.t_rand + n * P.a.S + s) : 0.f);
+  return coarse_z_sample(nearv, farv, P.f.t_vals, s, P.a.S, P.f.lindisp, jit, jit ? __ldg(P.f.t_rand + n * P.a.S + s) : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -494,8 +503,9 @@ __device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, i
 #pragma unroll
       for (int i = 0; i < 4; ++i) rs.ex[i] = 0.f;
     }
-    const float* rp = P.a.rays + ray * 11;
-    const float dx = __ldg(rp + 3), dy = __ldg(rp + 4), dz = __ldg(rp + 5);
+    float rr[11];
+    get_ray(P, ray, rr);
+    const float dx = rr[3], dy = rr[4], dz = rr[5];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float zs = sample_depth(P, ray, s);
     float znext = __shfl_down_sync(FULLMASK, zs, 1);
@@ -593,14 +603,15 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
     const bool pre_embedded = P.a.emb != nullptr;
     const float* e = pre_embedded ? P.a.emb + m * (PE_PTS + PE_DIR) : nullptr;
     if (!pre_embedded) {
-      if (P.a.rays != nullptr) {
+      if (P.a.rays != nullptr || P.a.cam_on) {
         const int64_t n = m / P.a.S;
-        const float* ray = P.a.rays + n * 11;
+        float ray[11];
+        get_ray(P, n, ray);
         const float zv = sample_depth(P, n, (int)(m - n * P.a.S));
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          x[i] = __fadd_rn(__ldg(ray + i), __fmul_rn(__ldg(ray + 3 + i), zv));   // o + d z (run_nerf.py:488)
-          d[i] = __ldg(ray + 8 + i);
+          x[i] = __fadd_rn(ray[i], __fmul_rn(ray[3 + i], zv));   // o + d z (run_nerf.py:488)
+          d[i] = ray[8 + i];
         }
       } else {
 #pragma unroll
@@ -1180,7 +1191,7 @@ int64_t mlp_tc_ring_bytes(int n_classes) {
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   if (a.M == 0) return INRF_OK;
   if (fuse != nullptr) {
-    if (a.rays == nullptr || a.S <= 0 || (a.S & 31) || a.endpoint || a.stash_img || fuse->rec == nullptr || fuse->ring == nullptr ||
+    if ((a.rays == nullptr && !a.cam_on) || a.S <= 0 || (a.S & 31) || a.endpoint || a.stash_img || fuse->rec == nullptr || fuse->ring == nullptr ||
         (a.z == nullptr && fuse->t_vals == nullptr)) {
       set_error("internal: fused tensor-core launch needs ray addressing, S %% 32 == 0, no endpoint feature, rec and ring");
       return INRF_EINVAL;

@@ -44,13 +44,14 @@ __global__ void k_embed(const float* __restrict__ x, int64_t M, int L, float sca
 // coarse sample depths (run_nerf.py:464-486; trainer.py:730-746)
 // ---------------------------------------------------------------------------------
 __global__ void k_coarse_z(const float* __restrict__ rays, const float* __restrict__ t_vals,
-                           const float* __restrict__ t_rand, int64_t N, int S, int lindisp, float* __restrict__ z) {
+                           const float* __restrict__ t_rand, int64_t N, int S, int lindisp, float* __restrict__ z, Rng rng) {
   int64_t total = N * S;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t n = i / S;
     int s = (int)(i - n * S);
     float nearv = rays[n * 11 + 6], farv = rays[n * 11 + 7];
-    z[i] = coarse_z_sample(nearv, farv, t_vals, s, S, lindisp, t_rand != nullptr, t_rand != nullptr ? t_rand[i] : 0.f);
+    const bool jit = t_rand != nullptr || rng.on;
+    z[i] = coarse_z_sample(nearv, farv, t_vals, s, S, lindisp, jit, t_rand != nullptr ? t_rand[i] : (rng.on ? rng_uniform(rng, i) : 0.f));
   }
 }
 
@@ -62,7 +63,7 @@ __global__ void k_coarse_z(const float* __restrict__ rays, const float* __restri
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_raw2outputs(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int ld_d,
               const float* __restrict__ noise, int64_t N, int S, int ch, int n_extra, int white_bkgd,
-              float* __restrict__ rec, int rec_ch, float* __restrict__ weights) {
+              float* __restrict__ rec, int rec_ch, float* __restrict__ weights, Rng rng) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)WARPS_PER_CTA + (threadIdx.x >> 5);
   if (ray >= N) return;
@@ -91,6 +92,7 @@ k_raw2outputs(const float* __restrict__ raw, const float* __restrict__ z, const 
       for (int i = 0; i < INRF_RAW_BASE; ++i) c[i] = rw[(int64_t)s * ch + i];
       float sig = c[3];
       if (noise != nullptr) sig = __fadd_rn(sig, noise[ray * S + s]);
+      else if (rng.on) sig = __fadd_rn(sig, rng_normal(rng, ray * S + s));
       float alpha = __fsub_rn(1.f, expf(-__fmul_rn(fmaxf(sig, 0.f), dist)));
       one_minus = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
       w = alpha;
@@ -165,7 +167,7 @@ constexpr int BWD_MAXG = 8;
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_raw2outputs_bwd(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int ld_d,
                   const float* __restrict__ noise, int64_t N, int S, int ch, int n_sem, int n_extra, int white_bkgd,
-                  const float* __restrict__ grec, int rec_ch, const float* __restrict__ gweights, float* __restrict__ graw) {
+                  const float* __restrict__ grec, int rec_ch, const float* __restrict__ gweights, float* __restrict__ graw, Rng rng) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * (int64_t)WARPS_PER_CTA + (threadIdx.x >> 5);
   if (ray >= N) return;
@@ -187,7 +189,7 @@ k_raw2outputs_bwd(const float* __restrict__ raw, const float* __restrict__ z, co
       if (s < S) {
         float d = (s + 1 < S) ? (zr[s + 1] - zr[s]) : 1e10f;
         d *= dnorm;
-        float sig = rw[(int64_t)s * ch + 3] + (noise ? noise[ray * S + s] : 0.f);
+        float sig = rw[(int64_t)s * ch + 3] + (noise ? noise[ray * S + s] : (rng.on ? rng_normal(rng, ray * S + s) : 0.f));
         a = 1.f - expf(-fmaxf(sig, 0.f) * d);
         one_minus = 1.f - a + 1e-10f;
         dist[gi] = d;
@@ -292,7 +294,7 @@ __device__ __forceinline__ void invert_one(const float* cdf_s, const float* bins
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_sample_pdf(const float* __restrict__ bins, const float* __restrict__ weights, int ld_w, const float* __restrict__ cdf_in,
              const float* __restrict__ u, const float* __restrict__ u_det, int64_t N, int B, int n_samples,
-             float* __restrict__ samples, int64_t* __restrict__ inds, float* __restrict__ cdf_out) {
+             float* __restrict__ samples, int64_t* __restrict__ inds, float* __restrict__ cdf_out, Rng rng) {
   __shared__ float s_cdf[WARPS_PER_CTA][MAX_BINS];
   __shared__ float s_bins[WARPS_PER_CTA][MAX_BINS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -325,7 +327,7 @@ k_sample_pdf(const float* __restrict__ bins, const float* __restrict__ weights, 
   __syncwarp();
   if (cdf_out != nullptr) for (int i = lane; i < B; i += 32) cdf_out[ray * B + i] = cdf_s[i];
   for (int j = lane; j < n_samples; j += 32) {
-    float uj = (u != nullptr) ? u[ray * n_samples + j] : u_det[j];
+    float uj = (u != nullptr) ? u[ray * n_samples + j] : (rng.on ? rng_uniform(rng, ray * n_samples + j) : u_det[j]);
     float smp; int64_t ind;
     invert_one(cdf_s, bin_s, B, uj, &smp, &ind);
     samples[ray * n_samples + j] = smp;
@@ -422,31 +424,13 @@ __global__ void k_zmid(const float* __restrict__ z, int64_t N, int S, float* __r
 // create_rays (SSR/models/rays.py:48-76 get_rays_camera, :79-84 get_rays_world, :223-256), for a full image
 // (pix == nullptr) or for selected pixels pix[n] = row * W + column (training batches: sampling_index,
 // rays.py:153-172; run_nerf.py:913-932 - the random draws stay with the caller).
-struct Cam { float fx, fy, cx, cy, m[12], nearv, farv; int opencv, euclidean; };
 __global__ void k_get_rays(int H, int W, Cam c, const int64_t* __restrict__ pix, int64_t total, float* __restrict__ rays) {
   for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < total; n += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = pix ? pix[n] : n;
-    if (p < 0) p = 0;
-    if (p >= (int64_t)H * W) p = (int64_t)H * W - 1;
-    const int j = (int)(p / W), i = (int)(p - (int64_t)j * W);
-    float dx = __fdiv_rn(__fsub_rn((float)i, c.cx), c.fx);
-    float dy = __fdiv_rn(__fsub_rn((float)j, c.cy), c.fy);
-    float dz = 1.f;
-    if (!c.opencv) { dy = -dy; dz = -1.f; }          // OpenGL: x right, y up, camera looks along -z
-    if (c.euclidean) {                                 // depth_type == "euclidean": unit camera-frame directions
-      const float inv = __fdiv_rn(1.f, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
-      dx = __fmul_rn(dx, inv); dy = __fmul_rn(dy, inv); dz = __fmul_rn(dz, inv);
-    }
-    float d[3];
+    float o[11];
+    cam_ray(c, H, W, pix ? pix[n] : n, o);
+    float* dst = rays + n * 11;
 #pragma unroll
-    for (int r = 0; r < 3; ++r)      // torch.sum(dirs[..., None, :] * c2w[:3, :3], -1): ((x*m0 + y*m1) + z*m2)
-      d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c.m[4 * r]), __fmul_rn(dy, c.m[4 * r + 1])), __fmul_rn(dz, c.m[4 * r + 2]));
-    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-    float* o = rays + n * 11;
-    o[0] = c.m[3]; o[1] = c.m[7]; o[2] = c.m[11];
-    o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
-    o[6] = c.nearv; o[7] = c.farv;
-    o[8] = __fdiv_rn(d[0], nrm); o[9] = __fdiv_rn(d[1], nrm); o[10] = __fdiv_rn(d[2], nrm);
+    for (int i = 0; i < 11; ++i) dst[i] = o[i];
   }
 }
 
@@ -486,20 +470,20 @@ int launch_embed(const float* x, int64_t M, int L, float scale, float* out, cuda
 }
 
 int launch_coarse_z(const float* rays, const float* t_vals, const float* t_rand, int64_t N, int S, int lindisp,
-                    float* z, cudaStream_t st) {
+                    float* z, cudaStream_t st, Rng rng) {
   if (N == 0) return INRF_OK;
-  k_coarse_z<<<grid_for(N * S, 256), 256, 0, st>>>(rays, t_vals, t_rand, N, S, lindisp, z);
+  k_coarse_z<<<grid_for(N * S, 256), 256, 0, st>>>(rays, t_vals, t_rand, N, S, lindisp, z, rng);
   INRF_LAUNCH_CHECK();
   return INRF_OK;
 }
 
 int launch_raw2outputs(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise, int64_t N,
-                       int S, int n_classes, int endpoint, int white_bkgd, float* rec, float* weights, cudaStream_t st) {
+                       int S, int n_classes, int endpoint, int white_bkgd, float* rec, float* weights, cudaStream_t st, Rng rng) {
   if (N == 0) return INRF_OK;
   int ch = raw_channels(n_classes, endpoint), rc = rec_channels(n_classes, endpoint);
   int64_t blocks = (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   k_raw2outputs<<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, st>>>(raw, z, rays_d, ld_d, noise, N, S, ch, ch - INRF_RAW_BASE,
-                                                               white_bkgd, rec, rc, weights);
+                                                               white_bkgd, rec, rc, weights, rng);
   INRF_LAUNCH_CHECK();
   if (white_bkgd && n_classes > 0) {
     k_add_bg_sem<<<grid_for(N * n_classes, 256), 256, 0, st>>>(rec, N, rc, n_classes);
@@ -510,25 +494,25 @@ int launch_raw2outputs(const float* raw, const float* z, const float* rays_d, in
 
 int launch_raw2outputs_bwd(const float* raw, const float* z, const float* rays_d, int ld_d, const float* noise, int64_t N,
                            int S, int n_classes, int endpoint, int white_bkgd, const float* grec, const float* gweights,
-                           float* graw, cudaStream_t st) {
+                           float* graw, cudaStream_t st, Rng rng) {
   if (N == 0) return INRF_OK;
   if (S > BWD_MAXG * 32) { set_error("raw2outputs_bwd: %d samples per ray > %d", S, BWD_MAXG * 32); return INRF_EUNSUPPORTED; }
   int ch = raw_channels(n_classes, endpoint), rc = rec_channels(n_classes, endpoint);
   int64_t blocks = (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   k_raw2outputs_bwd<<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, st>>>(raw, z, rays_d, ld_d, noise, N, S, ch, n_classes,
-                                                                   ch - INRF_RAW_BASE, white_bkgd, grec, rc, gweights, graw);
+                                                                   ch - INRF_RAW_BASE, white_bkgd, grec, rc, gweights, graw, rng);
   INRF_LAUNCH_CHECK();
   return INRF_OK;
 }
 
 int launch_sample_pdf(const float* bins, const float* weights, int ld_w, const float* cdf_in, const float* u,
                       const float* u_det, int64_t N, int B, int n_samples, float* samples, int64_t* inds,
-                      float* cdf_out, cudaStream_t st) {
+                      float* cdf_out, cudaStream_t st, Rng rng) {
   if (N == 0) return INRF_OK;
   if (B > MAX_BINS || B < 2) { set_error("sample_pdf: bins per ray %d outside [2,%d]", B, MAX_BINS); return INRF_EUNSUPPORTED; }
   int64_t blocks = (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   k_sample_pdf<<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, st>>>(bins, weights, ld_w, cdf_in, u, u_det, N, B, n_samples,
-                                                              samples, inds, cdf_out);
+                                                              samples, inds, cdf_out, rng);
   INRF_LAUNCH_CHECK();
   return INRF_OK;
 }

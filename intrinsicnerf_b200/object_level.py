@@ -123,12 +123,15 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             return draw_uniform(*shape) * raw_noise_std
         return torch.randn(*shape, device=dev) * raw_noise_std
 
-    t_rand = draw_uniform(N, N_samples) if perturb > 0. else None
-    u = draw_uniform(N, N_importance) if (N_importance > 0 and perturb != 0.) else None
-
     fused = isinstance(network_query_fn, _FusedQuery) and network_query_fn.fusable_with(network_fn, network_fine)
     if fused and (network_fn.needs_grad() or (network_fine is not None and network_fine.needs_grad())):
         fused = False          # training: stage kernels + differentiable MLP / compositing (MlpFn, CompositeFn)
+    # stage path without the pytest hooks: the reference's three random tensors per pass (run_nerf.py:478, 387,
+    # run_nerf_helpers.py:414) are generated inside the stage kernels from one seed per call (inrf_*_rng)
+    in_kernel_rng = (not fused) and (not pytest)
+    seed = ops.next_seed() if in_kernel_rng and (perturb > 0. or raw_noise_std > 0.) else None
+    t_rand = draw_uniform(N, N_samples) if (perturb > 0. and not in_kernel_rng) else None
+    u = draw_uniform(N, N_importance) if (N_importance > 0 and perturb != 0. and not in_kernel_rng) else None
     ret = {}
     if fused:
         fine = network_fine if network_fine is not None else network_fn
@@ -150,18 +153,21 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     else:
         rays_d, viewdirs = ray_batch[:, 3:6], ray_batch[:, -3:]
         rays_o = ray_batch[:, 0:3]
-        z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand)
+        z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand, seed if (in_kernel_rng and perturb > 0.) else None)
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         raw = network_query_fn(pts, viewdirs, network_fn)
-        rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, draw_noise(N, N_samples), white_bkgd)
+        rng_c = (raw_noise_std, seed, False) if (in_kernel_rng and raw_noise_std > 0.) else None
+        rng_f = (raw_noise_std, seed, True) if (in_kernel_rng and raw_noise_std > 0.) else None
+        rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, None if in_kernel_rng else draw_noise(N, N_samples), white_bkgd, rng=rng_c)
         rec0 = rec
         if N_importance > 0:
             z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
-            z_samples = ops.sample_pdf(z_mid, weights[..., 1:-1].detach(), N_importance, u)[0]   # detached (run_nerf.py:501)
+            z_samples = ops.sample_pdf(z_mid, weights[..., 1:-1].detach(), N_importance, u,
+                                       seed=seed if (in_kernel_rng and perturb != 0.) else None)[0]   # detached (run_nerf.py:501)
             z_vals, z_std = ops.merge_sorted(z_vals, z_samples)
             pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
             raw = network_query_fn(pts, viewdirs, network_fn if network_fine is None else network_fine)
-            rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, draw_noise(N, St), white_bkgd)
+            rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, None if in_kernel_rng else draw_noise(N, St), white_bkgd, rng=rng_f)
         for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
             ret[k + "_map"] = _split_rec(rec, k)
         if retraw:
@@ -238,6 +244,33 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
     return o, d
 
 
+def _render_frame_from_camera(H, W, K, c2w, near, far, chunk, dev, network_fn=None, network_query_fn=None, N_samples=64, retraw=False,
+                              lindisp=False, perturb=0., N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., **_):
+    """render()'s full-image case with the rays generated inside the fused kernels (inrf_render_fwd_camera): the dict
+    batchify_rays would return, or None when this call needs the general path (training, random draws, raw output,
+    foreign networks, sample counts the fused kernel does not cover)."""
+    q = network_query_fn
+    if retraw or perturb or raw_noise_std or not (isinstance(q, _FusedQuery) and q.fusable_with(network_fn, network_fine)) \
+            or not ops.frame_camera_ok(N_samples, N_importance) or network_fn.needs_grad() \
+            or (network_fine is not None and network_fine.needs_grad()):
+        return None
+    fine = network_fine if network_fine is not None else network_fn
+    pc, pf = network_fn.packed(), (fine.packed() if N_importance > 0 else None)
+    parts = []
+    for i in range(0, H * W, chunk):
+        parts.append(ops.render_frame_camera(H, W, K, c2w, near, far, pc, pf, dev, pix0=i, n=min(chunk, H * W - i), variant=network_fn.variant,
+                                             n_samples=N_samples, n_importance=N_importance, lindisp=lindisp, white_bkgd=white_bkgd,
+                                             pe_scalar_factor=q.embed_fn.scalar_factor))
+    cat = lambda k: parts[0][k] if len(parts) == 1 else torch.cat([p[k] for p in parts], 0)  # noqa: E731
+    rec = cat("rec_fine" if N_importance > 0 else "rec_coarse")
+    ret = {k + "_map": _split_rec(rec, k) for k in ("rgb", "disp", "acc", "albedo", "shading", "residual")}
+    if N_importance > 0:
+        rec0 = cat("rec_coarse")
+        ret.update({k + "0": _split_rec(rec0, k) for k in ("rgb", "disp", "acc", "albedo", "shading", "residual")})
+        ret["z_std"] = cat("z_std")
+    return ret
+
+
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
     """-> [rgb_map, disp_map, acc_map, albedo_map, shading_map, residual_map, extras_dict]."""
@@ -246,8 +279,10 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
         # full-image fast path: rays are generated and packed on the device by one kernel
         net = kwargs.get("network_fn")
         dev = next(net.parameters()).device if isinstance(net, torch.nn.Module) else torch.device("cuda")
-        packed = ops.get_rays_packed(H, W, K, c2w, near, far, dev)
-        all_ret = batchify_rays(packed, chunk, **kwargs)
+        all_ret = _render_frame_from_camera(H, W, K, c2w, near, far, chunk, dev, **kwargs)
+        if all_ret is None:
+            packed = ops.get_rays_packed(H, W, K, c2w, near, far, dev)
+            all_ret = batchify_rays(packed, chunk, **kwargs)
         for k in all_ret:
             all_ret[k] = torch.reshape(all_ret[k], [H, W] + list(all_ret[k].shape[1:]))
         main = ["rgb_map", "disp_map", "acc_map", "albedo_map", "shading_map", "residual_map"]
@@ -352,9 +387,17 @@ def render_record(H, W, K, chunk, c2w, near=0., far=1., **kwargs):
             and not kwargs.get("raw_noise_std", 0.) and kwargs.get("use_viewdirs", False) and not kwargs.get("ndc", True) \
             and kwargs.get("c2w_staticcam") is None:
         dev = next(fn.parameters()).device
-        rays = ops.get_rays_packed(H, W, K, c2w, near, far, dev)
         pc, pf = fn.packed(), ((fine if fine is not None else fn).packed() if n_imp > 0 else None)
         recs = []
+        if ops.frame_camera_ok(kwargs["N_samples"], n_imp):
+            # rays generated inside the kernels from (K, c2w, pixel index): no [H*W, 11] table is written or read
+            for i in range(0, H * W, chunk):
+                o = ops.render_frame_camera(H, W, K, c2w, near, far, pc, pf, dev, pix0=i, n=min(chunk, H * W - i), variant=fn.variant,
+                                            n_samples=kwargs["N_samples"], n_importance=n_imp, lindisp=kwargs.get("lindisp", False),
+                                            white_bkgd=kwargs.get("white_bkgd", False), pe_scalar_factor=q.embed_fn.scalar_factor)
+                recs.append(o["rec_fine"] if n_imp > 0 else o["rec_coarse"])
+            return recs[0] if len(recs) == 1 else torch.cat(recs, 0)
+        rays = ops.get_rays_packed(H, W, K, c2w, near, far, dev)
         for i in range(0, rays.shape[0], chunk):
             o = ops.render_chunk(rays[i:i + chunk], pc, pf, variant=fn.variant, n_samples=kwargs["N_samples"], n_importance=n_imp,
                                  lindisp=kwargs.get("lindisp", False), white_bkgd=kwargs.get("white_bkgd", False),

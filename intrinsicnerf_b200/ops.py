@@ -27,6 +27,19 @@ def poll_status():
     check(_lib.lib().inrf_poll_status())
 
 
+_SEED_STATE = [None, 0]
+
+
+def next_seed():
+    """Seed for one in-kernel random tensor (inrf_*_rng): a pure host-side function of torch's seed and a call counter,
+    so torch.manual_seed(s) makes a training run reproducible without any generator kernel being launched."""
+    base = torch.initial_seed()
+    if _SEED_STATE[0] != base:
+        _SEED_STATE[0], _SEED_STATE[1] = base, 0
+    _SEED_STATE[1] += 1
+    return (base * 0x9E3779B97F4A7C15 + _SEED_STATE[1] * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+
+
 def launch_count():
     """Kernels launched by libinrf.so in this process so far (inrf_launch_count)."""
     return int(_lib.lib().inrf_launch_count())
@@ -130,7 +143,8 @@ def mlp_forward_rays(packed, variant, n_classes, rays, z, endpoint=False, pe_sca
     return raw
 
 
-def raw2outputs_rec(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, endpoint=False, want_weights=True):
+def raw2outputs_rec(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, endpoint=False, want_weights=True, rng=None):
+    """rng = (noise_std, seed, fine_pass): sigma noise generated inside the kernel (inrf_raw2outputs_rng) instead of `noise`."""
     raw, z_vals, rays_d = _f32(raw, "raw"), _f32(z_vals, "z_vals"), _f32(rays_d, "rays_d")
     N, S, ch = raw.shape
     if ch != RAW_BASE + n_classes + (128 if endpoint else 0):
@@ -139,21 +153,30 @@ def raw2outputs_rec(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes
     weights = torch.empty(N, S, dtype=torch.float32, device=raw.device) if want_weights else None
     noise = None if noise is None else _f32(noise, "noise")
     with torch.cuda.device(raw.device):
-        check(_lib.lib().inrf_raw2outputs(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S, n_classes,
-                                          int(endpoint), int(bool(white_bkgd)), _ptr(rec), _ptr(weights), _stream()))
+        if rng is not None and noise is None:
+            check(_lib.lib().inrf_raw2outputs_rng(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, float(rng[0]), int(rng[1]), int(bool(rng[2])), N, S,
+                                                  n_classes, int(endpoint), int(bool(white_bkgd)), _ptr(rec), _ptr(weights), _stream()))
+        else:
+            check(_lib.lib().inrf_raw2outputs(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S, n_classes,
+                                              int(endpoint), int(bool(white_bkgd)), _ptr(rec), _ptr(weights), _stream()))
     return rec, weights
 
 
-def raw2outputs_bwd(raw, z_vals, rays_d, noise, grad_rec, grad_weights, white_bkgd=False, n_classes=0, endpoint=False):
+def raw2outputs_bwd(raw, z_vals, rays_d, noise, grad_rec, grad_weights, white_bkgd=False, n_classes=0, endpoint=False, rng=None):
     raw, z_vals, rays_d, grad_rec = _f32(raw, "raw"), _f32(z_vals, "z_vals"), _f32(rays_d, "rays_d"), _f32(grad_rec, "grad_rec")
     N, S, ch = raw.shape
     noise = None if noise is None else _f32(noise, "noise")
     grad_weights = None if grad_weights is None else _f32(grad_weights, "grad_weights")
     grad_raw = torch.empty_like(raw)
     with torch.cuda.device(raw.device):
-        check(_lib.lib().inrf_raw2outputs_bwd(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S, n_classes,
-                                              int(endpoint), int(bool(white_bkgd)), _ptr(grad_rec), _ptr(grad_weights),
-                                              _ptr(grad_raw), _stream()))
+        if rng is not None and noise is None:
+            check(_lib.lib().inrf_raw2outputs_bwd_rng(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, float(rng[0]), int(rng[1]), int(bool(rng[2])), N, S,
+                                                      n_classes, int(endpoint), int(bool(white_bkgd)), _ptr(grad_rec), _ptr(grad_weights),
+                                                      _ptr(grad_raw), _stream()))
+        else:
+            check(_lib.lib().inrf_raw2outputs_bwd(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, _ptr(noise), N, S, n_classes,
+                                                  int(endpoint), int(bool(white_bkgd)), _ptr(grad_rec), _ptr(grad_weights),
+                                                  _ptr(grad_raw), _stream()))
     return grad_raw
 
 
@@ -270,27 +293,30 @@ class CompositeFn(torch.autograd.Function):
     through the compositing kernel."""
 
     @staticmethod
-    def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint):
-        rec, w = raw2outputs_rec(raw.detach(), z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True)
+    def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, rng=None):
+        rec, w = raw2outputs_rec(raw.detach(), z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True, rng)
         ctx.save_for_backward(raw.detach(), z_vals, rays_d, noise if noise is not None else torch.empty(0))
-        ctx.cfg = (bool(white_bkgd), int(n_classes), bool(endpoint), noise is not None)
+        ctx.cfg = (bool(white_bkgd), int(n_classes), bool(endpoint), noise is not None, rng)
         return rec, w
 
     @staticmethod
     def backward(ctx, g_rec, g_w):
         raw, z_vals, rays_d, noise = ctx.saved_tensors
-        wb, C, ep, has_noise = ctx.cfg
+        wb, C, ep, has_noise, rng = ctx.cfg
         g_rec = torch.zeros(raw.shape[0], REC_BASE + C + (128 if ep else 0), device=raw.device) if g_rec is None else g_rec
         g = raw2outputs_bwd(raw, z_vals, rays_d, noise if has_noise else None, g_rec.contiguous(),
-                            None if g_w is None else g_w.contiguous(), wb, C, ep)
-        return g, None, None, None, None, None, None
+                            None if g_w is None else g_w.contiguous(), wb, C, ep, rng)   # the same (seed, element) -> the same noise
+        return g, None, None, None, None, None, None, None
 
 
-def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, endpoint=False):
-    """rec, weights = raw2outputs; differentiable w.r.t. raw when autograd is recording."""
+def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, endpoint=False, rng=None):
+    """rec, weights = raw2outputs; differentiable w.r.t. raw when autograd is recording.  rng = (noise_std, seed,
+    fine_pass) generates the sigma noise inside the kernels (forward and backward) instead of taking a `noise` tensor."""
+    if rng is not None and not rng[0] > 0:
+        rng = None
     if torch.is_grad_enabled() and raw.requires_grad:
-        return CompositeFn.apply(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint)
-    return raw2outputs_rec(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True)
+        return CompositeFn.apply(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, rng)
+    return raw2outputs_rec(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True, rng)
 
 
 LOSS_TERMS = ("img", "chroma", "residual", "reflect_sparsity", "shading_smooth", "far_reflect", "intensity", "cluster")
@@ -342,11 +368,17 @@ def intrinsic_losses(rgb, albedo, shading, residual, gt_rgb, label, target_albed
     return IntrinsicLossFn.apply(rgb, albedo, shading.reshape(-1), residual, gt_rgb, label, target_albedo, 0 if mode == "object" else 1)
 
 
-def sample_pdf(bins, weights, n_samples, u=None, want_inds=False, want_cdf=False):
+def sample_pdf(bins, weights, n_samples, u=None, want_inds=False, want_cdf=False, seed=None):
+    """seed: draw u ~ U[0,1) inside the kernel (inrf_sample_pdf_rng) instead of taking a `u` tensor / the deterministic u."""
     bins, weights = _f32(bins, "bins"), _f32(weights, "weights")
     N, B = bins.shape
     if weights.shape != (N, B - 1):
         raise ValueError("weights must be [N, bins-1]")
+    if seed is not None and u is None and not want_inds and not want_cdf:
+        samples = torch.empty(N, n_samples, dtype=torch.float32, device=bins.device)
+        with torch.cuda.device(bins.device):
+            check(_lib.lib().inrf_sample_pdf_rng(_ptr(bins), _ptr(weights), B - 1, int(seed), N, B, n_samples, _ptr(samples), _stream()))
+        return samples, None, None
     u = None if u is None else _f32(u, "u")
     u_det = linspace01(n_samples, bins.device) if u is None else None
     samples = torch.empty(N, n_samples, dtype=torch.float32, device=bins.device)
@@ -380,10 +412,16 @@ def merge_sorted(z_a, z_b, want_std=True):
     return out, std
 
 
-def coarse_z(rays, n_samples, lindisp=False, t_rand=None):
+def coarse_z(rays, n_samples, lindisp=False, t_rand=None, seed=None):
+    """seed: stratified jitter drawn inside the kernel (inrf_coarse_z_rng) instead of a `t_rand` tensor."""
     rays = _f32(rays, "rays")
     N = rays.shape[0]
     z = torch.empty(N, n_samples, dtype=torch.float32, device=rays.device)
+    if seed is not None and t_rand is None:
+        with torch.cuda.device(rays.device):
+            check(_lib.lib().inrf_coarse_z_rng(_ptr(rays), _ptr(linspace01(n_samples, rays.device)), int(seed), N, n_samples,
+                                               int(bool(lindisp)), _ptr(z), _stream()))
+        return z
     t_rand = None if t_rand is None else _f32(t_rand, "t_rand")
     with torch.cuda.device(rays.device):
         check(_lib.lib().inrf_coarse_z(_ptr(rays), _ptr(linspace01(n_samples, rays.device)), _ptr(t_rand), N, n_samples,
@@ -480,6 +518,44 @@ def render_chunk(rays, packed_coarse, packed_fine, variant=0, n_classes=0, n_sam
                                 _ptr(noise_coarse), _ptr(noise_fine), _ptr(out["rec_coarse"]), _ptr(out.get("rec_fine")),
                                 _ptr(out.get("z_std")), _ptr(out.get("raw_coarse")), _ptr(out.get("raw_fine")),
                                 _ptr(out.get("z_fine")), _ptr(out.get("weights_fine")), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def frame_camera_ok(n_samples, n_importance, precision=None):
+    """True when inrf_render_fwd_camera covers this configuration (see include/inrf.h)."""
+    import os
+    return _prec(precision) == PREC_TC and os.environ.get("INRF_NO_FUSE", "0")[:1] != "1" and n_samples % 32 == 0 \
+        and (n_importance == 0 or (n_samples == 64 and n_importance == 128))
+
+
+def render_frame_camera(H, W, K, c2w, near, far, packed_coarse, packed_fine, device, pix0=0, n=None, variant=0, n_classes=0,
+                        n_samples=64, n_importance=128, lindisp=False, white_bkgd=False, pe_scalar_factor=1.0,
+                        convention="opengl", depth_type="z", want_z=False):
+    """inrf_render_fwd_camera: pixels [pix0, pix0 + n) of the frame seen by (K, c2w), rays generated inside the kernels
+    (no [N,11] table).  Returns the same dict as render_chunk.  Raises InrfError (INRF_EUNSUPPORTED) for configurations
+    the fused kernel does not cover - callers then build the rays and use render_chunk."""
+    n = H * W - pix0 if n is None else int(n)
+    m = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].contiguous()
+    cam = _lib.Camera(H=int(H), W=int(W), fx=float(K[0][0]), fy=float(K[1][1]), cx=float(K[0][2]), cy=float(K[1][2]),
+                      near_=float(near), far_=float(far), convention=1 if convention == "opencv" else 0,
+                      euclidean=1 if depth_type == "euclidean" else 0)
+    for i, v in enumerate(m.reshape(-1).tolist()):
+        cam.c2w[i] = float(v)
+    cfg = RenderCfg(variant=variant, n_classes=n_classes, n_samples=n_samples, n_importance=n_importance, lindisp=int(bool(lindisp)),
+                    white_bkgd=int(bool(white_bkgd)), endpoint_feat=0, precision=_DEFAULT_PRECISION, pe_scalar_factor=float(pe_scalar_factor))
+    L = _lib.lib()
+    ws = _Workspace.get(device, check(L.inrf_render_workspace_bytes(C.byref(cfg), n)))
+    new = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)  # noqa: E731
+    out = {"rec_coarse": new(n, REC_BASE + n_classes)}
+    if n_importance > 0:
+        out["rec_fine"], out["z_std"] = new(n, REC_BASE + n_classes), new(n)
+        if want_z:
+            out["z_fine"] = new(n, n_samples + n_importance)
+    with torch.cuda.device(device):
+        check(L.inrf_render_fwd_camera(C.byref(cam), int(pix0), n, _ptr(packed_coarse), _ptr(packed_fine), C.byref(cfg),
+                                       _ptr(linspace01(n_samples, device)), _ptr(linspace01(n_importance, device)) if n_importance > 0 else None,
+                                       _ptr(out["rec_coarse"]), _ptr(out.get("rec_fine")), _ptr(out.get("z_std")), _ptr(out.get("z_fine")),
+                                       _ptr(ws), ws.numel(), _stream()))
     return out
 
 

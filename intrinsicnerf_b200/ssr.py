@@ -106,12 +106,62 @@ def rays_for_batch(index_hw, T_c2w, height, width, fx, fy, cx, cy, near, far, de
     return ops.rays_from_pixels(index_hw.reshape(-1), height, width, fx, fy, cx, cy, T_c2w, near, far, convention, depth_type)
 
 
+class LazyRawDict(dict):
+    """The dict volumetric_rendering returns in eval mode.  The reference always returns raw_coarse / raw_fine
+    (trainer.py:777-802) but reads them only for a tensorboard histogram every 1000 training steps (quirk A6,
+    trainer.py:1024-1028); materialising them costs 40 KB/ray and forces the stage-by-stage path.  Here they are
+    ordinary keys whose tensors are produced on first access (one extra stage-path render of the same rays)."""
+
+    def __init__(self, base, thunk, names):
+        super().__init__(base)
+        self._thunk, self._lazy = thunk, set(names)
+        for n in names:
+            dict.__setitem__(self, n, None)
+
+    def force(self):
+        if self._lazy:
+            vals = self._thunk()
+            for n in list(self._lazy):
+                dict.__setitem__(self, n, vals[n])
+            self._lazy = set()
+        return self
+
+    def lazy_names(self):
+        return set(self._lazy)
+
+    def eager_items(self):
+        return [(k, dict.__getitem__(self, k)) for k in dict.keys(self) if k not in self._lazy]
+
+    def __getitem__(self, k):
+        if k in self._lazy:
+            self.force()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return dict.items(self.force())
+
+    def values(self):
+        return dict.values(self.force())
+
+
+def _map_lazy(pieces, combine):
+    """Apply `combine(list of tensors) -> tensor` key by key over a list of result dicts, keeping lazy keys lazy."""
+    first = pieces[0]
+    if not isinstance(first, LazyRawDict):
+        return {k: combine([p[k] for p in pieces]) for k in first}
+    names = first.lazy_names()
+    base = {k: combine([dict.__getitem__(p, k) for p in pieces]) for k, _ in first.eager_items()}
+    if not names:
+        return base
+    return LazyRawDict(base, lambda: {n: combine([p[n] for p in pieces]) for n in names}, names)
+
+
 def batchify_rays(render_fn, rays_flat, chunk=1024 * 32):
-    pieces = {}
-    for i in range(0, rays_flat.shape[0], chunk):
-        for k, v in render_fn(rays_flat[i:i + chunk]).items():
-            pieces.setdefault(k, []).append(v)
-    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in pieces.items()}
+    pieces = [render_fn(rays_flat[i:i + chunk]) for i in range(0, rays_flat.shape[0], chunk)]
+    return _map_lazy(pieces, lambda v: v[0] if len(v) == 1 else torch.cat(v, 0))
 
 
 class SSRRenderer:
@@ -120,7 +170,7 @@ class SSRRenderer:
     def render_rays(self, flat_rays):
         shape = flat_rays.shape
         out = batchify_rays(self.volumetric_rendering, flat_rays, self.chunk)
-        return {k: torch.reshape(v, list(shape[:-1]) + list(v.shape[1:])) for k, v in out.items()}
+        return _map_lazy([out], lambda v: torch.reshape(v[0], list(shape[:-1]) + list(v[0].shape[1:])))
 
     def volumetric_rendering(self, ray_batch):
         N, dev = ray_batch.shape[0], ray_batch.device
@@ -128,25 +178,28 @@ class SSRRenderer:
         C = self.num_valid_semantic_class if self.enable_semantic else 0
         training = bool(self.training)
         jitter = self.perturb > 0. and training
-        t_rand = torch.rand(N, Sc, device=dev) if jitter else None
         std = self.raw_noise_std if training else 0
-        noise_c = torch.randn(N, Sc, device=dev) * std if std > 0 else None
         det = (self.perturb == 0.) or (not training)
+        coarse, fine = self.ssr_net_coarse, self.ssr_net_fine
+        if isinstance(coarse, Semantic_NeRF) and (coarse.needs_grad() or (fine is not None and fine.needs_grad())) \
+                and isinstance(self.embed_fn, Embedder) and isinstance(self.embeddirs_fn, Embedder):
+            # training step: every random tensor of the reference (trainer.py:737-746, rays.py:198, model_utils.py:70-72)
+            # is generated inside the stage kernels from one seed per step - no generator launches, no [N,S] tensors
+            return self._volumetric_rendering_train(ray_batch, C, jitter, det, std, ops.next_seed())
+        t_rand = torch.rand(N, Sc, device=dev) if jitter else None
+        noise_c = torch.randn(N, Sc, device=dev) * std if std > 0 else None
         u = None if (det or Sf == 0) else torch.rand(N, Sf, device=dev)
         noise_f = torch.randn(N, Sc + Sf, device=dev) * std if (std > 0 and Sf > 0) else None
-        coarse, fine = self.ssr_net_coarse, self.ssr_net_fine
         if not (isinstance(coarse, Semantic_NeRF) and (fine is None or isinstance(fine, Semantic_NeRF))
                 and isinstance(self.embed_fn, Embedder) and isinstance(self.embeddirs_fn, Embedder)):
             raise NotImplementedError("SSRRenderer needs intrinsicnerf_b200 Semantic_NeRF networks and embedders "
                                       "(build them with create_ssr); there is no fallback path")
-        if coarse.needs_grad() or (fine is not None and fine.needs_grad()):
-            return self._volumetric_rendering_train(ray_batch, t_rand, u, noise_c, noise_f, C)
-        o = ops.render_chunk(ray_batch, coarse.packed(), (fine or coarse).packed() if Sf > 0 else None,
-                             variant=coarse.variant, n_classes=C, n_samples=Sc, n_importance=Sf, lindisp=False,
-                             white_bkgd=self.white_bkgd, endpoint=bool(self.endpoint_feat) and Sf > 0,
-                             pe_scalar_factor=self.embed_fn.scalar_factor, t_rand=t_rand, u=u, noise_coarse=noise_c,
-                             noise_fine=noise_f, want_raw=True)
-        ret = {"raw_coarse": o["raw_coarse"]}
+        kw = dict(variant=coarse.variant, n_classes=C, n_samples=Sc, n_importance=Sf, lindisp=False, white_bkgd=self.white_bkgd,
+                  endpoint=bool(self.endpoint_feat) and Sf > 0, pe_scalar_factor=self.embed_fn.scalar_factor, t_rand=t_rand, u=u,
+                  noise_coarse=noise_c, noise_fine=noise_f)
+        pc, pf = coarse.packed(), ((fine or coarse).packed() if Sf > 0 else None)
+        o = ops.render_chunk(ray_batch, pc, pf, **kw)          # fused kernel when the configuration allows: no raw tensor
+        ret = {}
         names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual")
         for k in names:
             ret[k + "_coarse"] = _split_rec(o["rec_coarse"], k)
@@ -158,9 +211,12 @@ class SSRRenderer:
             if C > 0:
                 ret["sem_logits_fine"] = o["rec_fine"][:, 13:13 + C]
             ret["z_std"] = o["z_std"]
-            ret["raw_fine"] = o["raw_fine"]
             if self.endpoint_feat:
                 ret["feat_map_fine"] = o["rec_fine"][:, 13 + C:13 + C + 128]
+
+        def raws():                                             # raw_coarse / raw_fine on first access (quirk A6)
+            r = ops.render_chunk(ray_batch, pc, pf, want_raw=True, **kw)
+            return {"raw_coarse": r["raw_coarse"], "raw_fine": r.get("raw_fine")}
         # the reference's per-key "contains nan or inf" report (trainer.py:804-806) with ONE host synchronisation
         # instead of two per key
         keys = list(ret)
@@ -168,17 +224,18 @@ class SSRRenderer:
         for k, b in zip(keys, bad):
             if b:
                 print(f"! [Numerical Error] {k} contains nan or inf.")
-        return ret
+        return LazyRawDict(ret, raws, ("raw_coarse", "raw_fine") if Sf > 0 else ("raw_coarse",))
 
-    def _volumetric_rendering_train(self, ray_batch, t_rand, u, noise_c, noise_f, C):
+    def _volumetric_rendering_train(self, ray_batch, C, jitter, det, std, seed):
         """Training step (trainer.py:717-808 under autograd): the stage kernels composed in PyTorch with the
-        differentiable field network (ops.MlpFn) and compositing (ops.CompositeFn)."""
+        differentiable field network (ops.MlpTcFn / MlpFn) and compositing (ops.CompositeFn); jitter, u and the sigma
+        noise are drawn inside those kernels from `seed` (include/inrf.h: inrf_*_rng)."""
         Sc, Sf = self.N_samples, self.N_importance
         rays_o, rays_d, viewdirs = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, 8:11]
-        z = ops.coarse_z(ray_batch, Sc, False, t_rand)
+        z = ops.coarse_z(ray_batch, Sc, False, None, seed if jitter else None)
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
         raw_c = run_network(pts, viewdirs, self.ssr_net_coarse, self.embed_fn, self.embeddirs_fn)
-        rec_c, w_c = ops.composite(raw_c, z, rays_d, noise_c, self.white_bkgd, C, False)
+        rec_c, w_c = ops.composite(raw_c, z, rays_d, None, self.white_bkgd, C, False, (std, seed, False))
         ret = {"raw_coarse": raw_c}
         names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual")
         for k in names:
@@ -187,12 +244,12 @@ class SSRRenderer:
             ret["sem_logits_coarse"] = rec_c[:, 13:13 + C]
         if Sf > 0:
             z_mid = .5 * (z[:, 1:] + z[:, :-1])
-            z_samples = ops.sample_pdf(z_mid, w_c[:, 1:-1].detach(), Sf, u)[0]
+            z_samples = ops.sample_pdf(z_mid, w_c[:, 1:-1].detach(), Sf, None, seed=None if det else seed)[0]
             z_f, z_std = ops.merge_sorted(z, z_samples)
             pts = rays_o[:, None, :] + rays_d[:, None, :] * z_f[:, :, None]
             ep = bool(self.endpoint_feat)
             raw_f = run_network(pts, viewdirs, with_endpoint(self.ssr_net_fine, ep), self.embed_fn, self.embeddirs_fn)
-            rec_f, _ = ops.composite(raw_f, z_f, rays_d, noise_f, self.white_bkgd, C, ep)
+            rec_f, _ = ops.composite(raw_f, z_f, rays_d, None, self.white_bkgd, C, ep, (std, seed, True))
             for k in names:
                 ret[k + "_fine"] = _split_rec(rec_f, k)
             if C > 0:

@@ -107,3 +107,51 @@ def test_fused_chunking_and_sharding_are_bitwise_neutral(dev):
     torch.cuda.synchronize()
     for k in ("rec_coarse", "rec_fine", "z_std"):
         assert _same(whole[k], torch.cat([p[k] for p in parts], 0)), k
+
+
+@pytest.mark.parametrize("conv,dt", [("opengl", "z"), ("opencv", "z"), ("opencv", "euclidean")])
+def test_in_kernel_ray_generation_equals_ray_table(dev, conv, dt):
+    """inrf_render_fwd_camera (rays generated per pixel inside the kernels) against the same frame
+    rendered from the [H*W, 11] table that inrf_rays_from_pixels writes: bit-identical records, any pixel sub-range."""
+    from intrinsicnerf_b200 import ops
+    coarse, fine, _, _ = build_nets("object")
+    H, W = 37, 53
+    K = orc.blender_intrinsics(H, W)
+    c2w = torch.as_tensor(orc.pose_spherical(40.0, -30.0, 4.0))[:3, :4]
+    rays = ops.rays_from_pixels(None, H, W, K[0][0], K[1][1], K[0][2], K[1][2], c2w, 2.0, 6.0, conv, dt, dev)
+    want = ops.render_chunk(rays, coarse.packed(), fine.packed(), white_bkgd=True, want_z=True)
+    n0 = ops.launch_count()
+    got = ops.render_frame_camera(H, W, K, c2w, 2.0, 6.0, coarse.packed(), fine.packed(), dev, white_bkgd=True, convention=conv,
+                                  depth_type=dt, want_z=True)
+    assert ops.launch_count() - n0 == 2                  # no k_get_rays
+    part = ops.render_frame_camera(H, W, K, c2w, 2.0, 6.0, coarse.packed(), fine.packed(), dev, pix0=700, n=333, white_bkgd=True,
+                                   convention=conv, depth_type=dt)
+    torch.cuda.synchronize()
+    ops.poll_status()
+    for k in ("rec_coarse", "rec_fine", "z_std", "z_fine"):
+        assert _same(got[k], want[k]), k
+    assert _same(part["rec_fine"], want["rec_fine"][700:1033])
+
+
+def test_render_with_c2w_uses_the_camera_path_and_matches_rays_path(dev):
+    """object_level.render(c2w=...) (run_nerf.py:100-103): same maps as render(rays=get_rays(...)) - which goes through the
+    reference's own torch ray generation - to the ray-generation rounding."""
+    from intrinsicnerf_b200 import object_level as ol, ops
+    coarse, fine, _, _ = build_nets("object")
+    e, _ = ol.get_embedder(10, 0)
+    ed, _ = ol.get_embedder(4, 0)
+    kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=ol._FusedQuery(e, ed, 65536), N_samples=64, N_importance=128,
+              perturb=0., white_bkgd=True, raw_noise_std=0.)
+    H = W = 24
+    K = orc.blender_intrinsics(H, W)
+    c2w = torch.as_tensor(orc.pose_spherical(-120.0, -30.0, 4.0))[:3, :4].to(dev)
+    coarse.packed(), fine.packed()
+    n0 = ops.launch_count()
+    a = ol.render(H, W, K, chunk=200, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+    assert ops.launch_count() - n0 == 2 * 3              # three chunks, two launches each, no ray-table kernel
+    b = ol.render(H, W, K, chunk=4096, rays=ol.get_rays(H, W, K, c2w), ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+    torch.cuda.synchronize()
+    for x, y in zip(a[:6], b[:6]):
+        assert x.shape == y.shape
+        assert float((x - y).abs().max()) < 2e-5
+    assert set(a[6]) == set(b[6])
