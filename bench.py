@@ -351,7 +351,7 @@ def run_room0(args, rank, local, world, dev, dist):
 
     def step_e2e():
         r = rays_host.to(dev, non_blocking=True)
-        with torch.no_grad():
+        with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):     # (the renderer mirrors the reference's NaN report prints)
             d = t.render_rays(r)
         for dst, k in zip(out_host, ("rgb_fine", "depth_fine", "sem_logits_fine")):
             dst.copy_(d[k].reshape(n_rays, -1), non_blocking=True)

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libinrf.so")
-SOURCES = ["pack.cu", "stages.cu", "mlp_fp32.cu", "mlp_bwd_fp32.cu", "mlp_tc.cu", "mlp_tc2.cu", "train_tc.cu", "cluster.cu", "loss.cu", "frame.cu", "status.cu", "api.cu"]
+SOURCES = ["pack.cu", "stages.cu", "mlp_fp32.cu", "mlp_bwd_fp32.cu", "mlp_tc.cu", "train_tc.cu", "cluster.cu", "loss.cu", "frame.cu", "status.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

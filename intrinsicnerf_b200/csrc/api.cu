@@ -23,12 +23,7 @@ int launch_get_rays(int H, int W, float fx, float fy, float cx, float cy, const 
 
 static int run_mlp(const MlpArgs& a, int precision, cudaStream_t st) {
   if (precision == INRF_PREC_FP32) return launch_mlp_fp32(a, st);
-  if (precision == INRF_PREC_TC) {
-    // INRF_TC_PAIR=1: experimental CTA-pair kernel (mlp_tc2.cu, two tiles in flight per CTA); parity-green but
-    // slower than k_mlp_tc so far - see DESIGN.md section 4b
-    static const bool pair = getenv("INRF_TC_PAIR") != nullptr && getenv("INRF_TC_PAIR")[0] == '1';
-    return pair ? launch_mlp_tc2(a, st) : launch_mlp_tc(a, st);
-  }
+  if (precision == INRF_PREC_TC) return launch_mlp_tc(a, st);
   set_error("unknown precision %d", precision);
   return INRF_EINVAL;
 }

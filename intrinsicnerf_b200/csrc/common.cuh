@@ -318,6 +318,5 @@ struct TcBwdArgs {
 };
 int64_t tc_bwd_workspace_bytes(int variant, int n_classes, int64_t M);
 int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st);
-int launch_mlp_tc2(const MlpArgs& a, cudaStream_t st);
 
 }  // namespace inrf

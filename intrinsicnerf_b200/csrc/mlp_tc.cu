@@ -537,13 +537,27 @@ __device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, i
       if (s0 == 0) { rs.zc[0] = zs; rs.wc[0] = w; } else { rs.zc[1] = zs; rs.wc[1] = w; }
     }
     if (P.C > 0) {                                       // semantic logits: lanes stride over channels, weights by shuffle
-      for (int j = 0; j < 32; ++j) {
-        const float wj = __shfl_sync(FULLMASK, w, j);
-        const float* rj = ring + (size_t)(q * 32 + j) * P.out_ch + INRF_RAW_BASE;
+      const float* r0 = ring + (size_t)(q * 32) * P.out_ch + INRF_RAW_BASE;
+      const int nslab = (P.C + 31) >> 5;                 // channel slabs of 32 (C <= 112: at most 4)
+      for (int j0 = 0; j0 < 32; j0 += 8) {               // 8 rows per batch: their loads are independent and issue back to back
+        float v[8][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = lane + 32 * i;
-          if (e < P.C) rs.ex[i] += wj * rj[e];
+        for (int jj = 0; jj < 8; ++jj) {
+          const float* rj = r0 + (size_t)(j0 + jj) * P.out_ch;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = lane + 32 * i;
+            v[jj][i] = (i < nslab && e < P.C) ? rj[e] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {                 // same accumulation order as k_raw2outputs: samples ascending
+          const float wj = __shfl_sync(FULLMASK, w, j0 + jj);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = lane + 32 * i;
+            if (i < nslab && e < P.C) rs.ex[i] += wj * v[jj][i];
+          }
         }
       }
     }

@@ -1,5 +1,5 @@
 // Thin PTX wrappers for the sm_100a tensor-core kernels of the training path (train_tc.cu): mbarrier, bulk copies,
-// tcgen05 alloc / mma / commit / ld, UMMA descriptors.  (mlp_tc.cu / mlp_tc2.cu carry their own tuned copies.)
+// tcgen05 alloc / mma / commit / ld, UMMA descriptors.  (mlp_tc.cu carries its own tuned copies.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

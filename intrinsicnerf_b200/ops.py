@@ -30,14 +30,25 @@ def poll_status():
 _SEED_STATE = [None, 0]
 
 
-def next_seed():
-    """Seed for one in-kernel random tensor (inrf_*_rng): a pure host-side function of torch's seed and a call counter,
-    so torch.manual_seed(s) makes a training run reproducible without any generator kernel being launched."""
-    base = torch.initial_seed()
-    if _SEED_STATE[0] != base:
-        _SEED_STATE[0], _SEED_STATE[1] = base, 0
-    _SEED_STATE[1] += 1
-    return (base * 0x9E3779B97F4A7C15 + _SEED_STATE[1] * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+def next_seed(device=None):
+    """Seed for one step's in-kernel random tensors (inrf_*_rng).  Derived on the host from torch's CUDA generator -
+    its seed and Philox offset, which torch.manual_seed resets - and the offset is advanced, exactly as a torch.rand
+    call would consume it: runs are reproducible from torch.manual_seed, and no generator kernel is launched.
+    (While a CUDA graph is being captured the generator cannot be read; a host-side counter is used instead and the
+    captured step replays the same draws - pass fresh seeds by re-capturing or use the tensor arguments for that.)"""
+    try:
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        gen = torch.cuda.default_generators[idx]
+        off = int(gen.get_offset())
+        gen.set_offset(off + 4)
+        base, ctr = int(gen.initial_seed()), off // 4 + 1
+    except Exception:
+        base = torch.initial_seed()
+        if _SEED_STATE[0] != base:
+            _SEED_STATE[0], _SEED_STATE[1] = base, 0
+        _SEED_STATE[1] += 1
+        ctr = _SEED_STATE[1]
+    return (base * 0x9E3779B97F4A7C15 + ctr * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
 
 
 def launch_count():

@@ -146,10 +146,11 @@ def test_render_with_c2w_uses_the_camera_path_and_matches_rays_path(dev):
     K = orc.blender_intrinsics(H, W)
     c2w = torch.as_tensor(orc.pose_spherical(-120.0, -30.0, 4.0))[:3, :4].to(dev)
     coarse.packed(), fine.packed()
-    n0 = ops.launch_count()
-    a = ol.render(H, W, K, chunk=200, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, **kw)
-    assert ops.launch_count() - n0 == 2 * 3              # three chunks, two launches each, no ray-table kernel
-    b = ol.render(H, W, K, chunk=4096, rays=ol.get_rays(H, W, K, c2w), ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+    with torch.no_grad():                                # as render_path does (run_nerf.py:167); under autograd render() trains
+        n0 = ops.launch_count()
+        a = ol.render(H, W, K, chunk=200, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True, **kw)
+        assert ops.launch_count() - n0 == 2 * 3          # three chunks, two launches each, no ray-table kernel
+        b = ol.render(H, W, K, chunk=4096, rays=ol.get_rays(H, W, K, c2w), ndc=False, near=2., far=6., use_viewdirs=True, **kw)
     torch.cuda.synchronize()
     for x, y in zip(a[:6], b[:6]):
         assert x.shape == y.shape

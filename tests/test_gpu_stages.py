@@ -275,20 +275,6 @@ def test_mlp_backward_matches_autograd(dev, variant, C, endpoint, monkeypatch):
     assert rel_err(p.grad.cpu(), 2 * p64[name].grad.float(), floor=float(p64[name].grad.abs().max())) < 1e-3
 
 
-def test_pair_kernel_matches_fp32_kernel():
-    """The experimental CTA-pair tensor-core kernel (k_mlp_tc2, INRF_TC_PAIR=1 - read once per process, hence
-    the subprocess) agrees with the strict-fp32 kernel on both variants, ragged tile counts and the endpoint
-    feature rows (tests/tools/tc_debug.py; bar: 1e-3 absolute on every raw channel)."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, INRF_TC_PAIR="1", INRF_TC_CHECK="1")
-    out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "tc_debug.py")], env=env, cwd=root,
-                         capture_output=True, text=True, timeout=600)
-    assert "TC_DEBUG PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
-
-
 # ---- SURVEY section 8f row 1: ray generation for whole images and for sampled pixels ------------------------
 @pytest.mark.parametrize("conv", ["opencv", "opengl"])
 @pytest.mark.parametrize("dt", ["z", "euclidean"])
