@@ -22,7 +22,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_uniform", "smsp__cycles_active.avg"]
 
 
-def launches(tag, csv_name="launches.csv", out_name="launches_summary", command="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"):
+def launches(tag, csv_name="launches.csv", out_name="launches_summary", command="python bench.py --views 1 --steps 1 --warmup 3 --no-cpu-baseline --no-config5"):
     src = os.path.join(GP, csv_name)
     if not os.path.exists(src):
         return
@@ -68,11 +68,35 @@ def full(tag, name):
     print("wrote", name)
 
 
+def traffic(name="prof_mlp_tc_fused_fine", rows=40000 * 192):
+    """profiles/mlp_tc_traffic.json (read by bench.py: roofline.traffic) from the full capture of the fused fine launch."""
+    import json
+    rep = os.path.join(GP, f"{name}.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(raw)))
+    hdr, units, row = rd[0], rd[1], rd[2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(metric):
+        i = hdr.index(metric)
+        return float(row[i].replace(",", "")) * scale[units[i]]
+    rd_b, wr_b = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    json.dump({"bytes_per_row": round((rd_b + wr_b) / rows, 3),
+               "source": f"ncu --set full --clock-control none of the FUSED fine-pass k_mlp_tc<2,false> launch on 40 000 rays "
+                         f"(profiles/r02_{name}_raw.md): ({rd_b / 1e6:.2f} MB dram read + {wr_b / 1e6:.2f} MB dram written) / {rows} rows; "
+                         f"algorithmic 4 B (depth) + 44/192 B (ray) in, 52/192 B out per row"},
+              open(os.path.join(OUT, "mlp_tc_traffic.json"), "w"))
+    print("wrote mlp_tc_traffic.json")
+
+
 if __name__ == "__main__":
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
     launches(tag, "launches_train.csv", "launches_train_summary", "python tests/tools/train_target.py  (3 SSR training steps: render + backward, 1024 rays)")
     for n in sorted(os.listdir(GP)):
         if n.endswith(".ncu-rep"):
             full(tag, n[:-8])
+    traffic()
