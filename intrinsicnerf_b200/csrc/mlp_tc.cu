@@ -85,7 +85,6 @@ struct Params {
   int out_ch, C, sem_rows;
   int bias_mma;                   // 1: accumulators are initialised with the bias by an MMA (default)
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
-  int epi;                        // epilogue drain schedule: 0 = every warp owns 32 columns of every chunk, 1 / 2 = chunk per warp group
   int fuse;                       // 1: composite (and resample) in-kernel, CTAs walk CONTIGUOUS tiles (whole rays per CTA)
   FuseArgs f;
   int* dbg;                       // [16] per-launch abort / claim words (device, cleared before every launch)
@@ -970,41 +969,7 @@ template <int MODE>
 __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst0, int n_chunks,
                                           const RowAddr& ra, int jj, int lane, Sync& sy, int free_bar0, int ready_bar0,
                                           const float* alpha_smem, float* sigma_acc, float* gout0, unsigned char* gimg0,
-                                          uint32_t& amax, int epi) {
-  if (epi != 0) {
-    // Chunk-per-warp-group drain: warp group jj (4 warps = all 128 rows) owns the whole 64-column chunks jj, jj+2.
-    // tcgen05.wait::ld waits for ALL of a thread's loads, so one thread cannot convert chunk c while its load of chunk c+1
-    // is in flight - but two warp groups can: group 0 loads chunk 0 (32 KB through the 64 B/clk TMEM read port) while
-    // group 1's load of chunk 1 queues behind it, the first K chunk of the next layer is released after a quarter of the
-    // drain instead of half, and the port never idles while a group converts and stores.  epi == 2 additionally orders the
-    // groups' loads explicitly (named barriers: "chunk c loaded" -> the other group issues chunk c+1).
-    bool first = true;
-#pragma unroll 1
-    for (int c = jj; c < n_chunks; c += 2) {
-      if (epi == 2 && c > 0) asm volatile("bar.sync %0, 256;" ::"r"(2 + ((c - 1) & 3)) : "memory");
-      uint32_t v0[32], v1[32];
-      tmem_ld32(taddr + c * 64, v0);
-      tmem_ld32(taddr + c * 64 + 32, v1);
-      tmem_ld_wait();
-      if (epi == 2 && c + 1 < n_chunks) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (c & 3)) : "memory");
-      if (free_bar0 >= 0 && first) sy.wait(free_bar0);
-      first = false;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int col = c * 64 + half * 32;
-        const uint32_t* v = half == 0 ? v0 : v1;
-        float* g = (MODE == 2 && gout0) ? gout0 + col : nullptr;
-        const float* aw = (MODE == 1) ? alpha_smem + col : nullptr;
-        unsigned char* gi = gimg0 ? gimg0 + c * IMG_BYTES : nullptr;
-        if (add_bias) epi_store32<true, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, half * 4, aw, sigma_acc, g, gi, amax);
-        else epi_store32<false, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, half * 4, aw, sigma_acc, g, gi, amax);
-      }
-      fence_async_smem();
-      tc_fence_before();
-      if (ready_bar0 >= 0) warp_arrive(sy.addr(ready_bar0 + c), lane);
-    }
-    return;
-  }
+                                          uint32_t& amax) {
 #pragma unroll 1
   for (int cp = 0; cp < n_chunks; cp += 2) {
     uint32_t v0[32], v1[32];
@@ -1062,8 +1027,8 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     for (int l = 0; l < 8; ++l) {
       sy.wait(B_ACC_FULL + (l & 1));
       tc_fence_after();
-      if (l == 7) epi_layer<1>(add_bias, lane_addr + A1, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28), amax, P.epi);
-      else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l), amax, P.epi);
+      if (l == 7) epi_layer<1>(add_bias, lane_addr + A1, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28), amax);
+      else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l), amax);
     }
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
@@ -1072,17 +1037,17 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
       tc_fence_after();
     if (P.a.endpoint)
       epi_layer<2>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
-                   valid ? grow + INRF_RAW_BASE + P.C : nullptr, SLOT(IS_V), amax, P.epi);
+                   valid ? grow + INRF_RAW_BASE + P.C : nullptr, SLOT(IS_V), amax);
     else
-      epi_layer<0>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V), amax, P.epi);
+      epi_layer<0>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V), amax);
     warp_arrive(sy.addr(B_V_READY), lane);
     // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ---------------------------------
     sy.wait(B_ACC_FULL + 1);
       tc_fence_after();
-    epi_layer<0>(add_bias, lane_addr + A1, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS), amax, P.epi);
+    epi_layer<0>(add_bias, lane_addr + A1, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS), amax);
     // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
     if (sem)
-      epi_layer<0>(add_bias, lane_addr + A0 + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1), amax, P.epi);
+      epi_layer<0>(add_bias, lane_addr + A0 + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1), amax);
 #undef SLOT
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
@@ -1168,7 +1133,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), CL); }
     mbar_init(sy.addr(B_F_READY), 4); mbar_init(sy.addr(B_F_FREE), 1);
-    for (int c = 0; c < 4; ++c) mbar_init(sy.addr(B_A_READY + c), P.epi ? 4 : 8);
+    for (int c = 0; c < 4; ++c) mbar_init(sy.addr(B_A_READY + c), 8);
     mbar_init(sy.addr(B_H_FREE), 1);
     mbar_init(sy.addr(B_ACC_FULL + 0), 1); mbar_init(sy.addr(B_ACC_FULL + 1), 1);
     mbar_init(sy.addr(B_V_READY), 8);
@@ -1289,8 +1254,6 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   if (P.status == nullptr) return INRF_ECUDA;
   static const long long wd_env = getenv("INRF_TC_WATCHDOG_CYCLES") ? atoll(getenv("INRF_TC_WATCHDOG_CYCLES")) : 3000000000LL;
   static int faults_left = getenv("INRF_TC_FAULT") ? atoi(getenv("INRF_TC_FAULT")) : 0;   // test hook: fault the first n launches
-  static const int epi_env = getenv("INRF_TC_EPI") ? atoi(getenv("INRF_TC_EPI")) : 0;
-  P.epi = (epi_env == 1 || epi_env == 2) ? epi_env : 0;
   P.watchdog = wd_env > 0 ? wd_env : 3000000000LL;
   P.fault = faults_left > 0 ? 1 : 0;
   if (faults_left > 0) --faults_left;
