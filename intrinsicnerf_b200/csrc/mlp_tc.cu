@@ -37,7 +37,8 @@ namespace tc {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 512;
-constexpr int NS = 4;                       // weight ring stages of TC_SLOT_BYTES (32 KB)
+constexpr int NS = 4;                       // weight ring stages of TC_SLOT_BYTES (32 KB), shared-memory-activation kernel
+constexpr int NS_MAX = 6;                   // TS variant: no H buffer, so the ring gets its 64 KB (runtime Params.ns)
 constexpr int CHUNK = 16384;                // 128 rows x 64 fp16, SWIZZLE_128B
 // shared memory map (bytes)
 constexpr int SM_H = 0;                     // 4 chunks: hidden activations (A operand), in place
@@ -58,9 +59,9 @@ constexpr int TCB_VIEWS = 2048, TCB_SEM1 = 2176, TCB_ALBSH = 2304, TCB_ALPHA_W =
 
 // barrier ids
 enum {
-  B_WFULL = 0,                 // [NS] ring slot filled (tx bytes)
-  B_WEMPTY = B_WFULL + NS,     // [NS] ring slot consumed (tcgen05.commit)
-  B_F_READY = B_WEMPTY + NS,   // PE|DIR tiles of the next tile written (128 front-end threads)
+  B_WFULL = 0,                 // [ns] ring slot filled (tx bytes)
+  B_WEMPTY = B_WFULL + NS_MAX, // [ns] ring slot consumed (tcgen05.commit)
+  B_F_READY = B_WEMPTY + NS_MAX,   // PE|DIR tiles of the next tile written (128 front-end threads)
   B_F_FREE,                    // PE|DIR|V region no longer read by the tensor core
   B_A_READY,                   // [4] H chunk c written by all 8 epilogue warps (256 threads)
   B_H_FREE = B_A_READY + 4,    // tail only: the tensor core finished reading H (before it is overwritten
@@ -85,6 +86,8 @@ struct Params {
   int out_ch, C, sem_rows;
   int bias_mma;                   // 1: accumulators are initialised with the bias by an MMA (default)
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
+  int ts_fine;                    // TS variant: 1 = one K chunk per TMEM load batch (INRF_TC_TS=2)
+  int ns;                         // weight ring stages in use (4, or 6 in the TS variant)
   int fuse;                       // 1: composite (and resample) in-kernel, CTAs walk CONTIGUOUS tiles (whole rays per CTA)
   FuseArgs f;
   int* dbg;                       // [16] per-launch abort / claim words (device, cleared before every launch)
@@ -160,6 +163,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
                : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory ("TS" form): lanes = the 128 rows, 32-bit column j of the operand holds K elements 2j (low
+// half) and 2j+1 of the row, so one K=16 step reads 8 columns (cute::SM100_MMA_F16BF16_TS / tmem_frg_1sm<half, half>)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp):
 //  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024>>4 |
@@ -726,7 +743,7 @@ __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t sme
         }
       }
       __syncwarp();
-      slot = (slot + 1 == NS) ? 0 : slot + 1;
+      slot = (slot + 1 == P.ns) ? 0 : slot + 1;
     }
   }
 }
@@ -739,6 +756,8 @@ struct Issuer {
   Sync& sy;
   uint32_t smem_base, tmem;
   int slot;
+  int ns;
+  uint32_t ones;          // shared-memory address of the constant "ones" A tile (absolute: smem_base may be a shifted role base)
   int cl;
   int bias_mma;
   int no_weights;
@@ -776,7 +795,7 @@ struct Issuer {
     }
     __syncwarp();
   }
-  __device__ __forceinline__ void advance() { slot = (slot + 1 == NS) ? 0 : slot + 1; }
+  __device__ __forceinline__ void advance() { slot = (slot + 1 == ns) ? 0 : slot + 1; }
   // K = 16*KSTEPS of A chunk `a_chunk` times the operand tile at byte offset `b_off` of slot `sl`
   template <int KSTEPS>
   __device__ __forceinline__ void mma(uint32_t a_chunk, uint32_t b_addr, int n, uint32_t col, bool first) {
@@ -790,6 +809,26 @@ struct Issuer {
     }
     __syncwarp();
   }
+  // the same with the A operand in tensor memory: 16*KSTEPS K elements starting at TMEM column a_col (8 columns per step)
+  template <int KSTEPS>
+  __device__ __forceinline__ void mma_ts(uint32_t a_col, uint32_t b_addr, int n, uint32_t col, bool first) {
+    const uint64_t bd = make_desc(b_addr);
+    const uint32_t id = make_idesc(n);
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k)
+        tc_mma_ts(tmem + col, tmem + a_col + 8u * k, bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+    }
+    __syncwarp();
+  }
+  template <int KSTEPS>
+  __device__ __forceinline__ void fill_mma_ts(uint32_t a_col, int n, uint32_t col, bool first, int next_act) {
+    acquire();
+    mma_ts<KSTEPS>(a_col, slot_addr(), n, col, first);
+    release();
+    advance();
+    if (next_act != -2) probe(next_act);
+  }
   // whole fill = one operand tile.  `next_act`: activation barrier of the FOLLOWING fill (-1 none,
   // -2: do not probe ahead - the caller probes after doing something else)
   template <int KSTEPS>
@@ -800,11 +839,24 @@ struct Issuer {
     advance();
     if (next_act != -2) probe(next_act);                  // the probe's round trip overlaps MMA execution
   }
+  // two N=128 accumulators initialised from the two 128-row bias sub-blocks of ONE fill (albedo1 | shading1 in TS mode)
+  __device__ __forceinline__ bool bias2(uint32_t col_a, uint32_t col_b, int next_act) {
+    acquire();
+    if (bias_mma && leader) {
+      tc_mma(tmem + col_a, make_desc_flat(ones, 128, 0), make_desc_flat(slot_addr(), 128, 256), make_idesc(128), 0u);
+      tc_mma(tmem + col_b, make_desc_flat(ones, 128, 0), make_desc_flat(slot_addr() + 4096, 128, 256), make_idesc(128), 0u);
+    }
+    __syncwarp();
+    release();
+    advance();
+    if (next_act != -2) probe(next_act);
+    return bias_mma != 0;
+  }
   // accumulator columns [col, col+n) := bias (one K=16 MMA of the constant "ones" tile)
   __device__ __forceinline__ bool bias(int n, uint32_t col, int next_act) {
     acquire();
     if (bias_mma && leader)
-      tc_mma(tmem + col, make_desc_flat(smem_base + SM_ONES, 128, 0), make_desc_flat(slot_addr(), 128, 256), make_idesc(n), 0u);
+      tc_mma(tmem + col, make_desc_flat(ones, 128, 0), make_desc_flat(slot_addr(), 128, 256), make_idesc(n), 0u);
     __syncwarp();
     release();
     advance();
@@ -813,8 +865,8 @@ struct Issuer {
   }
 };
 
-__device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl) {
-  Issuer I{sy, smem_base, tmem, 0, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
+__device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
+  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
   const bool sem = P.C > 0;
   const int nv = sem ? 256 : 128;       // views' [| sem1] width
@@ -1107,9 +1159,285 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 }
 
 // ------------------------------------------------------------------------------------------
+// "TS" variant (object network, inference): the hidden activations never touch shared memory.  The epilogue writes
+// relu(accumulator) as packed fp16 pairs back INTO the tensor-memory columns it has just drained (tcgen05.st), and the next
+// layer's MMAs take their A operand from there (tcgen05.mma with a TMEM A operand).  Per layer-tile this removes the 68 KB
+// of A-operand reads and the 64 KB of activation stores from the 404 KB of shared-memory traffic that bound the SS kernel
+// (DESIGN.md section 4b), and fence.proxy.async from the layer-to-layer chain.
+//   layer l accumulates in R(l) = A0 (even l) / A1 (odd l); its packed output lives in R(l)[0,128) and is dead once layer
+//   l+1 has been issued, i.e. before layer l+2 overwrites R(l).  Tail: h7 sits in A1[0,128); views' -> A0[0,128),
+//   albedo1 -> A1[128,256), shading1 -> A0[128,256) (two N=128 accumulators fed from the same weight fill); their packed
+//   ReLUs go to A0[0,64), A1[128,192), A0[128,192); residual -> A0[64,80), albedo2|shading2 -> A0[80,96).
+// Two warps share each 32-lane quadrant, and a warp's packed store may land on columns the OTHER warp of the quadrant has
+// only just loaded, so the pair meets at a 64-thread named barrier between "all loads of the batch are in registers" and
+// the stores.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
+  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
+  const uint32_t PE = smem_base + SM_PE, DIR = smem_base + SM_DIR;
+  I.probe(-1);
+  for (int it = 0; it < P.n_iter; ++it) {
+    sy.tile = it;
+    const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;
+    sy.wait(B_F_READY);
+    {
+      const bool init = I.bias(256, A0, -1);
+      I.fill_mma<4>(PE, 256, A0, !init, -1);
+      I.commit(B_ACC_FULL + 0);
+    }
+    sy.wait(B_TAIL_DONE);
+    for (int l = 1; l < 8; ++l) {
+      const uint32_t acc = (l & 1) ? A1 : A0, src = (l & 1) ? A0 : A1;      // input = packed output of layer l-1
+      bool first = !I.bias(256, acc, l == 5 ? -1 : B_A_READY + 0);
+      if (l == 5) {
+        I.fill_mma<4>(PE, 256, acc, first, B_A_READY + 0);
+        first = false;
+      }
+      for (int c = 0; c < 4; ++c) {
+        I.fill_mma_ts<4>(src + 32u * c, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
+        first = false;
+      }
+      I.commit(B_ACC_FULL + (l & 1));
+    }
+    // ---- views' on h7 (A1[0,128)) + gamma(d) -> A0[0,128) -------------------------------------------------
+    {
+      bool first = !I.bias(128, A0, B_A_READY + 0);
+      for (int c = 0; c < 4; ++c) {
+        I.fill_mma_ts<4>(A1 + 32u * c, 128, A0, first, c < 3 ? B_A_READY + c + 1 : -1);
+        first = false;
+      }
+      I.fill_mma<2>(DIR, 128, A0, false, -1);
+      I.commit(B_ACC_FULL + 0);
+    }
+    // ---- albedo1 -> A1[128,256), shading1 -> A0[128,256): both halves of every albedo1|shading1 weight fill -----
+    {
+      const bool init = I.bias2(A1 + 128, A0 + 128, -1);
+      for (int c = 0; c < 4; ++c) {
+        I.acquire();
+        I.mma_ts<4>(A1 + 32u * c, I.slot_addr(), 128, A1 + 128, !init && c == 0);
+        I.mma_ts<4>(A1 + 32u * c, I.slot_addr() + 16384, 128, A0 + 128, !init && c == 0);
+        I.release();
+        I.advance();
+        I.probe(-1);
+      }
+      I.commit(B_ACC_FULL + 1);
+    }
+    // ---- residual head on relu(views') (A0[0,64)) -> A0[64,80) ---------------------------------------------------
+    sy.wait(B_V_READY);
+    {
+      I.acquire();
+      const uint32_t b_addr = I.slot_addr();
+      I.mma_ts<4>(A0 + 0, b_addr, 16, A0 + 64, true);
+      I.mma_ts<4>(A0 + 32, b_addr + 2048, 16, A0 + 64, false);
+      I.release();
+      I.advance();
+      I.probe(-1);
+    }
+    I.commit(B_F_FREE);
+    // ---- albedo2 / shading2 on [relu(albedo1) (A1[128,192)) | relu(shading1) (A0[128,192))] -> A0[80,96) -----------
+    {
+      I.acquire();
+      const uint32_t b_addr = I.slot_addr();
+      for (int c = 0; c < 4; ++c) {
+        sy.wait(B_A_READY + c);
+        tc_fence_after();
+        I.mma_ts<4>((c < 2 ? A1 + 128 + 32u * c : A0 + 128 + 32u * (c - 2)), b_addr + 2048 * c, 16, A0 + 80, c == 0);
+      }
+      I.release();
+      I.advance();
+      I.probe(-1);
+    }
+    I.commit(B_SMALL_FULL);
+  }
+}
+
+// 2 chunks (64 fp32 columns each) of the accumulator at `src` -> relu -> packed halves -> TMEM columns `dst` + 32 c + 16 jj.
+// MODE 1 also accumulates the sigma head.  `pair_bar`: the quadrant's named barrier (two warps).
+template <int MODE>
+__device__ __forceinline__ void epi_batch_ts(uint32_t src, uint32_t dst, int col0, int jj, int lane, Sync& sy, int ready_bar0,
+                                             const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(src + jj * 32, v0);
+  tmem_ld32(src + 64 + jj * 32, v1);
+  tmem_ld_wait();
+  // both warps of the quadrant hold their columns in registers (immediate barrier ids keep ptxas from reserving all 16)
+  switch (pair_bar) {
+    case 2: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t* v = half == 0 ? v0 : v1;
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    if (MODE == 1) {
+      float s = *sigma_acc;
+      const float* aw = alpha_smem + col0 + half * 64 + jj * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(aw + 4 * i);
+        s = fmaf(fmaxf(f[4 * i], 0.f), t.x, s);
+        s = fmaf(fmaxf(f[4 * i + 1], 0.f), t.y, s);
+        s = fmaf(fmaxf(f[4 * i + 2], 0.f), t.z, s);
+        s = fmaf(fmaxf(f[4 * i + 3], 0.f), t.w, s);
+      }
+      *sigma_acc = s;
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      pk[i] = pack_relu_sat_h2(f[2 * i], f[2 * i + 1]);
+      amax = hmax2_u32(amax, pk[i]);
+    }
+    tmem_st16(dst + half * 32 + jj * 16, pk);
+    tmem_st_wait();
+    tc_fence_before();
+    if (ready_bar0 >= 0) warp_arrive(sy.addr(ready_bar0 + half), lane);
+  }
+}
+
+// one chunk per batch: a thread cannot convert while its own load is in flight (wait::ld waits for all of them), but the
+// eight warps reach this point staggered by the read port (4 KB each, 64 B/clk), so with ONE x32 load per wait the port
+// stays busy with other warps' loads while a warp converts, and K chunk c of the next layer is released after (c+1)/4 of
+// the drain instead of after 1/2 and 1/1 of it
+template <int MODE>
+__device__ __forceinline__ void epi_chunk_ts(uint32_t src, uint32_t dst, int col, int jj, int lane, Sync& sy, int ready_bar,
+                                             const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar) {
+  uint32_t v[32];
+  tmem_ld32(src + jj * 32, v);
+  tmem_ld_wait();
+  switch (pair_bar) {
+    case 2: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+  }
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (MODE == 1) {
+    float s = *sigma_acc;
+    const float* aw = alpha_smem + col + jj * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(aw + 4 * i);
+      s = fmaf(fmaxf(f[4 * i], 0.f), t.x, s);
+      s = fmaf(fmaxf(f[4 * i + 1], 0.f), t.y, s);
+      s = fmaf(fmaxf(f[4 * i + 2], 0.f), t.z, s);
+      s = fmaf(fmaxf(f[4 * i + 3], 0.f), t.w, s);
+    }
+    *sigma_acc = s;
+  }
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    pk[i] = pack_relu_sat_h2(f[2 * i], f[2 * i + 1]);
+    amax = hmax2_u32(amax, pk[i]);
+  }
+  tmem_st16(dst + jj * 16, pk);
+  tmem_st_wait();
+  tc_fence_before();
+  if (ready_bar >= 0) warp_arrive(sy.addr(ready_bar), lane);
+}
+
+// `n_chunks` 64-column chunks of the accumulator at `src` -> packed into `dst`, either two chunks per load batch or one
+template <int MODE>
+__device__ __forceinline__ void epi_acc_ts(int fine, uint32_t src, uint32_t dst, int n_chunks, int jj, int lane, Sync& sy, int ready_bar0,
+                                           const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar) {
+  if (fine) {
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c)
+      epi_chunk_ts<MODE>(src + 64 * c, dst + 32 * c, 64 * c, jj, lane, sy, ready_bar0 >= 0 ? ready_bar0 + c : -1, alpha_smem, sigma_acc, amax, pair_bar);
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; c += 2)
+      epi_batch_ts<MODE>(src + 64 * c, dst + 32 * c, 64 * c, jj, lane, sy, ready_bar0 >= 0 ? ready_bar0 + c : -1, alpha_smem, sigma_acc, amax, pair_bar);
+  }
+}
+
+__device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* smem, uint32_t tmem, int q, int jj, int lane) {
+  const int row = q * 32 + lane;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  float* s_sig = reinterpret_cast<float*>(smem + SM_SIG);
+  const float* s_alpha = reinterpret_cast<const float*>(smem + SM_ALPHA);
+  const int pair_bar = 2 + q;
+  const int fine = P.ts_fine;
+  for (int it = 0; it < P.n_iter; ++it) {
+    const int64_t tile = tile_of(P, it);
+    sy.tile = (int)tile;
+    const int64_t m = tile * TILE_M + row;
+    const bool valid = P.fuse ? true : (m < P.a.M);
+    float* grow = P.fuse ? P.f.ring + (((size_t)blockIdx.x * 2 + (it & 1)) * TILE_M + row) * P.out_ch
+                         : P.a.raw + (m < P.a.M ? m : 0) * P.out_ch;
+    float sig = 0.f;
+    uint32_t amax = 0u;
+    const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;
+    for (int l = 0; l < 8; ++l) {
+      sy.wait(B_ACC_FULL + (l & 1));
+      tc_fence_after();
+      const uint32_t R = lane_addr + ((l & 1) ? A1 : A0);
+      if (l == 7) epi_acc_ts<1>(fine, R, R, 4, jj, lane, sy, B_A_READY, s_alpha, &sig, amax, pair_bar);
+      else epi_acc_ts<0>(fine, R, R, 4, jj, lane, sy, B_A_READY, nullptr, nullptr, amax, pair_bar);
+    }
+    s_sig[row * 2 + jj] = sig;
+    // relu(views') : A0[0,128) -> A0[0,64)
+    sy.wait(B_ACC_FULL + 0);
+    tc_fence_after();
+    epi_acc_ts<0>(fine, lane_addr + A0, lane_addr + A0, 2, jj, lane, sy, -1, nullptr, nullptr, amax, pair_bar);
+    warp_arrive(sy.addr(B_V_READY), lane);
+    // relu(albedo1) : A1[128,256) -> A1[128,192) ; relu(shading1) : A0[128,256) -> A0[128,192)
+    sy.wait(B_ACC_FULL + 1);
+    tc_fence_after();
+    epi_acc_ts<0>(fine, lane_addr + A1 + 128, lane_addr + A1 + 128, 2, jj, lane, sy, B_A_READY, nullptr, nullptr, amax, pair_bar);
+    epi_acc_ts<0>(fine, lane_addr + A0 + 128, lane_addr + A0 + 128, 2, jj, lane, sy, B_A_READY + 2, nullptr, nullptr, amax, pair_bar);
+    // heads -> raw row
+    sy.wait(B_SMALL_FULL);
+    if (P.fuse) sy.wait(B_RAW_FREE + (it & 1));
+    tc_fence_after();
+    __syncwarp();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (jj == 0) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + A0 + 64, v);
+      tmem_ld_wait();
+      if (valid) {
+        float res[3], alb[3], sh;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) res[i] = sigmoid_(__uint_as_float(v[i]) + __ldg(P.bias + TCB_RES + i));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) alb[i] = sigmoid_(__uint_as_float(v[16 + i]) + __ldg(P.bias + TCB_ALB2 + i));
+        sh = sigmoid_(__uint_as_float(v[19]) + __ldg(P.bias + TCB_SH2));
+        const float sigma = (s_sig[row * 2] + s_sig[row * 2 + 1]) + __ldg(P.bias + TCB_ALPHA_B);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grow[i] = __fadd_rn(__fmul_rn(alb[i], sh), res[i]);
+        grow[3] = sigma;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grow[4 + i] = alb[i];
+        grow[7] = sh;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grow[8 + i] = res[i];
+      }
+    }
+    if (m < P.a.M && !sy.dead && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {
+      if (atomicCAS(P.dbg + 8, 0, 1) == 0) status_raise(P.status, DST_F16_ACT, 0, (int)tile, blockIdx.x);
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    warp_arrive(sy.addr(B_TAIL_DONE), lane);
+    if (P.fuse) {
+      __threadfence_block();
+      warp_arrive(sy.addr(B_RAW_READY + (it & 1)), lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int CL, bool STASH>
+template <int CL, bool STASH, bool TS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -1131,7 +1459,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     return;                                            // same for every CTA of the launch
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), CL); }
+    for (int s = 0; s < NS_MAX; ++s) { mbar_init(sy.addr(B_WFULL + s), 1); mbar_init(sy.addr(B_WEMPTY + s), CL); }
     mbar_init(sy.addr(B_F_READY), 4); mbar_init(sy.addr(B_F_FREE), 1);
     for (int c = 0; c < 4; ++c) mbar_init(sy.addr(B_A_READY + c), 8);
     mbar_init(sy.addr(B_H_FREE), 1);
@@ -1165,7 +1493,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   const uint32_t tmem = *tmem_slot;
 
   // "free"-type barriers start released: the first wait must pass on a fresh barrier
-  const uint64_t released = (((1ull << NS) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (1ull << B_TAIL_DONE) | (3ull << B_RAW_FREE);
+  const uint64_t released = (((1ull << NS_MAX) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (1ull << B_TAIL_DONE) | (3ull << B_RAW_FREE);
   sy.phase = released;
 
   if (P.prof != nullptr && blockIdx.x == 0) {
@@ -1176,14 +1504,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   // warp roles.  The scheduler favours the highest warp id of each sub-partition, so the MMA issuer
   // (15) and the weight producer (14) sit on top of their sub-partitions; both run converged on all
   // 32 lanes (addresses and descriptors stay on the uniform datapath) and elect one lane to issue.
+  // TS variant: there is no H buffer; PE | DIR | ring slide down to offset 0 (the roles address them relative to a base
+  // shifted by -SM_PE), which gives the ring six 32 KB stages below the same SM_SIG.. tail of the map
+  const uint32_t role_base = TS ? smem_base - (uint32_t)SM_PE : smem_base;
   if (warp == 14) {
-    if (!P.no_weights) producer(P, sy, smem_base, CL, rank);
+    if (!P.no_weights) producer(P, sy, role_base, CL, rank);
   } else if (warp == 15) {
-    issuer(P, sy, smem_base, tmem, CL);
+    if (TS) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer(P, sy, smem_base, tmem, CL, smem_base + SM_ONES);
   } else if (warp >= 8 && warp < 12) {
-    front_end<STASH>(P, sy, smem_base, (warp - 8) * 32 + lane);
+    front_end<STASH>(P, sy, role_base, (warp - 8) * 32 + lane);
   } else if (warp < 8) {
-    epilogue<STASH>(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
+    if (TS) epilogue_ts(P, sy, smem, tmem, warp & 3, warp >> 2, lane);
+    else epilogue<STASH>(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
   }
   if (sy.prof != nullptr) sy.prof[63] = clock64() - t_start;
   tc_fence_before();
@@ -1286,8 +1618,16 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
     grid = grid / cl * cl;
     P.n_iter = (int)((units + grid - 1) / grid) * unit_tiles;
   }
+  // INRF_TC_TS=1: activations stay in tensor memory (object network, inference, bias by MMA) - see issuer_ts
+  static const int ts_mode = getenv("INRF_TC_TS") ? atoi(getenv("INRF_TC_TS")) : 0;
+  static const bool ts_env = ts_mode == 1 || ts_mode == 2;
+  P.ts_fine = ts_mode == 2 ? 1 : 0;
+  static const int ns_env = getenv("INRF_TC_NS") ? atoi(getenv("INRF_TC_NS")) : 0;
+  const bool ts = ts_env && !a.stash_img && a.n_classes == 0 && !a.endpoint && a.variant == INRF_NET_OBJECT && P.bias_mma;
+  P.ns = ts ? ((ns_env >= 2 && ns_env <= tc::NS_MAX) ? ns_env : tc::NS_MAX) : tc::NS;
   void (*kern)(tc::Params) = a.stash_img ? (cl == 2 ? tc::k_mlp_tc<2, true> : tc::k_mlp_tc<1, true>)
-                                         : (cl == 2 ? tc::k_mlp_tc<2, false> : tc::k_mlp_tc<1, false>);
+                             : ts ? (cl == 2 ? tc::k_mlp_tc<2, false, true> : tc::k_mlp_tc<1, false, true>)
+                                  : (cl == 2 ? tc::k_mlp_tc<2, false> : tc::k_mlp_tc<1, false>);
   INRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
