@@ -1618,8 +1618,10 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
     grid = grid / cl * cl;
     P.n_iter = (int)((units + grid - 1) / grid) * unit_tiles;
   }
-  // INRF_TC_TS=1: activations stay in tensor memory (object network, inference, bias by MMA) - see issuer_ts
-  static const int ts_mode = getenv("INRF_TC_TS") ? atoi(getenv("INRF_TC_TS")) : 0;
+  // Activations in tensor memory (issuer_ts / epilogue_ts) wherever that variant is implemented: object network,
+  // inference, bias by MMA.  INRF_TC_TS=0 selects the shared-memory-activation kernel everywhere (A/B, debugging),
+  // =1 the two-chunks-per-load-batch drain.
+  static const int ts_mode = getenv("INRF_TC_TS") ? atoi(getenv("INRF_TC_TS")) : 2;
   static const bool ts_env = ts_mode == 1 || ts_mode == 2;
   P.ts_fine = ts_mode == 2 ? 1 : 0;
   static const int ns_env = getenv("INRF_TC_NS") ? atoi(getenv("INRF_TC_NS")) : 0;

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/ts.log
 export INRF_TC_WATCHDOG_CYCLES=400000000
-for cfg in "0 0" "2 4" "2 6" "2 5" "2 6" "2 4"; do
+for cfg in "0 0" "2 6" "1 6" "2 6" "0 0"; do
   set -- $cfg
   echo "TS=$1 NS=$2" >> gpurun_out/ts.log
   INRF_TC_TS=$1 INRF_TC_NS=$2 timeout 200 python tests/tools/tc_perf.py 160000 >> gpurun_out/ts.log 2>&1
