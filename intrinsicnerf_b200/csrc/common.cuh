@@ -270,7 +270,11 @@ struct MlpArgs {
 // ---------------------------------------------------------------------------------
 constexpr int IMG_BYTES = 16384;
 // forward stash slots of one tile
-constexpr int IS_PE = 0, IS_DIR = 1, IS_H = 2 /* + 4*layer + chunk */, IS_V = 34, IS_AS = 36, IS_S1 = 40, IMG_STASH_SLOTS = 42;
+constexpr int IS_PE = 0, IS_DIR = 1, IS_H = 2 /* + 4*layer + chunk */, IS_V = 34, IS_AS = 36, IS_S1 = 40;
+// slots 42..44: the ReLU masks of image slots IS_H.. as bit words - for image slot s, 32-column half jj and row r the
+// u32 at word ((s - IS_H) * 2 + jj) * 128 + r holds "column 32 jj + i of that chunk is > 0 in fp16" at bit i/2 (even i) or
+// 16 + i/2 (odd i) (1 KB per image, 40 KB per tile).  The dX epilogue reads one coalesced word per thread and chunk instead of the 16 KB image.
+constexpr int IS_MASK = 42, IMG_STASH_SLOTS = 45;
 // backward workspace slots of one tile: G = head gradients (g_albedo[0:3] g_shading[3] g_residual[4:7] g_sigma[7]
 // g_sem[8:8+C]), dZ of albedo1|shading1, views', sem1 and of the eight trunk layers
 constexpr int IB_G = 0, IB_DAS = 2, IB_DV = 6, IB_DS1 = 8, IB_DZ = 10 /* + 4*layer + chunk */, IMG_BWD_SLOTS = 42;

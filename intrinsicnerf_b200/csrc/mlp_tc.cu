@@ -72,7 +72,9 @@ enum {
   B_SMALL_FULL, B_SEM2_FULL, B_TAIL_DONE,
   B_RAW_READY,                 // [2] fused mode: the raw rows of a tile are in ring slot (it & 1) (8 epilogue warps)
   B_RAW_FREE = B_RAW_READY + 2,  // [2] both back-end warps have consumed the slot
-  B_COUNT = B_RAW_FREE + 2
+  B_ST_DONE = B_RAW_FREE + 2,    // [4] training: the stash copy of H chunk c has left shared memory (the chunk may be rewritten)
+  B_STV_DONE = B_ST_DONE + 4,    // training: the same for the two relu(views') chunks in the PE|DIR region
+  B_COUNT
 };
 static_assert(B_COUNT <= 40, "barrier area");
 
@@ -695,6 +697,7 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
       for (int i = 0; i < 16; ++i) dw[i] = pack_h2(de[2 * i], de[2 * i + 1]);
     }
     sy.wait(B_F_FREE);
+    if (STASH) sy.wait(B_STV_DONE);            // the stash copy of the previous tile's relu(views') has been read out of this region
 #pragma unroll
     for (int u = 0; u < 8; ++u) st_shared_v4(smem_base + SM_PE + ra.unit[u], pw[4 * u], pw[4 * u + 1], pw[4 * u + 2], pw[4 * u + 3]);
 #pragma unroll
@@ -746,6 +749,64 @@ __device__ __forceinline__ void producer(const Params& P, Sync& sy, uint32_t sme
       slot = (slot + 1 == P.ns) ? 0 : slot + 1;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// stash warp (training forward): every fp16 operand chunk the epilogue builds in shared memory is, as it stands, the
+// 16 KB image the backward reads - one elected lane copies it to HBM with a bulk store as soon as the chunk's
+// "written" barrier completes (the same barrier that releases it to the MMA issuer).  The epilogue warps used to
+// write these images themselves: 4 x 16 B per thread and chunk into 32 different lines per instruction, more LSU
+// wavefronts per tile than the tensor pipe has cycles (the training forward ran at 47 us per tile, 2.3x the inference
+// kernel).  B_ST_DONE[c] / B_STV_DONE tell the epilogue (and the front end, for the PE|DIR|V region) that the copy has
+// finished READING the chunk, so it may be rewritten in place.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void stasher(const Params& P, Sync& sy, uint32_t smem_base) {
+  const bool leader = elect_one();
+  const bool sem = P.C > 0;
+  const uint32_t H = smem_base + SM_H, V = smem_base + SM_V;
+  int pending = -1;                          // "read done" barrier of the copy in flight
+  for (int it = 0; it < P.n_iter; ++it) {
+    const int64_t tile = tile_of(P, it);
+    sy.tile = (int)tile;
+    const bool live = tile * TILE_M < P.a.M;                    // tiles past the end of the batch are not stored
+    unsigned char* simg = P.a.stash_img + (live ? tile : 0) * IMG_STASH_SLOTS * (int64_t)IMG_BYTES;
+    // One copy stays in flight: the "has been read" signal of a chunk is given when the NEXT copy has been issued (the
+    // wait for a copy's own read would put ~0.5 us per chunk, 40 chunks per tile, on the epilogue's critical path -
+    // measured: 41 us per tile).  The next copy never depends on that signal, so the chain cannot deadlock.
+    auto chunk = [&](int ready_bar, int done_bar, uint32_t src, int slot, uint32_t bytes) {
+      sy.wait(ready_bar);                    // the writers fenced (fence.proxy.async) before arriving
+      if (leader && !sy.dead) {
+        if (live) {
+          bulk_s2g(simg + (int64_t)slot * IMG_BYTES, src, bytes);
+          bulk_wait_read1();                 // every copy but the one just issued has read its source
+        } else {
+          bulk_wait_read0();
+        }
+        if (pending >= 0) mbar_arrive(sy.addr(pending));
+      }
+      __syncwarp();
+      pending = done_bar;
+    };
+    for (int l = 0; l < 8; ++l)
+      for (int c = 0; c < 4; ++c) chunk(B_A_READY + c, B_ST_DONE + c, H + c * CHUNK, IS_H + 4 * l + c, CHUNK);
+    chunk(B_V_READY, B_STV_DONE, V, IS_V, 2 * CHUNK);
+    for (int c = 0; c < 4; ++c) chunk(B_A_READY + c, B_ST_DONE + c, H + c * CHUNK, IS_AS + c, CHUNK);
+    if (sem)
+      for (int c = 0; c < 2; ++c) chunk(B_A_READY + c, B_ST_DONE + c, H + c * CHUNK, IS_S1 + c, CHUNK);
+  }
+  if (leader) {
+    bulk_wait_all0();                        // the images are complete in global memory before the CTA retires
+    if (pending >= 0 && !sy.dead) mbar_arrive(sy.addr(pending));
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -974,7 +1035,7 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
 template <bool ADD_BIAS, bool SIGMA, bool GOUT>
 __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __restrict__ bias, uint32_t dst_chunk,
                                             const RowAddr& ra, int unit0, const float* alpha_w_smem, float* sigma_acc,
-                                            float* gout, unsigned char* gimg, uint32_t& amax) {
+                                            float* gout, uint32_t* gmask, uint32_t& amax) {
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -1001,6 +1062,9 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
 #pragma unroll
     for (int i = 0; i < 32; ++i) gout[i] = fmaxf(f[i], 0.f);
   }
+  // training: ReLU decisions of these 32 columns as one word - bit j = column 2j, bit 16 + j = column 2j + 1 (the order
+  // three instructions per packed pair produce: a stored half h >= 0 is non-zero iff bit 15 of h + 0x7fff is set)
+  uint32_t bits = 0u;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     uint32_t pk[4];
@@ -1008,10 +1072,11 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
     for (int i = 0; i < 4; ++i) {
       pk[i] = pack_relu_sat_h2(f[8 * u + 2 * i], f[8 * u + 2 * i + 1]);
       amax = hmax2_u32(amax, pk[i]);          // running maximum of the stored halves: fp16-range check at the tile end
+      if (gmask != nullptr) bits = (bits >> 1) | ((pk[i] + 0x7fff7fffu) & 0x80008000u);
     }
     st_shared_v4(dst_chunk + ra.unit[unit0 + u], pk[0], pk[1], pk[2], pk[3]);
-    if (gimg != nullptr) st_global_v4(gimg + ra.unit[unit0 + u], pk[0], pk[1], pk[2], pk[3]);   // training stash image
   }
+  if (gmask != nullptr) *gmask = bits;         // lanes = consecutive rows: one coalesced 128-byte store per warp
 }
 
 // A 256-column accumulator -> 4 H chunks, two chunks per TMEM load batch.
@@ -1020,8 +1085,8 @@ __device__ __forceinline__ void epi_store32(const uint32_t* v, const float* __re
 template <int MODE>
 __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const float* bias, uint32_t dst0, int n_chunks,
                                           const RowAddr& ra, int jj, int lane, Sync& sy, int free_bar0, int ready_bar0,
-                                          const float* alpha_smem, float* sigma_acc, float* gout0, unsigned char* gimg0,
-                                          uint32_t& amax) {
+                                          const float* alpha_smem, float* sigma_acc, float* gout0, uint32_t* gmask0,
+                                          uint32_t& amax, int st_bar0 = -1, bool st_per_chunk = true) {
 #pragma unroll 1
   for (int cp = 0; cp < n_chunks; cp += 2) {
     uint32_t v0[32], v1[32];
@@ -1034,9 +1099,11 @@ __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const f
       const int col = c * 64 + jj * 32;
       const uint32_t* v = half == 0 ? v0 : v1;
       if (free_bar0 >= 0 && c == 0) sy.wait(free_bar0);     // one "H free" barrier for the whole layer
+      // training: the stash warp's bulk copy of the chunk's previous contents has finished reading shared memory
+      if (st_bar0 >= 0 && (st_per_chunk || c == 0)) sy.wait(st_bar0 + (st_per_chunk ? c : 0));
       float* g = (MODE == 2 && gout0) ? gout0 + col : nullptr;
       const float* aw = (MODE == 1) ? alpha_smem + col : nullptr;
-      unsigned char* gi = gimg0 ? gimg0 + c * IMG_BYTES : nullptr;
+      uint32_t* gi = gmask0 ? gmask0 + c * 256 : nullptr;            // mask words of image slot +c
       if (add_bias) epi_store32<true, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi, amax);
       else epi_store32<false, MODE == 1, MODE == 2>(v, bias + col, dst0 + c * CHUNK, ra, jj * 4, aw, sigma_acc, g, gi, amax);
       fence_async_smem();
@@ -1069,9 +1136,13 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     // raw row destination: the caller's [M, out_ch] tensor, or (fused) this tile's slot of the L2-resident ring
     float* grow = P.fuse ? P.f.ring + (((size_t)blockIdx.x * 2 + (it & 1)) * TILE_M + row) * P.out_ch
                          : P.a.raw + (m < P.a.M ? m : 0) * P.out_ch;
-    // training: image slot 0 of this tile in the stash (tiles past the end of the batch are not stored)
-    unsigned char* simg = (STASH && tile * TILE_M < P.a.M) ? P.a.stash_img + tile * IMG_STASH_SLOTS * (int64_t)IMG_BYTES : nullptr;
-#define SLOT(s) (simg ? simg + (s) * IMG_BYTES : nullptr)
+    // training: every operand chunk built here also goes to the stash - copied out of shared memory by the stash warp
+    // (stasher), which needs the chunk intact until its bulk copy has read it: B_ST_DONE / B_STV_DONE
+    constexpr int ST = STASH ? B_ST_DONE : -1, STV = STASH ? B_STV_DONE : -1;
+    // ... and its ReLU mask goes out as one bit word per thread and chunk (slots IS_MASK.., common.cuh)
+    uint32_t* smask = (STASH && tile * TILE_M < P.a.M)
+        ? reinterpret_cast<uint32_t*>(P.a.stash_img + (tile * IMG_STASH_SLOTS + IS_MASK) * (int64_t)IMG_BYTES) + jj * 128 + row : nullptr;
+#define MSLOT(s) (smask ? smask + ((s) - IS_H) * 256 : nullptr)
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
     float sig = 0.f;
     uint32_t amax = 0u;                                  // running max of every fp16 activation this thread stored
@@ -1079,8 +1150,8 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     for (int l = 0; l < 8; ++l) {
       sy.wait(B_ACC_FULL + (l & 1));
       tc_fence_after();
-      if (l == 7) epi_layer<1>(add_bias, lane_addr + A1, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, SLOT(IS_H + 28), amax);
-      else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_H + 4 * l), amax);
+      if (l == 7) epi_layer<1>(add_bias, lane_addr + A1, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, MSLOT(IS_H + 28), amax, ST);
+      else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, MSLOT(IS_H + 4 * l), amax, ST);
     }
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
@@ -1089,18 +1160,18 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
       tc_fence_after();
     if (P.a.endpoint)
       epi_layer<2>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr,
-                   valid ? grow + INRF_RAW_BASE + P.C : nullptr, SLOT(IS_V), amax);
+                   valid ? grow + INRF_RAW_BASE + P.C : nullptr, MSLOT(IS_V), amax, STV, false);
     else
-      epi_layer<0>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, SLOT(IS_V), amax);
+      epi_layer<0>(add_bias, lane_addr + A0, P.bias + TCB_VIEWS, V, 2, ra, jj, lane, sy, -1, -1, nullptr, nullptr, nullptr, MSLOT(IS_V), amax, STV, false);
     warp_arrive(sy.addr(B_V_READY), lane);
     // ---- relu(albedo1 | shading1) -> H (in place over the trunk output) ---------------------------------
     sy.wait(B_ACC_FULL + 1);
       tc_fence_after();
-    epi_layer<0>(add_bias, lane_addr + A1, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_AS), amax);
+    epi_layer<0>(add_bias, lane_addr + A1, P.bias + TCB_ALBSH, H, 4, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, MSLOT(IS_AS), amax, ST);
     // ---- relu(sem1) -> H chunks 0,1 (after the albedo2/shading2 MMAs released them) -------------------
     if (sem)
-      epi_layer<0>(add_bias, lane_addr + A0 + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, SLOT(IS_S1), amax);
-#undef SLOT
+      epi_layer<0>(add_bias, lane_addr + A0 + 128, P.bias + TCB_SEM1, H, 2, ra, jj, lane, sy, B_H_FREE, B_A_READY, nullptr, nullptr, nullptr, MSLOT(IS_S1), amax, ST);
+#undef MSLOT
     // ---- heads -> raw row ------------------------------------------------------------------------------
     sy.wait(B_SMALL_FULL);
     if (sem) sy.wait(B_SEM2_FULL);
@@ -1468,6 +1539,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     mbar_init(sy.addr(B_SMALL_FULL), 1); mbar_init(sy.addr(B_SEM2_FULL), 1);
     mbar_init(sy.addr(B_TAIL_DONE), 8);
     for (int k = 0; k < 2; ++k) { mbar_init(sy.addr(B_RAW_READY + k), 8); mbar_init(sy.addr(B_RAW_FREE + k), 2); }
+    for (int c = 0; c < 4; ++c) mbar_init(sy.addr(B_ST_DONE + c), 1);
+    mbar_init(sy.addr(B_STV_DONE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
@@ -1493,7 +1566,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   const uint32_t tmem = *tmem_slot;
 
   // "free"-type barriers start released: the first wait must pass on a fresh barrier
-  const uint64_t released = (((1ull << NS_MAX) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (1ull << B_TAIL_DONE) | (3ull << B_RAW_FREE);
+  const uint64_t released = (((1ull << NS_MAX) - 1) << B_WEMPTY) | (1ull << B_F_FREE) | (1ull << B_TAIL_DONE) | (3ull << B_RAW_FREE) |
+                            (15ull << B_ST_DONE) | (1ull << B_STV_DONE);
   sy.phase = released;
 
   if (P.prof != nullptr && blockIdx.x == 0) {
@@ -1509,6 +1583,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   const uint32_t role_base = TS ? smem_base - (uint32_t)SM_PE : smem_base;
   if (warp == 14) {
     if (!P.no_weights) producer(P, sy, role_base, CL, rank);
+  } else if (STASH && warp == 13) {
+    stasher(P, sy, smem_base);
   } else if (warp == 15) {
     if (TS) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer(P, sy, smem_base, tmem, CL, smem_base + SM_ONES);
   } else if (warp >= 8 && warp < 12) {

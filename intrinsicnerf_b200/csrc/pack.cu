@@ -178,13 +178,19 @@ __global__ void k_compose_views(const float* __restrict__ flat, unsigned char* _
   float* cb = cw + 128 * 256;
   int n = blockIdx.x;       // 128 blocks
   int k = threadIdx.x;      // 256 threads
-  double acc = 0.0;
-  for (int j = 0; j < W_HID; ++j) acc += (double)vw[n * (W_HID + PE_DIR) + j] * (double)fw[j * W_HID + k];
-  cw[n * W_HID + k] = (float)acc;
-  if (k == 0) {
-    double b = (double)vb[n];
-    for (int j = 0; j < W_HID; ++j) b += (double)vw[n * (W_HID + PE_DIR) + j] * (double)fb[j];
-    cb[n] = (float)b;
+  // four interleaved partial sums: the dependent fp64 FMA chain, not the loads, paced the single-accumulator loop
+  double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+  for (int j = 0; j < W_HID; j += 4) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a4[i] += (double)vw[n * (W_HID + PE_DIR) + j + i] * (double)fw[(j + i) * W_HID + k];
+  }
+  cw[n * W_HID + k] = (float)((a4[0] + a4[1]) + (a4[2] + a4[3]));
+  if (k < 32) {                        // bias: one warp, lane-strided partial sums + butterfly
+    double b = 0.0;
+    for (int j = k; j < W_HID; j += 32) b += (double)vw[n * (W_HID + PE_DIR) + j] * (double)fb[j];
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (k == 0) cb[n] = (float)(b + (double)vb[n]);
   }
 }
 

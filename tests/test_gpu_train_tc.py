@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as orc
-from tests.util import build_nets, rel_err, stash_activations
+from tests.util import build_nets, rel_err, stash_activations, stash_mask_bits
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -48,6 +48,10 @@ def test_tc_training_forward_stash_and_gradients(variant, C, endpoint, M, g_scal
     # ---- stash: every activation tile of the forward, as the backward will read it ----------------------------------
     act = stash_activations(out.grad_fn.saved_tensors[3], M, C)
     names = orc.OBJECT_HEADS if variant == "object" else orc.SSR_HEADS
+    # the bit words the dX epilogue reads are exactly "stored activation > 0" of the images the dW GEMM reads
+    mb = stash_mask_bits(out.grad_fn.saved_tensors[3], M)
+    imgs = torch.cat([act[f"h{l}"] for l in range(8)] + [act["v"], act["as"]] + ([act["s1"]] if C > 0 else []), 1)
+    assert torch.equal(mb[:, :imgs.shape[1]], imgs > 0)
     masks = [act[f"h{l}"] > 0 for l in range(8)] + [act["as"][:, :128] > 0, act["as"][:, 128:] > 0, act["v"] > 0]
     if C > 0:
         masks.append(act["s1"] > 0)

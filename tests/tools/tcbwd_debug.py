@@ -92,7 +92,7 @@ err = float((raw.detach().cpu().double() - want.detach()).abs().max())
 print(f"[fwd] raw max abs err {err:.3e}")
 T = (M + 127) // 128
 stash = raw.grad_fn.saved_tensors[3]
-img = decode(stash, T, 42)
+img = decode(stash, T, stash.numel() // (T * 16384))
 names = orc.TRUNK
 h = emb[:, :63]
 for i, name in enumerate(names):

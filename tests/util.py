@@ -98,10 +98,21 @@ def decode_images(buf, n_tiles, slots):
     return torch.gather(x, 4, idx).reshape(n_tiles, slots, 128, 64).float()
 
 
+def stash_mask_bits(stash, M):
+    """The ReLU-mask bit words of the forward stash (csrc/common.cuh IS_MASK) -> bool [M, 40 * 64]: column (s * 64 + c) is
+    the decision for column c of image slot 2 + s (trunk h0..h7, views', albedo1|shading1, sem1)."""
+    T = (M + 127) // 128
+    slots = stash.numel() // (T * 16384)
+    w = stash.view(T, slots * 16384)[:, 42 * 16384: 42 * 16384 + 40 * 1024].contiguous().view(torch.int32).reshape(T, 40, 2, 128)
+    i = torch.arange(32, device=stash.device, dtype=torch.int32)
+    bits = (w.unsqueeze(-1) >> ((i >> 1) + 16 * (i & 1))) & 1            # [T, 40, 2, 128, 32]: even columns in bits 0..15, odd in 16..31
+    return bits.permute(0, 3, 1, 2, 4).reshape(T * 128, 40 * 64)[:M].bool().cpu()
+
+
 def stash_activations(stash, M, n_classes):
     """Decoded forward stash -> dict of [M, width] activations: 'pe' 64, 'dir' 32, 'h0'..'h7' 256, 'v' 128, 'as' 256, ['s1' 128]."""
     T = (M + 127) // 128
-    img = decode_images(stash, T, 42)
+    img = decode_images(stash, T, stash.numel() // (T * 16384))      # 42 image slots + the ReLU-mask bit words
     rows = lambda s0, n: img[:, s0:s0 + n].permute(0, 2, 1, 3).reshape(T * 128, 64 * n)[:M].cpu()  # noqa: E731
     out = {"pe": rows(0, 1), "dir": rows(1, 1)[:, :32], "v": rows(34, 2), "as": rows(36, 4)}
     for l in range(8):

@@ -9,4 +9,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ml
   python tests/tools/profile_target.py 40000 tc > gpurun_out/prof_target.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_train.csv \
   python tests/tools/train_target.py > gpurun_out/train_under_ncu.log 2>&1
+# the same three steps with warm caches (--cache-control none): per-kernel durations closer to the ones inside a running step
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 600 --csv --log-file gpurun_out/launches_train_warm.csv \
+  python tests/tools/train_target.py > gpurun_out/train_under_ncu_warm.log 2>&1
 ls -la gpurun_out | head -30

@@ -96,6 +96,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
     launches(tag, "launches_train.csv", "launches_train_summary", "python tests/tools/train_target.py  (3 SSR training steps: render + backward, 1024 rays)")
+    launches(tag, "launches_train_warm.csv", "launches_train_warm_summary",
+             "python tests/tools/train_target.py  (the same three steps under --cache-control none: L2 keeps what the previous kernel left)")
     for n in sorted(os.listdir(GP)):
         if n.endswith(".ncu-rep"):
             full(tag, n[:-8])
