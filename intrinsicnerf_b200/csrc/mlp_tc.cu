@@ -98,10 +98,11 @@ struct Params {
   int fault;                      // test hook (INRF_TC_FAULT=n, first n launches): the weight producer stops after three fills
   long long* prof;                // optional wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
+  int stash_abl;                  // timing experiment (INRF_TC_STASH_ABL): 1 no mask words, 2 no bulk copies, 4 no "copy has read" waits
 };
 
 __device__ int g_dbg[16];
-__device__ long long g_prof[4 * 128];
+__device__ long long g_prof[5 * 128];
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -620,7 +621,7 @@ template <bool STASH>
 __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
   RayState rs;                                           // fused mode, warps 0 and 2 of the front end only
   rs.carry = 1.f;
-  const bool backend = P.fuse && (row < 32 || (row >= 64 && row < 96));
+  const bool backend = !STASH && P.fuse && (row < 32 || (row >= 64 && row < 96));   // (no fused back end in the training instantiation)
   const int which = row >= 64 ? 1 : 0;
   const int blane = row & 31;
   const bool sampler = P.f.n_importance > 0;
@@ -704,9 +705,6 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
     for (int u = 0; u < 4; ++u) st_shared_v4(smem_base + SM_DIR + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     fence_async_smem();
     warp_arrive(sy.addr(B_F_READY), row & 31);
-    if (backend && it > 0) {                     // composite (and resample) the previous tile while this one is in the pipe
-      if (sampler) ray_backend<true>(P, sy, it - 1, blane, rs, which); else ray_backend<false>(P, sy, it - 1, blane, rs, which);
-    }
     if (STASH && tile * TILE_M < P.a.M) {        // training: the same operand images go to the stash
       unsigned char* g = P.a.stash_img + (tile * IMG_STASH_SLOTS + IS_PE) * (int64_t)IMG_BYTES;
 #pragma unroll
@@ -715,8 +713,11 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
 #pragma unroll
       for (int u = 0; u < 4; ++u) st_global_v4(g + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     }
+    if (!STASH && backend && it > 0) {           // composite (and resample) the previous tile while this one is in the pipe
+      if (sampler) ray_backend<true>(P, sy, it - 1, blane, rs, which); else ray_backend<false>(P, sy, it - 1, blane, rs, which);
+    }
   }
-  if (backend && P.n_iter > 0) {                 // the last tile of this CTA
+  if (!STASH && backend && P.n_iter > 0) {       // the last tile of this CTA
     if (sampler) ray_backend<true>(P, sy, P.n_iter - 1, blane, rs, which); else ray_backend<false>(P, sy, P.n_iter - 1, blane, rs, which);
   }
 }
@@ -776,7 +777,7 @@ __device__ __forceinline__ void stasher(const Params& P, Sync& sy, uint32_t smem
   for (int it = 0; it < P.n_iter; ++it) {
     const int64_t tile = tile_of(P, it);
     sy.tile = (int)tile;
-    const bool live = tile * TILE_M < P.a.M;                    // tiles past the end of the batch are not stored
+    const bool live = tile * TILE_M < P.a.M && !(P.stash_abl & 2);   // tiles past the end of the batch are not stored
     unsigned char* simg = P.a.stash_img + (live ? tile : 0) * IMG_STASH_SLOTS * (int64_t)IMG_BYTES;
     // One copy stays in flight: the "has been read" signal of a chunk is given when the NEXT copy has been issued (the
     // wait for a copy's own read would put ~0.5 us per chunk, 40 chunks per tile, on the epilogue's critical path -
@@ -1138,9 +1139,9 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
                          : P.a.raw + (m < P.a.M ? m : 0) * P.out_ch;
     // training: every operand chunk built here also goes to the stash - copied out of shared memory by the stash warp
     // (stasher), which needs the chunk intact until its bulk copy has read it: B_ST_DONE / B_STV_DONE
-    constexpr int ST = STASH ? B_ST_DONE : -1, STV = STASH ? B_STV_DONE : -1;
+    const int ST = (STASH && !(P.stash_abl & 4)) ? B_ST_DONE : -1, STV = (STASH && !(P.stash_abl & 4)) ? B_STV_DONE : -1;
     // ... and its ReLU mask goes out as one bit word per thread and chunk (slots IS_MASK.., common.cuh)
-    uint32_t* smask = (STASH && tile * TILE_M < P.a.M)
+    uint32_t* smask = (STASH && tile * TILE_M < P.a.M && !(P.stash_abl & 1))
         ? reinterpret_cast<uint32_t*>(P.a.stash_img + (tile * IMG_STASH_SLOTS + IS_MASK) * (int64_t)IMG_BYTES) + jj * 128 + row : nullptr;
 #define MSLOT(s) (smask ? smask + ((s) - IS_H) * 256 : nullptr)
     // ---- trunk: accumulator of layer l -> A operand of layer l+1 (in place in H) ------------------
@@ -1571,7 +1572,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   sy.phase = released;
 
   if (P.prof != nullptr && blockIdx.x == 0) {
-    const int role = (threadIdx.x == 448) ? 0 : (threadIdx.x == 480 ? 1 : (threadIdx.x == 256 ? 2 : (threadIdx.x == 0 ? 3 : -1)));
+    const int role = (threadIdx.x == 448) ? 0 : (threadIdx.x == 480 ? 1 : (threadIdx.x == 256 ? 2 : (threadIdx.x == 0 ? 3 : (threadIdx.x == 416 ? 4 : -1))));
     if (role >= 0) sy.prof = P.prof + role * 128;
   }
   const long long t_start = clock64();
@@ -1648,11 +1649,13 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   static const bool prof_env = getenv("INRF_TC_PROF") != nullptr && getenv("INRF_TC_PROF")[0] == '1';
   static const bool now_env = getenv("INRF_TC_NOWEIGHTS") != nullptr && getenv("INRF_TC_NOWEIGHTS")[0] == '1';
   P.no_weights = now_env ? 1 : 0;
+  static const int abl_env = getenv("INRF_TC_STASH_ABL") ? atoi(getenv("INRF_TC_STASH_ABL")) : 0;
+  P.stash_abl = abl_env;
   P.prof = nullptr;
   if (prof_env) {
     long long* pp = nullptr;
     INRF_CUDA(cudaGetSymbolAddress((void**)&pp, tc::g_prof));
-    INRF_CUDA(cudaMemsetAsync(pp, 0, 4 * 128 * sizeof(long long), st));
+    INRF_CUDA(cudaMemsetAsync(pp, 0, 5 * 128 * sizeof(long long), st));
     P.prof = pp;
   }
   int* dbg = nullptr;
@@ -1722,14 +1725,14 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   INRF_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
   note_launch();
   if (prof_env) {
-    static const char* bar_names[] = {"WFULL0","WFULL1","WFULL2","WFULL3","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3","F_READY","F_FREE",
-      "A_READY0","A_READY1","A_READY2","A_READY3","H_FREE","ACC_FULL0","ACC_FULL1","V_READY",
-      "SMALL_FULL","SEM2_FULL","TAIL_DONE"};
-    static const char* roles[] = {"producer", "issuer", "frontend", "epilogue"};
-    long long h[4 * 128];
+    static const char* bar_names[tc::B_COUNT] = {"WFULL0","WFULL1","WFULL2","WFULL3","WFULL4","WFULL5","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3",
+      "WEMPTY4","WEMPTY5","F_READY","F_FREE","A_READY0","A_READY1","A_READY2","A_READY3","H_FREE","ACC_FULL0","ACC_FULL1","V_READY",
+      "SMALL_FULL","SEM2_FULL","TAIL_DONE","RAW_READY0","RAW_READY1","RAW_FREE0","RAW_FREE1","ST_DONE0","ST_DONE1","ST_DONE2","ST_DONE3","STV_DONE"};
+    static const char* roles[] = {"producer", "issuer", "frontend", "epilogue", "stasher"};
+    long long h[5 * 128];
     INRF_CUDA(cudaStreamSynchronize(st));
     INRF_CUDA(cudaMemcpyFromSymbol(h, tc::g_prof, sizeof(h)));
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 5; ++r) {
       fprintf(stderr, "TCPROF role=%s total_cycles=%lld n_iter=%d\n", roles[r], h[r * 128 + 63], P.n_iter);
       for (int b = 0; b < tc::B_COUNT; ++b) {
         if (h[r * 128 + 64 + b] == 0) continue;

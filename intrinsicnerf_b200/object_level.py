@@ -154,8 +154,18 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         rays_d, viewdirs = ray_batch[:, 3:6], ray_batch[:, -3:]
         rays_o = ray_batch[:, 0:3]
         z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand, seed if (in_kernel_rng and perturb > 0.) else None)
-        pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
-        raw = network_query_fn(pts, viewdirs, network_fn)
+        # our modules take (rays, z) and form o + d z in the kernel's front end (same two roundings as the line below):
+        # no [N,S,3] tensors, four launches fewer per pass
+        by_rays = isinstance(network_query_fn, _FusedQuery) and network_query_fn.fusable_with(network_fn, network_fine) \
+            and ray_batch.shape[1] == 11
+
+        def query(z, net):
+            if by_rays:
+                out = net.evaluate("rays", ray_batch, z, False, network_query_fn.embed_fn.scalar_factor)
+                return out.reshape(z.shape[0], z.shape[1], out.shape[-1])
+            pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+            return network_query_fn(pts, viewdirs, net)
+        raw = query(z_vals, network_fn)
         rng_c = (raw_noise_std, seed, False) if (in_kernel_rng and raw_noise_std > 0.) else None
         rng_f = (raw_noise_std, seed, True) if (in_kernel_rng and raw_noise_std > 0.) else None
         rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, None if in_kernel_rng else draw_noise(N, N_samples), white_bkgd, rng=rng_c)
@@ -165,8 +175,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             z_samples = ops.sample_pdf(z_mid, weights[..., 1:-1].detach(), N_importance, u,
                                        seed=seed if (in_kernel_rng and perturb != 0.) else None)[0]   # detached (run_nerf.py:501)
             z_vals, z_std = ops.merge_sorted(z_vals, z_samples)
-            pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
-            raw = network_query_fn(pts, viewdirs, network_fn if network_fine is None else network_fine)
+            raw = query(z_vals, network_fn if network_fine is None else network_fine)
             rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, None if in_kernel_rng else draw_noise(N, St), white_bkgd, rng=rng_f)
         for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
             ret[k + "_map"] = _split_rec(rec, k)

@@ -233,8 +233,18 @@ class SSRRenderer:
         Sc, Sf = self.N_samples, self.N_importance
         rays_o, rays_d, viewdirs = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, 8:11]
         z = ops.coarse_z(ray_batch, Sc, False, None, seed if jitter else None)
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
-        raw_c = run_network(pts, viewdirs, self.ssr_net_coarse, self.embed_fn, self.embeddirs_fn)
+        ours = isinstance(self.embed_fn, Embedder) and isinstance(self.embeddirs_fn, Embedder) and self.embed_fn.n_freqs == 10 \
+            and self.embeddirs_fn.n_freqs == 4 and ray_batch.shape[1] == 11
+
+        def query(zz, net, ep=False):
+            # our modules take (rays, z) and form o + d z in the kernel's front end (the same two roundings as the
+            # tensor expression below): no [N,S,3] tensors, four launches fewer per pass
+            if ours and isinstance(net, Semantic_NeRF):
+                out = net.evaluate("rays", ray_batch, zz, ep, self.embed_fn.scalar_factor)
+                return out.reshape(zz.shape[0], zz.shape[1], out.shape[-1])
+            pts = rays_o[:, None, :] + rays_d[:, None, :] * zz[:, :, None]
+            return run_network(pts, viewdirs, with_endpoint(net, ep) if ep else net, self.embed_fn, self.embeddirs_fn)
+        raw_c = query(z, self.ssr_net_coarse)
         rec_c, w_c = ops.composite(raw_c, z, rays_d, None, self.white_bkgd, C, False, (std, seed, False))
         ret = {"raw_coarse": raw_c}
         names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual")
@@ -246,9 +256,8 @@ class SSRRenderer:
             z_mid = .5 * (z[:, 1:] + z[:, :-1])
             z_samples = ops.sample_pdf(z_mid, w_c[:, 1:-1].detach(), Sf, None, seed=None if det else seed)[0]
             z_f, z_std = ops.merge_sorted(z, z_samples)
-            pts = rays_o[:, None, :] + rays_d[:, None, :] * z_f[:, :, None]
             ep = bool(self.endpoint_feat)
-            raw_f = run_network(pts, viewdirs, with_endpoint(self.ssr_net_fine, ep), self.embed_fn, self.embeddirs_fn)
+            raw_f = query(z_f, self.ssr_net_fine, ep)
             rec_f, _ = ops.composite(raw_f, z_f, rays_d, None, self.white_bkgd, C, ep, (std, seed, True))
             for k in names:
                 ret[k + "_fine"] = _split_rec(rec_f, k)
