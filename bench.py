@@ -316,7 +316,7 @@ def train_step_record(dev, dist, rank, world, steps=20, warmup=5, n_rays=1024, C
             "frac_of_sustained_bf16": flop / (per * 1e-3) / 1e12 / ((pk["bf16_sustained"] or pk["bf16_tflops"]) * world),
             "libinrf_launches_per_step": launches,
             "collectives": None if dist is None else
-            f"all_gather of {len(keys)} rendered maps (~{n_rays * (3 * 8 + 2 * C) * 4 // 1024} KB, autograd) + one all_reduce of "
+            f"one all_gather of the {len(keys)} rendered maps as a single record (~{n_rays * (3 * 8 + 2 * C) * 4 // 1024} KB, autograd) + one in-place all_reduce per network of "
             f"{n_grad} fp32 gradients ({n_grad * 4 / 1e6:.1f} MB)",
             "includes": "ray sampling excluded; render (training mode, in-kernel stash) + losses + backward + all-reduce + Adam"}
 
