@@ -141,7 +141,8 @@ int inrf_mlp_bwd(const float* flat_params, int variant, int n_classes, int endpo
 
 /* Tensor-core training forward / backward (INRF_PREC_TC arithmetic: fp16 operands, fp32 accumulation).
  * The forward is the inference kernel with one addition: every activation tile is also written to
- * `stash_img` (inrf_mlp_stash_img_bytes(M) bytes) as 16 KB images of the tensor-core operand chunks.  The backward
+ * `stash_img` (inrf_mlp_stash_img_bytes(M) bytes) as 16 KB images of the tensor-core operand chunks (42 per 128-row
+ * tile) followed by the ReLU decisions of those tiles as bit words (3 more 16 KB slots per tile).  The backward
  * walks those images with tcgen05 GEMMs (dX chain, then all dW in one launch) and ACCUMULATES dL/d(parameters)
  * into grad_flat like inrf_mlp_bwd; `workspace` needs inrf_mlp_bwd_tc_workspace_bytes(variant, n_classes, M) bytes.
  * Gradients are scaled on the device by a power of two derived from max|grad_raw| so that fp16 holds them. */
