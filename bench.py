@@ -273,6 +273,24 @@ def train_step_record(dev, dist, rank, world, steps=20, warmup=5, n_rays=1024, C
     launches = (ops.launch_count() - l0) / (steps + warmup)
     torch.cuda.synchronize()
     ops.poll_status()
+    if os.environ.get("INRF_BENCH_HOSTPROF") == "1":          # development aid: where the host time of an eager step goes
+        import cProfile
+        import pstats
+        import time
+        t0 = time.perf_counter()
+        for _ in range(20):
+            step()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"HOSTPROF issue {1e3 * (t1 - t0) / 20:.3f} ms/step, drain after the loop {1e3 * (t2 - t1):.3f} ms", file=sys.stderr)
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(20):
+            step()
+        pr.disable()
+        torch.cuda.synchronize()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     # the same step replayed from a CUDA graph (one rank: no collective inside): what is left when the ~150 launches of
     # the step (ours + PyTorch's loss / Adam kernels) cost no host time
     ms_graph = None

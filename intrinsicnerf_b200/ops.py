@@ -76,8 +76,34 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Current CUDA stream of the current device as a void* (the raw-handle query: torch.cuda.current_stream() builds a
+    Stream object and costs ~20 us of host time per call, 17 calls per training step)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _dev:
+    """`with _dev(d)` without the cost when d already is the current device (the usual case)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if getattr(device, "index", None) is not None else -1
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.idx >= 0 and self.idx != self.prev:
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.idx >= 0 and self.idx != self.prev:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 _LINSPACE = {}
@@ -104,7 +130,7 @@ def pack_weights(flat, variant, n_classes):
         raise ValueError(f"flat parameter vector has {flat.numel()} values, expected {n}")
     nbytes = check(_lib.lib().inrf_packed_bytes(variant, n_classes))
     packed = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
-    with torch.cuda.device(flat.device):
+    with _dev(flat.device):
         check(_lib.lib().inrf_pack_weights(_ptr(flat), variant, n_classes, _ptr(packed), nbytes, _stream()))
     return packed
 
@@ -114,7 +140,7 @@ def embed(x, n_freqs, scalar_factor=1.0):
     lead = x.shape[:-1]
     x2 = x.reshape(-1, 3)
     out = torch.empty(x2.shape[0], 3 + 6 * n_freqs, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _dev(x.device):
         check(_lib.lib().inrf_embed(_ptr(x2), x2.shape[0], n_freqs, float(scalar_factor), _ptr(out), _stream()))
     return out.reshape(*lead, out.shape[-1])
 
@@ -125,7 +151,7 @@ def mlp_forward(packed, variant, n_classes, pts, viewdirs, endpoint=False, pe_sc
     if viewdirs.shape[0] != M:
         raise ValueError("pts and viewdirs must have one row per sample")
     raw = torch.empty(M, RAW_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=pts.device)
-    with torch.cuda.device(pts.device):
+    with _dev(pts.device):
         check(_lib.lib().inrf_mlp_fwd(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor),
                                       _ptr(pts), _ptr(viewdirs), M, _ptr(raw), _prec(precision), _stream()))
     return raw
@@ -138,7 +164,7 @@ def mlp_forward_embedded(packed, variant, n_classes, emb, endpoint=False, precis
     lead = emb.shape[:-1]
     e2 = emb.reshape(-1, 90)
     raw = torch.empty(e2.shape[0], RAW_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=emb.device)
-    with torch.cuda.device(emb.device):
+    with _dev(emb.device):
         check(_lib.lib().inrf_mlp_fwd_embedded(_ptr(packed), variant, n_classes, int(endpoint), _ptr(e2), e2.shape[0],
                                                _ptr(raw), _prec(precision), _stream()))
     return raw.reshape(*lead, raw.shape[-1])
@@ -148,7 +174,7 @@ def mlp_forward_rays(packed, variant, n_classes, rays, z, endpoint=False, pe_sca
     rays, z = _f32(rays, "rays"), _f32(z, "z")
     N, S = z.shape
     raw = torch.empty(N, S, RAW_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=z.device)
-    with torch.cuda.device(z.device):
+    with _dev(z.device):
         check(_lib.lib().inrf_mlp_fwd_rays(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor),
                                            _ptr(rays), _ptr(z), N, S, _ptr(raw), _prec(precision), _stream()))
     return raw
@@ -163,7 +189,7 @@ def raw2outputs_rec(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes
     rec = torch.empty(N, REC_BASE + n_classes + (128 if endpoint else 0), dtype=torch.float32, device=raw.device)
     weights = torch.empty(N, S, dtype=torch.float32, device=raw.device) if want_weights else None
     noise = None if noise is None else _f32(noise, "noise")
-    with torch.cuda.device(raw.device):
+    with _dev(raw.device):
         if rng is not None and noise is None:
             check(_lib.lib().inrf_raw2outputs_rng(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, float(rng[0]), int(rng[1]), int(bool(rng[2])), N, S,
                                                   n_classes, int(endpoint), int(bool(white_bkgd)), _ptr(rec), _ptr(weights), _stream()))
@@ -179,7 +205,7 @@ def raw2outputs_bwd(raw, z_vals, rays_d, noise, grad_rec, grad_weights, white_bk
     noise = None if noise is None else _f32(noise, "noise")
     grad_weights = None if grad_weights is None else _f32(grad_weights, "grad_weights")
     grad_raw = torch.empty_like(raw)
-    with torch.cuda.device(raw.device):
+    with _dev(raw.device):
         if rng is not None and noise is None:
             check(_lib.lib().inrf_raw2outputs_bwd_rng(_ptr(raw), _ptr(z_vals), _ptr(rays_d), 3, float(rng[0]), int(rng[1]), int(bool(rng[2])), N, S,
                                                       n_classes, int(endpoint), int(bool(white_bkgd)), _ptr(grad_rec), _ptr(grad_weights),
@@ -221,7 +247,7 @@ class MlpFn(torch.autograd.Function):
         dev = flat_c.device
         raw = torch.empty(M, ch, dtype=torch.float32, device=dev)
         stash = torch.empty(M, int(L.inrf_stash_floats_per_row()), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _dev(dev):
             check(L.inrf_mlp_fwd_train(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor), _ptr(pts), _ptr(vd),
                                        _ptr(rays), _ptr(z), S, _ptr(emb), M, _ptr(raw), _ptr(stash), _stream()))
         ctx.save_for_backward(flat_c, raw, stash, *[t for t in (pts, vd, rays, z, emb) if t is not None])
@@ -241,7 +267,7 @@ class MlpFn(torch.autograd.Function):
             (emb,) = addr
         g_raw = _f32(g_raw, "grad_raw").reshape(M, -1)
         g_flat = torch.zeros_like(flat_c)
-        with torch.cuda.device(flat_c.device):
+        with _dev(flat_c.device):
             check(_lib.lib().inrf_mlp_bwd(_ptr(flat_c), variant, n_classes, int(endpoint), pe, _ptr(pts), _ptr(vd), _ptr(rays),
                                           _ptr(z), S, _ptr(emb), M, _ptr(raw), _ptr(stash), _ptr(g_raw), _ptr(g_flat), _stream()))
         return g_flat, None, None, None, None, None, None, None
@@ -276,7 +302,7 @@ class MlpTcFn(torch.autograd.Function):
         dev = flat_c.device
         raw = torch.empty(M, ch, dtype=torch.float32, device=dev)
         stash = torch.empty(int(L.inrf_mlp_stash_img_bytes(M)), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _dev(dev):
             check(L.inrf_mlp_fwd_train_tc(_ptr(packed), variant, n_classes, int(endpoint), float(pe_scalar_factor), _ptr(pts), _ptr(vd),
                                           _ptr(rays), _ptr(z), S, _ptr(emb), M, _ptr(raw), _ptr(stash), _stream()))
         ctx.save_for_backward(flat_c, packed, raw, stash)
@@ -292,7 +318,7 @@ class MlpTcFn(torch.autograd.Function):
         L = _lib.lib()
         nbytes = int(L.inrf_mlp_bwd_tc_workspace_bytes(variant, n_classes, M))
         ws = _Workspace.get(flat_c.device, nbytes, "bwd")
-        with torch.cuda.device(flat_c.device):
+        with _dev(flat_c.device):
             check(L.inrf_mlp_bwd_tc(_ptr(packed), _ptr(flat_c), variant, n_classes, int(endpoint), M, _ptr(raw), _ptr(stash),
                                     _ptr(g_raw), _ptr(ws), ws.numel(), _ptr(g_flat), _stream()))
         return g_flat, None, None, None, None, None, None, None
@@ -348,7 +374,7 @@ class IntrinsicLossFn(torch.autograd.Function):
         if albedo.shape != (N, 3) or residual.shape != (N, 3) or gt_rgb.shape != (N, 3) or shading.numel() != N or label.numel() != N:
             raise ValueError("intrinsic loss: albedo/residual/gt_rgb must be [N,3], shading/label [N]")
         losses = torch.empty(8, dtype=torch.float32, device=albedo.device)
-        with torch.cuda.device(albedo.device):
+        with _dev(albedo.device):
             check(_lib.lib().inrf_intrinsic_loss_fwd(_ptr(rgb), 3, _ptr(albedo), 3, _ptr(shading), 1, _ptr(residual), 3, _ptr(gt_rgb),
                                                      _ptr(label), _ptr(target), N, int(mode), _ptr(losses), _stream()))
         ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in (rgb, albedo, shading, residual, gt_rgb, label, target)])
@@ -363,7 +389,7 @@ class IntrinsicLossFn(torch.autograd.Function):
         w = _f32(g_losses, "grad")
         g_alb, g_res, g_sh = torch.empty_like(albedo), torch.empty_like(residual), torch.empty_like(shading)
         g_rgb = torch.empty_like(rgb) if has_rgb else None
-        with torch.cuda.device(albedo.device):
+        with _dev(albedo.device):
             check(_lib.lib().inrf_intrinsic_loss_bwd(_ptr(rgb if has_rgb else None), 3, _ptr(albedo), 3, _ptr(shading), 1, _ptr(residual), 3,
                                                      _ptr(gt_rgb), _ptr(label), _ptr(target if has_target else None), N, mode, _ptr(w),
                                                      _ptr(g_rgb), _ptr(g_alb), _ptr(g_sh), _ptr(g_res), _stream()))
@@ -387,7 +413,7 @@ def sample_pdf(bins, weights, n_samples, u=None, want_inds=False, want_cdf=False
         raise ValueError("weights must be [N, bins-1]")
     if seed is not None and u is None and not want_inds and not want_cdf:
         samples = torch.empty(N, n_samples, dtype=torch.float32, device=bins.device)
-        with torch.cuda.device(bins.device):
+        with _dev(bins.device):
             check(_lib.lib().inrf_sample_pdf_rng(_ptr(bins), _ptr(weights), B - 1, int(seed), N, B, n_samples, _ptr(samples), _stream()))
         return samples, None, None
     u = None if u is None else _f32(u, "u")
@@ -395,7 +421,7 @@ def sample_pdf(bins, weights, n_samples, u=None, want_inds=False, want_cdf=False
     samples = torch.empty(N, n_samples, dtype=torch.float32, device=bins.device)
     inds = torch.empty(N, n_samples, dtype=torch.int64, device=bins.device) if want_inds else None
     cdf = torch.empty(N, B, dtype=torch.float32, device=bins.device) if want_cdf else None
-    with torch.cuda.device(bins.device):
+    with _dev(bins.device):
         check(_lib.lib().inrf_sample_pdf(_ptr(bins), _ptr(weights), B - 1, _ptr(u), _ptr(u_det), N, B, n_samples,
                                          _ptr(samples), _ptr(inds), _ptr(cdf), _stream()))
     return samples, inds, cdf
@@ -407,7 +433,7 @@ def invert_cdf(bins, cdf, u):
     n = u.shape[1]
     samples = torch.empty(N, n, dtype=torch.float32, device=bins.device)
     inds = torch.empty(N, n, dtype=torch.int64, device=bins.device)
-    with torch.cuda.device(bins.device):
+    with _dev(bins.device):
         check(_lib.lib().inrf_invert_cdf(_ptr(bins), _ptr(cdf), _ptr(u), N, B, n, _ptr(samples), _ptr(inds), _stream()))
     return samples, inds
 
@@ -418,7 +444,7 @@ def merge_sorted(z_a, z_b, want_std=True):
     Sb = z_b.shape[1]
     out = torch.empty(N, Sa + Sb, dtype=torch.float32, device=z_a.device)
     std = torch.empty(N, dtype=torch.float32, device=z_a.device) if want_std else None
-    with torch.cuda.device(z_a.device):
+    with _dev(z_a.device):
         check(_lib.lib().inrf_merge_sorted(_ptr(z_a), _ptr(z_b), N, Sa, Sb, _ptr(out), _ptr(std), _stream()))
     return out, std
 
@@ -429,12 +455,12 @@ def coarse_z(rays, n_samples, lindisp=False, t_rand=None, seed=None):
     N = rays.shape[0]
     z = torch.empty(N, n_samples, dtype=torch.float32, device=rays.device)
     if seed is not None and t_rand is None:
-        with torch.cuda.device(rays.device):
+        with _dev(rays.device):
             check(_lib.lib().inrf_coarse_z_rng(_ptr(rays), _ptr(linspace01(n_samples, rays.device)), int(seed), N, n_samples,
                                                int(bool(lindisp)), _ptr(z), _stream()))
         return z
     t_rand = None if t_rand is None else _f32(t_rand, "t_rand")
-    with torch.cuda.device(rays.device):
+    with _dev(rays.device):
         check(_lib.lib().inrf_coarse_z(_ptr(rays), _ptr(linspace01(n_samples, rays.device)), _ptr(t_rand), N, n_samples,
                                        int(bool(lindisp)), _ptr(z), _stream()))
     return z
@@ -445,7 +471,7 @@ def get_rays_packed(H, W, K, c2w, near, far, device):
     m = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].contiguous()
     arr = (C.c_float * 12)(*[float(v) for v in m.reshape(-1).tolist()])
     rays = torch.empty(H * W, 11, dtype=torch.float32, device=device)
-    with torch.cuda.device(device):
+    with _dev(device):
         check(_lib.lib().inrf_get_rays(int(H), int(W), float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), arr,
                                        float(near), float(far), _ptr(rays), _stream()))
     return rays
@@ -468,7 +494,7 @@ def rays_from_pixels(pix, H, W, fx, fy, cx, cy, c2w, near, far, convention="open
         pix = pix.detach().to(torch.int64).reshape(-1).contiguous()
         device, n = pix.device, pix.numel()
     rays = torch.empty(n, 11, dtype=torch.float32, device=device)
-    with torch.cuda.device(device):
+    with _dev(device):
         check(_lib.lib().inrf_rays_from_pixels(_ptr(pix), n, int(H), int(W), float(fx), float(fy), float(cx), float(cy), arr,
                                                1 if convention == "opencv" else 0, 1 if depth_type == "euclidean" else 0,
                                                float(near), float(far), _ptr(rays), _stream()))
@@ -523,7 +549,7 @@ def render_chunk(rays, packed_coarse, packed_fine, variant=0, n_classes=0, n_sam
     t_rand, u = opt(t_rand, "t_rand"), opt(u, "u")
     noise_coarse, noise_fine = opt(noise_coarse, "noise_coarse"), opt(noise_fine, "noise_fine")
     u_det = linspace01(n_importance, dev) if (n_importance > 0 and u is None) else None
-    with torch.cuda.device(dev):
+    with _dev(dev):
         check(L.inrf_render_fwd(_ptr(rays), N, _ptr(packed_coarse), _ptr(packed_fine), C.byref(cfg),
                                 _ptr(linspace01(n_samples, dev)), _ptr(u_det), _ptr(t_rand), _ptr(u),
                                 _ptr(noise_coarse), _ptr(noise_fine), _ptr(out["rec_coarse"]), _ptr(out.get("rec_fine")),
@@ -562,7 +588,7 @@ def render_frame_camera(H, W, K, c2w, near, far, packed_coarse, packed_fine, dev
         out["rec_fine"], out["z_std"] = new(n, REC_BASE + n_classes), new(n)
         if want_z:
             out["z_fine"] = new(n, n_samples + n_importance)
-    with torch.cuda.device(device):
+    with _dev(device):
         check(L.inrf_render_fwd_camera(C.byref(cam), int(pix0), n, _ptr(packed_coarse), _ptr(packed_fine), C.byref(cfg),
                                        _ptr(linspace01(n_samples, device)), _ptr(linspace01(n_importance, device)) if n_importance > 0 else None,
                                        _ptr(out["rec_coarse"]), _ptr(out.get("rec_fine")), _ptr(out.get("z_std")), _ptr(out.get("z_fine")),
@@ -603,7 +629,7 @@ def frame_finish(rec, H, W, n_classes=0, planes=("rgb8", "albedo8", "shading8", 
         cmap = torch.as_tensor(colour_map).to(device=dev, dtype=torch.uint8).contiguous()
         if cmap.ndim != 2 or cmap.shape[1] != 3 or cmap.shape[0] < n_classes:
             raise ValueError("colour_map must be uint8 [>= n_classes, 3]")
-    with torch.cuda.device(dev):
+    with _dev(dev):
         check(_lib.lib().inrf_frame_finish(_ptr(rec), int(H), int(W), rec.shape[1], int(n_classes), float(acc_threshold),
                                            _ptr(cmap), int(sub_step), C.byref(tab), _stream()))
     return out
@@ -618,6 +644,6 @@ def edit_recompose(cluster_rgb, rec, want_c8=True, want_edit8=True):
         raise ValueError("rec must have one record per pixel")
     c8 = torch.empty(P, 3, dtype=torch.uint8, device=rec.device) if want_c8 else None
     e8 = torch.empty(P, 3, dtype=torch.uint8, device=rec.device) if want_edit8 else None
-    with torch.cuda.device(rec.device):
+    with _dev(rec.device):
         check(_lib.lib().inrf_edit_recompose(_ptr(cluster_rgb), _ptr(rec), P, rec.shape[1], _ptr(c8), _ptr(e8), _stream()))
     return c8, e8
