@@ -301,6 +301,7 @@ def train_step_record(dev, dist, rank, world, steps=20, warmup=5, n_rays=1024, C
             side.wait_stream(torch.cuda.current_stream())
 
             def gstep():
+                ops.rng_epoch_bump()                 # the in-kernel RNG seeds are constants of the graph: fresh draws per replay
                 opt_g.zero_grad(set_to_none=False)
                 out = t.render_rays(rays)
                 loss = ((out["rgb_fine"] - gt) ** 2).mean() + ((out["rgb_coarse"] - gt) ** 2).mean() \

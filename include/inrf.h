@@ -205,7 +205,15 @@ int inrf_coarse_z(const float* rays, const float* t_vals, const float* t_rand, i
  * Philox4x32-10(key = seed, counter = (element index, tensor id)) evaluated where it is consumed: U[0,1) with 24 bits
  * for t_rand / u, Box-Muller N(0,1) * noise_std for the sigma noise.  The same (seed, element) always gives the same
  * number, so inrf_raw2outputs_bwd_rng regenerates the forward's noise.  `fine_pass` selects the noise tensor
- * (coarse / fine pass of one step use different streams of the same seed).  Everything else as the non-_rng entries. */
+ * (coarse / fine pass of one step use different streams of the same seed).  Everything else as the non-_rng entries.
+ *
+ * CUDA graphs: `seed` is a by-value argument and therefore baked into a captured launch.  The key of every draw is
+ * seed + epoch * 0x9E3779B97F4A7C15, where `epoch` is a device-resident word (one per device, 0 until bumped).
+ * inrf_rng_epoch_bump enqueues a one-thread kernel that increments it - capture it at the start of a training step and
+ * every replay draws fresh jitter / noise while the backward of that replay regenerates exactly the forward's numbers;
+ * inrf_rng_epoch_reset sets it back to 0 (the eager behaviour: key = seed). */
+int inrf_rng_epoch_bump(void* stream);
+int inrf_rng_epoch_reset(void* stream);
 int inrf_coarse_z_rng(const float* rays, const float* t_vals, uint64_t seed, int64_t N, int S, int lindisp, float* z,
                       void* stream);
 int inrf_sample_pdf_rng(const float* bins, const float* weights, int ld_w, uint64_t seed, int64_t N, int B,

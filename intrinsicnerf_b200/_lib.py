@@ -44,6 +44,8 @@ _SIGS = {
     "inrf_version": (i32, []),
     "inrf_poll_status": (i32, []),
     "inrf_launch_count": (i64, []),
+    "inrf_rng_epoch_bump": (i32, [p]),
+    "inrf_rng_epoch_reset": (i32, [p]),
     "inrf_flat_param_count": (i64, [i32, i32]),
     "inrf_packed_bytes": (i64, [i32, i32]),
     "inrf_pack_weights": (i32, [p, i32, i32, p, i64, p]),

@@ -110,6 +110,8 @@ const char* inrf_last_error_string(void) { return last_error(); }
 int inrf_version(void) { return 200; }
 int inrf_poll_status(void) { return status_poll(); }
 int64_t inrf_launch_count(void) { return launch_count(); }
+int inrf_rng_epoch_bump(void* stream) { return rng_epoch_set(1, (cudaStream_t)stream); }
+int inrf_rng_epoch_reset(void* stream) { return rng_epoch_set(0, (cudaStream_t)stream); }
 #define INRF_POLL() do { int rc__ = status_poll(); if (rc__) return rc__; } while (0)
 
 int64_t inrf_flat_param_count(int variant, int n_classes) {
@@ -382,7 +384,7 @@ int inrf_render_fwd(const float* rays, int64_t N, const void* packed_coarse, con
 /* ---- training-mode draws generated inside the stage kernels (no generator launch, no [N,S] tensors) -------------------- */
 int inrf_coarse_z_rng(const float* rays, const float* t_vals, uint64_t seed, int64_t N, int S, int lindisp, float* z, void* stream) {
   INRF_CHECK_ARG(N >= 0 && S > 0 && (N == 0 || (rays && t_vals && z)), "null pointer / bad size");
-  return launch_coarse_z(rays, t_vals, nullptr, N, S, lindisp, z, (cudaStream_t)stream, Rng{seed, RNG_T_RAND, 1.f, 1});
+  return launch_coarse_z(rays, t_vals, nullptr, N, S, lindisp, z, (cudaStream_t)stream, Rng{seed, RNG_T_RAND, 1.f, 1, rng_epoch_dev()});
 }
 
 int inrf_sample_pdf_rng(const float* bins, const float* weights, int ld_w, uint64_t seed, int64_t N, int B, int n_samples,
@@ -390,7 +392,7 @@ int inrf_sample_pdf_rng(const float* bins, const float* weights, int ld_w, uint6
   INRF_CHECK_ARG(N >= 0 && n_samples > 0 && (N == 0 || (bins && weights && samples)), "null pointer / bad size");
   INRF_CHECK_ARG(ld_w >= B - 1, "ld_w smaller than the number of weights per ray");
   return launch_sample_pdf(bins, weights, ld_w, nullptr, nullptr, nullptr, N, B, n_samples, samples, nullptr, nullptr,
-                           (cudaStream_t)stream, Rng{seed, RNG_U, 1.f, 1});
+                           (cudaStream_t)stream, Rng{seed, RNG_U, 1.f, 1, rng_epoch_dev()});
 }
 
 int inrf_raw2outputs_rng(const float* raw, const float* z, const float* rays_d, int ld_rays_d, float noise_std, uint64_t seed,
@@ -400,7 +402,7 @@ int inrf_raw2outputs_rng(const float* raw, const float* z, const float* rays_d, 
   INRF_CHECK_ARG(ld_rays_d >= 3, "ld_rays_d < 3");
   INRF_CHECK_SUPPORTED(n_classes >= 0 && n_classes <= MAX_CLASSES, "n_classes out of range");
   return launch_raw2outputs(raw, z, rays_d, ld_rays_d, nullptr, N, S, n_classes, endpoint_feat ? 1 : 0, white_bkgd, rec, weights,
-                            (cudaStream_t)stream, Rng{seed, (unsigned)(fine_pass ? RNG_NOISE_FINE : RNG_NOISE_COARSE), noise_std, noise_std > 0.f});
+                            (cudaStream_t)stream, Rng{seed, (unsigned)(fine_pass ? RNG_NOISE_FINE : RNG_NOISE_COARSE), noise_std, noise_std > 0.f, rng_epoch_dev()});
 }
 
 int inrf_raw2outputs_bwd_rng(const float* raw, const float* z, const float* rays_d, int ld_rays_d, float noise_std, uint64_t seed,
@@ -411,7 +413,7 @@ int inrf_raw2outputs_bwd_rng(const float* raw, const float* z, const float* rays
   INRF_CHECK_SUPPORTED(n_classes >= 0 && n_classes <= MAX_CLASSES, "n_classes out of range");
   return launch_raw2outputs_bwd(raw, z, rays_d, ld_rays_d, nullptr, N, S, n_classes, endpoint_feat ? 1 : 0, white_bkgd, grad_rec,
                                 grad_weights, grad_raw, (cudaStream_t)stream,
-                                Rng{seed, (unsigned)(fine_pass ? RNG_NOISE_FINE : RNG_NOISE_COARSE), noise_std, noise_std > 0.f});
+                                Rng{seed, (unsigned)(fine_pass ? RNG_NOISE_FINE : RNG_NOISE_COARSE), noise_std, noise_std > 0.f, rng_epoch_dev()});
 }
 
 int inrf_render_fwd_camera(const InrfCamera* cam, int64_t pix0, int64_t N, const void* packed_coarse, const void* packed_fine,

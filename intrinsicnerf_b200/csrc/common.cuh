@@ -48,6 +48,8 @@ enum DevStatusCode {
 };
 int* status_flag_dev();                 // device-visible pointer of the current device's record (nullptr: error set)
 int status_poll();                      // INRF_OK, or INRF_ECUDA / INRF_ERANGE with the message set; clears the record
+unsigned long long* rng_epoch_dev();    // the current device's RNG epoch word (device memory, starts at 0; nullptr: error set)
+int rng_epoch_set(int bump, cudaStream_t st);   // bump != 0: += 1 (a kernel, graph-capturable); 0: reset to 0
 #ifdef __CUDACC__
 // coarse sample depths (run_nerf.py:464-486; trainer.py:730-746) - shared by k_coarse_z and the fused kernel's front end
 __device__ __forceinline__ float coarse_depth(float nearv, float farv, float t, int lindisp) {
@@ -177,7 +179,10 @@ int make_tc_program(int variant, int n_classes, TcProgram* prog);
 // u of sample_pdf run_nerf_helpers.py:414, sigma noise run_nerf.py:385-387): Philox4x32-10 keyed by the caller's seed,
 // counter = (element index, stream id), so a draw is a pure function of (seed, which tensor, which element) - the
 // backward pass regenerates the forward's noise instead of reading it back, and no generator kernel is launched.
-struct Rng { unsigned long long seed; unsigned int stream; float scale; int on; };
+// `epoch` (optional) points at a device word that is mixed into the key: a CUDA graph bakes `seed` into its kernel
+// nodes, so a captured training step bumps the word with one tiny kernel at its start (inrf_rng_epoch_bump) and every
+// replay draws fresh numbers while forward and backward of one replay still see the same ones.
+struct Rng { unsigned long long seed; unsigned int stream; float scale; int on; const unsigned long long* epoch; };
 enum { RNG_T_RAND = 1, RNG_U = 2, RNG_NOISE_COARSE = 3, RNG_NOISE_FINE = 4 };
 #ifdef __CUDACC__
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -191,8 +196,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 __device__ __forceinline__ uint4 rng_bits(const Rng& g, long long i) {
+  const unsigned long long key = g.seed + (g.epoch != nullptr ? __ldg(g.epoch) * 0x9E3779B97F4A7C15ull : 0ull);   // epoch 0: the seed itself
   return philox4x32_10(make_uint4((unsigned int)i, (unsigned int)((unsigned long long)i >> 32), g.stream, 0u),
-                       make_uint2((unsigned int)g.seed, (unsigned int)(g.seed >> 32)));
+                       make_uint2((unsigned int)key, (unsigned int)(key >> 32)));
 }
 // U[0,1) with 24 random bits (what torch.rand produces for float32)
 __device__ __forceinline__ float rng_uniform(const Rng& g, long long i) { return (float)(rng_bits(g, i).x >> 8) * 5.9604644775390625e-08f; }

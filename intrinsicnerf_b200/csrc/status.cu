@@ -38,6 +38,33 @@ int* status_flag_dev() {
   return g_dev[dev];
 }
 
+static unsigned long long* g_epoch[64];
+
+unsigned long long* rng_epoch_dev() {
+  int dev;
+  if (slot(&dev)) { set_error("rng epoch: no current CUDA device"); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_epoch[dev] == nullptr) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 64);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc(rng epoch)"); return nullptr; }
+    e = cudaMemset(d, 0, 64);
+    if (e != cudaSuccess) { cudaFree(d); cuda_fail(e, "cudaMemset(rng epoch)"); return nullptr; }
+    g_epoch[dev] = static_cast<unsigned long long*>(d);
+  }
+  return g_epoch[dev];
+}
+
+__global__ void k_rng_epoch(unsigned long long* w, int bump) { *w = bump ? *w + 1ull : 0ull; }
+
+int rng_epoch_set(int bump, cudaStream_t st) {
+  unsigned long long* w = rng_epoch_dev();
+  if (w == nullptr) return INRF_ECUDA;
+  k_rng_epoch<<<1, 1, 0, st>>>(w, bump);
+  INRF_LAUNCH_CHECK();
+  return INRF_OK;
+}
+
 int status_poll() {
   int dev;
   if (slot(&dev)) return INRF_OK;

@@ -34,8 +34,9 @@ def next_seed(device=None):
     """Seed for one step's in-kernel random tensors (inrf_*_rng).  Derived on the host from torch's CUDA generator -
     its seed and Philox offset, which torch.manual_seed resets - and the offset is advanced, exactly as a torch.rand
     call would consume it: runs are reproducible from torch.manual_seed, and no generator kernel is launched.
-    (While a CUDA graph is being captured the generator cannot be read; a host-side counter is used instead and the
-    captured step replays the same draws - pass fresh seeds by re-capturing or use the tensor arguments for that.)"""
+    (While a CUDA graph is being captured the generator cannot be read; a host-side counter is used instead.  The seed
+    is then a constant of the graph: call rng_epoch_bump() at the start of the captured step and every replay draws
+    fresh numbers.)"""
     try:
         idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
         gen = torch.cuda.default_generators[idx]
@@ -49,6 +50,18 @@ def next_seed(device=None):
         _SEED_STATE[1] += 1
         ctr = _SEED_STATE[1]
     return (base * 0x9E3779B97F4A7C15 + ctr * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+
+
+def rng_epoch_bump():
+    """inrf_rng_epoch_bump on the current stream: increments the device-resident epoch that is mixed into the key of every
+    in-kernel draw.  Capture it as the first call of a CUDA-graphed training step (the seeds are baked into the graph);
+    eager code does not need it (next_seed already changes per step)."""
+    check(_lib.lib().inrf_rng_epoch_bump(_stream()))
+
+
+def rng_epoch_reset():
+    """Epoch back to 0 (key = seed), e.g. to reproduce a run from its first step."""
+    check(_lib.lib().inrf_rng_epoch_reset(_stream()))
 
 
 def launch_count():

@@ -145,3 +145,58 @@ def test_ssr_eval_render_is_fused_and_raw_is_lazy():
         want = ops.render_chunk(rays, coarse.packed(), fine.packed(), variant=1, n_classes=C, pe_scalar_factor=10.0, want_raw=True)
     torch.cuda.synchronize()
     assert torch.equal(raw, want["raw_fine"]) and torch.equal(rgb, want["rec_fine"][:, 0:3])
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replays_draw_fresh_numbers():
+    """A captured step bakes its seeds into the graph; the device-resident epoch (inrf_rng_epoch_bump, captured as the
+    first node) makes every replay draw new jitter / noise, the backward of a replay regenerates that replay's forward
+    noise, and resetting the epoch reproduces the sequence."""
+    from intrinsicnerf_b200 import ops
+    dev = torch.device("cuda:0")
+    N, S, C = 256, 64, 0
+    rays = orc.blender_rays(32, 32)[:N].contiguous().to(dev)
+    raw = torch.randn(N, S, 11, device=dev)
+    g_rec = torch.randn(N, 13, device=dev)
+    seed = 1234567
+    ops.rng_epoch_reset()
+    z_eager = ops.coarse_z(rays, S, False, None, seed)                    # epoch 0: key = seed
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    out = {}
+
+    def step():
+        ops.rng_epoch_bump()
+        out["z"] = ops.coarse_z(rays, S, False, None, seed)
+        rec, w = ops.raw2outputs_rec(raw, out["z"], rays[:, 3:6], None, False, C, False, True, (1.0, seed, False))
+        out["rec"] = rec
+        out["graw"] = ops.raw2outputs_bwd(raw, out["z"], rays[:, 3:6], None, g_rec, None, False, C, False, (1.0, seed, False))
+    with torch.cuda.stream(side):
+        step()                                                            # warm-up outside the capture (epoch 1)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    runs = []
+    for _ in range(3):                                                    # epochs 2, 3, 4
+        graph.replay()
+        torch.cuda.synchronize()
+        runs.append({k: v.clone() for k, v in out.items()})
+    assert not torch.equal(runs[0]["z"], runs[1]["z"]) and not torch.equal(runs[1]["z"], runs[2]["z"])
+    assert not torch.equal(runs[0]["z"], z_eager)
+    assert not torch.equal(runs[0]["rec"], runs[1]["rec"])
+    # reproducible: the same epochs give the same numbers
+    ops.rng_epoch_reset()
+    ops.rng_epoch_bump()                                                  # epoch 1 (the warm-up's)
+    for i in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        for k in out:
+            assert torch.equal(out[k], runs[i][k]), (i, k)
+    # the backward of a replay used that replay's forward noise: an eager backward with explicit noise differs per epoch,
+    # and two replays' gradients differ
+    assert not torch.equal(runs[0]["graw"], runs[1]["graw"])
+    ops.rng_epoch_reset()
+    assert torch.equal(ops.coarse_z(rays, S, False, None, seed), z_eager)
+    ops.poll_status()
