@@ -324,6 +324,203 @@ __global__ void __launch_bounds__(DX_THREADS, 1) k_gemm_dx(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// The seven trunk dX GEMMs (layers 7..1: dZ_{l-1} = relu'(H_{l-1}) * (dZ_l W_l)) as ONE persistent launch.  A tile's dZ
+// never returns from HBM between layers: the epilogue builds dZ_{l-1} in shared memory as the operand image (in place
+// over dZ_l, whose MMAs are complete), the next layer's MMAs read it from there, and a bulk store sends the same bytes to
+// the gradient-image slot the dW GEMM reads later.  Two tiles (X, Y) are in flight per CTA - one 64 KB image buffer and
+// one 256-column accumulator each - so that the epilogue of one overlaps the MMAs of the other; the weight tiles stream
+// through a 3-stage ring of 32 KB (from L2: 896 KB per network).  warps 0-7 epilogue, 8 producer, 9 issuer.
+// Measured (B200, 1536 tiles): 231 us against 7 x 42 us for the per-layer launches = 2.75 us per tile-layer.  The bound
+// is SHARED-MEMORY bandwidth, as for the SS forward: per tile-layer the MMAs read A 64 KB + B 128 KB, the ring takes
+// 128 KB of weight writes, the epilogue stores 64 KB and the bulk store reads them again - 448 KB = 3500 cycles at
+// 128 B/clk against 2176 cycles of MMAs.  It is not HBM (0.70 GB of gradient images leave at 3.0 TB/s; a fill kernel
+// writes 7.4 TB/s on this board) and not L2: CL = 2 (INRF_DX_CHAIN=2, A/B only), where the two CTAs of a cluster run
+// in lock-step and share every weight fetch by multicast, halves the 6 TB/s of L2 -> SM weight traffic and changes
+// nothing (240 us) - the multicast still writes every byte into both rings.  Lock-step needs the same trip counts, so
+// a CTA without a (second) tile computes on a clamped one and drops the result.
+// ------------------------------------------------------------------------------------------
+constexpr int CH_LAYERS = 7, CH_NSB = 3, CH_BUF = 4 * IMG_BYTES;
+constexpr int CH_RING = 2 * CH_BUF, CH_BAR = CH_RING + CH_NSB * 32768, CH_SMEM = CH_BAR + 256;
+struct ChainParams {
+  int n_tiles, n_pairs, n_iter;
+  ImgRef in;                         // dZ_7: 4 chunk images per tile
+  const unsigned char* b[CH_LAYERS]; // per layer: 4 K-major weight tiles of 32 KB (k_pack_bwd)
+  ImgRef mask[CH_LAYERS];            // forward stash slot whose ReLU bits gate the layer's output
+  ImgRef out[CH_LAYERS];             // gradient-image slot of the layer's output (4 chunks)
+  int* dbg;
+  int* status;
+};
+enum { CHB_BFULL = 0, CHB_BEMPTY = CH_NSB, CHB_IN_FULL = 2 * CH_NSB, CHB_A_READY = 2 * CH_NSB + 2, CHB_ACC_FULL = 2 * CH_NSB + 4,
+       CHB_BUF_FREE = 2 * CH_NSB + 6, CHB_COUNT = 2 * CH_NSB + 8 };
+
+template <int CL>
+__global__ void __launch_bounds__(DX_THREADS, 1) k_dx_chain(const __grid_constant__ ChainParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar0 = sb + CH_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + CH_BAR + 8 * CHB_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  bool dead = false;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CH_NSB; ++s) { mbar_init(bar0 + 8 * (CHB_BFULL + s), 1); mbar_init(bar0 + 8 * (CHB_BEMPTY + s), CL); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar0 + 8 * (CHB_IN_FULL + t), 1); mbar_init(bar0 + 8 * (CHB_A_READY + t), 8);
+      mbar_init(bar0 + 8 * (CHB_ACC_FULL + t), 1); mbar_init(bar0 + 8 * (CHB_BUF_FREE + t), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc512(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();                      // the peer's barriers exist before any multicast / remote arrive
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // pair `it` of this CTA: tiles 2p and 2p + 1 with p = it * gridDim.x + blockIdx.x.  Every CTA runs n_iter pairs of two
+  // tiles (cluster lock-step); tiles past the end are computed on the last tile's data and not stored.
+  auto pair_of = [&](int it) { return (int64_t)it * gridDim.x + blockIdx.x; };
+  auto clamp_tile = [&](int64_t t) { return t < P.n_tiles ? t : (int64_t)P.n_tiles - 1; };
+  constexpr int nt = 2;
+
+  if (warp == 8) {                                     // ---- producer: tile inputs, then the weight tiles layer by layer
+    const bool leader = elect_one();
+    int slot = 0;
+    uint32_t par_empty = (1u << CH_NSB) - 1, par_free = 3u;        // "empty" / "free" barriers start released
+    for (int it = 0; it < P.n_iter; ++it) {
+      const int64_t p = pair_of(it);
+      if (CL == 1 && p >= P.n_pairs) break;
+      for (int t = 0; t < nt; ++t) {
+        TTC_WAIT(bar0 + 8 * (CHB_BUF_FREE + t), (par_free >> t) & 1u, 11);
+        par_free ^= 1u << t;
+        if (leader && !dead) {
+          const uint32_t full = bar0 + 8 * (CHB_IN_FULL + t);
+          mbar_expect_tx(full, CH_BUF);
+          bulk_g2s(sb + t * CH_BUF, P.in.at(clamp_tile(2 * p + t)), CH_BUF, full);
+        }
+        __syncwarp();
+      }
+      for (int li = 0; li < CH_LAYERS; ++li)
+        for (int t = 0; t < nt; ++t)
+          for (int kc = 0; kc < 4; ++kc) {
+            TTC_WAIT(bar0 + 8 * (CHB_BEMPTY + slot), (par_empty >> slot) & 1u, 12);
+            par_empty ^= 1u << slot;
+            if (leader && !dead) {
+              const uint32_t full = bar0 + 8 * (CHB_BFULL + slot), dst = sb + CH_RING + slot * 32768;
+              mbar_expect_tx(full, 32768);
+              if (CL == 1) bulk_g2s(dst, P.b[li] + kc * 32768, 32768, full);
+              else bulk_g2s_mc(dst + rank * 16384, P.b[li] + kc * 32768 + rank * 16384, 16384, full, (uint16_t)3);
+            }
+            __syncwarp();
+            slot = (slot + 1 == CH_NSB) ? 0 : slot + 1;
+          }
+    }
+  } else if (warp == 9) {                              // ---- MMA issuer
+    const bool leader = elect_one();
+    int slot = 0;
+    uint32_t par_full = 0, par_in = 0, par_ready = 0;
+    const uint32_t idesc = idesc_f16(128, 256, 0, 0);
+    for (int it = 0; it < P.n_iter; ++it) {
+      if (CL == 1 && pair_of(it) >= P.n_pairs) break;
+      for (int li = 0; li < CH_LAYERS; ++li)
+        for (int t = 0; t < nt; ++t) {
+          if (li == 0) { TTC_WAIT(bar0 + 8 * (CHB_IN_FULL + t), (par_in >> t) & 1u, 13); par_in ^= 1u << t; }
+          else { TTC_WAIT(bar0 + 8 * (CHB_A_READY + t), (par_ready >> t) & 1u, 14); par_ready ^= 1u << t; }
+          tc_fence_after();
+          for (int kc = 0; kc < 4; ++kc) {
+            TTC_WAIT(bar0 + 8 * (CHB_BFULL + slot), (par_full >> slot) & 1u, 15);
+            par_full ^= 1u << slot;
+            tc_fence_after();
+            if (leader && !dead) {
+              const uint64_t ad = desc_k_sw128(sb + t * CH_BUF + kc * IMG_BYTES), bd = desc_k_sw128(sb + CH_RING + slot * 32768);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc_mma(tmem + t * 256, ad + 2 * k, bd + 2 * k, idesc, (kc | k) ? 1u : 0u);
+              if (CL == 1) tc_commit(bar0 + 8 * (CHB_BEMPTY + slot));
+              else tc_commit_mc(bar0 + 8 * (CHB_BEMPTY + slot), (uint16_t)3);      // both CTAs' producers learn that this CTA is done with the slot
+            }
+            __syncwarp();
+            slot = (slot + 1 == CH_NSB) ? 0 : slot + 1;
+          }
+          if (leader && !dead) tc_commit(bar0 + 8 * (CHB_ACC_FULL + t));
+          __syncwarp();
+        }
+      // the last layer's output of both tiles still has to be consumed by the epilogue: its A_READY arrivals of that
+      // layer are waited for here so that the parity bookkeeping stays aligned with the next pair
+      for (int t = 0; t < nt; ++t) { TTC_WAIT(bar0 + 8 * (CHB_A_READY + t), (par_ready >> t) & 1u, 16); par_ready ^= 1u << t; }
+    }
+  } else {                                             // ---- epilogue (both tiles, alternately)
+    const int q = warp & 3, jj = warp >> 2, row = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t uoff[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) uoff[u] = img_unit(row, jj * 4 + u);
+    uint32_t par_acc = 0;
+    for (int it = 0; it < P.n_iter; ++it) {
+      const int64_t p = pair_of(it);
+      if (CL == 1 && p >= P.n_pairs) break;
+      for (int li = 0; li < CH_LAYERS; ++li)
+        for (int t = 0; t < nt; ++t) {
+          const bool live = 2 * p + t < P.n_tiles;
+          const int64_t tile = clamp_tile(2 * p + t);
+          const uint32_t stage = sb + t * CH_BUF;
+          const uint32_t* mw = reinterpret_cast<const uint32_t*>(P.mask[li].base + (tile * P.mask[li].tslots + IS_MASK) * (int64_t)IMG_BYTES) +
+                               (P.mask[li].slot - IS_H) * 256 + jj * 128 + row;
+          uint32_t mbits[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mbits[c] = __ldg(mw + c * 256);
+          TTC_WAIT(bar0 + 8 * (CHB_ACC_FULL + t), (par_acc >> t) & 1u, 17);
+          par_acc ^= 1u << t;
+          tc_fence_after();
+          // this buffer's previous image has left shared memory: the stores alternate X, Y, X, ... so only the newest
+          // one (the other tile's) may still be reading
+          if (threadIdx.x == 0) bulk_wait_read1();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+          for (int cp = 0; cp < 4; cp += 2) {                            // two chunks per TMEM load batch
+            uint32_t v0[32], v1[32];
+            tmem_ld32(lane_addr + t * 256 + cp * 64 + jj * 32, v0);
+            tmem_ld32(lane_addr + t * 256 + (cp + 1) * 64 + jj * 32, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t* v = h ? v1 : v0;
+              const uint32_t mb = mbits[cp + h];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float lo = ((mb >> (4 * u + i)) & 1u) ? __uint_as_float(v[8 * u + 2 * i]) : 0.f;
+                  const float hi = ((mb >> (16 + 4 * u + i)) & 1u) ? __uint_as_float(v[8 * u + 2 * i + 1]) : 0.f;
+                  pk[i] = pack_h2(lo, hi);
+                }
+                st_shared_v4(stage + (cp + h) * IMG_BYTES + uoff[u], pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+          tc_fence_before();
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * (CHB_A_READY + t));      // operand of the next layer (and: accumulator drained)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (threadIdx.x == 0 && !dead) {
+            if (live) bulk_s2g(const_cast<unsigned char*>(P.out[li].at(tile, 0)), stage, CH_BUF);
+            else asm volatile("cp.async.bulk.commit_group;" ::: "memory");           // keeps the X, Y, X, ... group order
+            if (li == CH_LAYERS - 1) {                                  // the buffer goes back to the producer for the next pair
+              bulk_wait_read0();
+              mbar_arrive(bar0 + 8 * (CHB_BUF_FREE + t));
+            }
+          }
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();                      // nobody leaves while the peer may still multicast into this CTA
+  if (warp == 9) tmem_dealloc512(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
 // dW GEMM: D[128 out x N in] += sum over the tiles of a split of dZ^T X, both operands MN-major from the images.
 // grid = (items, splits); warps 0-3 epilogue, warp 4 producer, warp 5 issuer; 2-stage ring of (2 + n_x) chunks.
 // Accumulator columns [256, 272) hold dZ^T 1 = the bias gradient.
@@ -623,10 +820,45 @@ int launch_mlp_bwd_tc(const TcBwdArgs& a, cudaStream_t st) {
   INRF_LAUNCH_CHECK();
   INRF_CUDA(cudaFuncSetAttribute(k_gemm_dx, cudaFuncAttributeMaxDynamicSharedMemorySize, DX_SMEM));
   const int grid = (int)(T < sms ? T : sms);
-  for (int i = 0; i < ng; ++i) {
+  // the head GEMMs and the trunk-output GEMM one launch each, the seven trunk layers as one chained launch
+  // (INRF_DX_CHAIN=0: one launch per layer, for A/B)
+  static const int chain_mode = getenv("INRF_DX_CHAIN") != nullptr ? atoi(getenv("INRF_DX_CHAIN")) : 1;   // 0 per-layer launches, 2 clusters
+  const bool chain_env = chain_mode != 0;
+  const int n_single = chain_env ? ng - CH_LAYERS : ng;
+  for (int i = 0; i < n_single; ++i) {
     G[i].n_iter = (int)((T + grid - 1) / grid);
     k_gemm_dx<<<grid, DX_THREADS, DX_SMEM, st>>>(G[i]);
     INRF_LAUNCH_CHECK();
+  }
+  if (chain_env) {
+    ChainParams Cp;
+    memset(&Cp, 0, sizeof(Cp));
+    Cp.n_tiles = (int)T; Cp.n_pairs = (int)((T + 1) / 2); Cp.dbg = dbg; Cp.status = status;
+    Cp.in = G[n_single].a[0];                       // dZ_7: the trunk-output GEMM's four output images
+    for (int li = 0; li < CH_LAYERS; ++li) {
+      const DxParams& g = G[n_single + li];
+      Cp.b[li] = g.b; Cp.mask[li] = g.mask; Cp.out[li] = g.out;
+    }
+    int cl = (chain_mode == 2 && Cp.n_pairs >= 2) ? 2 : 1;
+    int cgrid = Cp.n_pairs < sms ? Cp.n_pairs : sms;
+    cgrid = cgrid / cl * cl;                         // whole clusters only
+    Cp.n_iter = (Cp.n_pairs + cgrid - 1) / cgrid;
+    void (*kern)(ChainParams) = cl == 2 ? k_dx_chain<2> : k_dx_chain<1>;
+    INRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cgrid);
+    cfg.blockDim = dim3(DX_THREADS);
+    cfg.dynamicSmemBytes = CH_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    INRF_CUDA(cudaLaunchKernelEx(&cfg, kern, Cp));
+    note_launch();
   }
 
   // ---- dW: one launch, one item per (GEMM, 128 output rows) --------------------------------------------
