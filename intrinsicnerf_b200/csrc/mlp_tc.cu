@@ -927,6 +927,12 @@ struct Issuer {
   }
 };
 
+// HY (hybrid, round 2): trunk layers 1..7 take their A operand from tensor memory like the TS variant (the epilogue packs
+// layers 0..6 into the drained accumulator), layer 7's output goes to the shared-memory H buffer and the tail below runs
+// unchanged - the networks whose tail does not fit the TS layout (Semantic_NeRF: views' | sem1 | albedo1 | shading1 need
+// 512 accumulator columns next to the packed trunk output; endpoint feature) still drop seven layers of activation
+// traffic from shared memory.
+template <bool HY>
 __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
   Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
@@ -957,7 +963,8 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
         first = false;
       }
       for (int c = 0; c < 4; ++c) {
-        I.fill_mma<4>(H + c * CHUNK, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
+        if (HY) I.fill_mma_ts<4>(((l & 1) ? A0 : A1) + 32u * c, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);   // packed output of layer l-1
+        else I.fill_mma<4>(H + c * CHUNK, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
         first = false;
       }
       I.commit(B_ACC_FULL + (l & 1));
@@ -1116,7 +1123,11 @@ __device__ __forceinline__ void epi_layer(bool add_bias, uint32_t taddr, const f
 
 __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x)); }
 
-template <bool STASH>
+template <int MODE>
+__device__ __forceinline__ void epi_acc_ts(int fine, uint32_t src, uint32_t dst, int n_chunks, int jj, int lane, Sync& sy, int ready_bar0,
+                                           const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar);
+
+template <bool STASH, bool HY>
 __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* smem, uint32_t smem_base, uint32_t tmem,
                                          int q, int jj, int lane) {
   const int row = q * 32 + lane;
@@ -1152,7 +1163,10 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
       sy.wait(B_ACC_FULL + (l & 1));
       tc_fence_after();
       if (l == 7) epi_layer<1>(add_bias, lane_addr + A1, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, MSLOT(IS_H + 28), amax, ST);
-      else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, MSLOT(IS_H + 4 * l), amax, ST);
+      else if (HY) {                                   // hybrid: packed halves back into the drained accumulator (see issuer)
+        const uint32_t R = lane_addr + ((l & 1) ? A1 : A0);
+        epi_acc_ts<0>(P.ts_fine, R, R, 4, jj, lane, sy, B_A_READY, nullptr, nullptr, amax, 2 + q);
+      } else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, MSLOT(IS_H + 4 * l), amax, ST);
     }
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
@@ -1509,7 +1523,7 @@ __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* 
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <int CL, bool STASH, bool TS = false>
+template <int CL, bool STASH, bool TS = false, bool HY = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -1587,12 +1601,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
   } else if (STASH && warp == 13) {
     stasher(P, sy, smem_base);
   } else if (warp == 15) {
-    if (TS) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer(P, sy, smem_base, tmem, CL, smem_base + SM_ONES);
+    if (TS) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer<HY>(P, sy, smem_base, tmem, CL, smem_base + SM_ONES);
   } else if (warp >= 8 && warp < 12) {
     front_end<STASH>(P, sy, role_base, (warp - 8) * 32 + lane);
   } else if (warp < 8) {
     if (TS) epilogue_ts(P, sy, smem, tmem, warp & 3, warp >> 2, lane);
-    else epilogue<STASH>(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
+    else epilogue<STASH, HY>(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
   }
   if (sy.prof != nullptr) sy.prof[63] = clock64() - t_start;
   tc_fence_before();
@@ -1705,9 +1719,13 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   P.ts_fine = ts_mode == 2 ? 1 : 0;
   static const int ns_env = getenv("INRF_TC_NS") ? atoi(getenv("INRF_TC_NS")) : 0;
   const bool ts = ts_env && !a.stash_img && a.n_classes == 0 && !a.endpoint && a.variant == INRF_NET_OBJECT && P.bias_mma;
+  // every other inference launch: TS trunk + shared-memory tail (INRF_TC_HY=0 keeps those on the SS kernel)
+  static const bool hy_env = !(getenv("INRF_TC_HY") != nullptr && getenv("INRF_TC_HY")[0] == '0');
+  const bool hy = ts_env && hy_env && !ts && !a.stash_img && P.bias_mma;
   P.ns = ts ? ((ns_env >= 2 && ns_env <= tc::NS_MAX) ? ns_env : tc::NS_MAX) : tc::NS;
   void (*kern)(tc::Params) = a.stash_img ? (cl == 2 ? tc::k_mlp_tc<2, true> : tc::k_mlp_tc<1, true>)
                              : ts ? (cl == 2 ? tc::k_mlp_tc<2, false, true> : tc::k_mlp_tc<1, false, true>)
+                             : hy ? (cl == 2 ? tc::k_mlp_tc<2, false, false, true> : tc::k_mlp_tc<1, false, false, true>)
                                   : (cl == 2 ? tc::k_mlp_tc<2, false> : tc::k_mlp_tc<1, false>);
   INRF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SM_TOTAL));
   cudaLaunchConfig_t cfg = {};
