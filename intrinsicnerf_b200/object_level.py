@@ -177,13 +177,15 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             z_vals, z_std = ops.merge_sorted(z_vals, z_samples)
             raw = query(z_vals, network_fn if network_fine is None else network_fine)
             rec, weights = ops.composite(raw[..., :11], z_vals, rays_d, None if in_kernel_rng else draw_noise(N, St), white_bkgd, rng=rng_f)
+        maps = ops.split_rec(rec)                       # under autograd: one backward kernel for all maps (ops.SplitRecFn)
         for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
-            ret[k + "_map"] = _split_rec(rec, k)
+            ret[k + "_map"] = maps[k]
         if retraw:
             ret["raw"] = raw
         if N_importance > 0:
+            maps0 = ops.split_rec(rec0)
             for k in ("rgb", "disp", "acc", "albedo", "shading", "residual"):
-                ret[k + "0"] = _split_rec(rec0, k)
+                ret[k + "0"] = maps0[k]
             ret["z_std"] = z_std
     if DEBUG:
         for k in ret:

@@ -344,6 +344,7 @@ class CompositeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, rng=None):
+        ctx.set_materialize_grads(False)            # an unused `weights` output costs no zero-fill and no extra read in the backward
         rec, w = raw2outputs_rec(raw.detach(), z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True, rng)
         ctx.save_for_backward(raw.detach(), z_vals, rays_d, noise if noise is not None else torch.empty(0))
         ctx.cfg = (bool(white_bkgd), int(n_classes), bool(endpoint), noise is not None, rng)
@@ -367,6 +368,64 @@ def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_classes=0, en
     if torch.is_grad_enabled() and raw.requires_grad:
         return CompositeFn.apply(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, rng)
     return raw2outputs_rec(raw, z_vals, rays_d, noise, white_bkgd, n_classes, endpoint, True, rng)
+
+
+REC_LAYOUT = (("rgb", 0, 3), ("disp", 3, 4), ("acc", 4, 5), ("albedo", 5, 8), ("shading", 8, 9), ("residual", 9, 12), ("depth", 12, 13))
+_ZERO_BLOCKS = {}
+
+
+def _zero_block(n, width, device):
+    """Read-only zeros [n, width] (cached): the gradient of a record column block nobody differentiated."""
+    key = (n, width, str(device))
+    z = _ZERO_BLOCKS.get(key)
+    if z is None:
+        if len(_ZERO_BLOCKS) > 64:
+            _ZERO_BLOCKS.clear()
+        z = torch.zeros(n, width, dtype=torch.float32, device=device)
+        _ZERO_BLOCKS[key] = z
+    return z
+
+
+def _rec_blocks(width, n_classes, endpoint):
+    blocks = list(REC_LAYOUT)
+    if n_classes > 0:
+        blocks.append(("sem", REC_BASE, REC_BASE + n_classes))
+    if endpoint:
+        blocks.append(("feat", REC_BASE + n_classes, REC_BASE + n_classes + 128))
+    if blocks[-1][2] != width:
+        raise ValueError(f"record has {width} columns, expected {blocks[-1][2]}")
+    return blocks
+
+
+class SplitRecFn(torch.autograd.Function):
+    """The packed per-ray record -> its maps, with ONE kernel in the backward.  Plain slicing under autograd costs a
+    zero-filled [N, 13+C] tensor, a slice copy and an accumulation per map that receives a gradient - 40 small kernels per
+    training step for the 2 x 8 maps of a coarse + fine render; here the incoming map gradients are concatenated in
+    column order (cached zero blocks for the maps without a gradient)."""
+
+    @staticmethod
+    def forward(ctx, rec, n_classes, endpoint):
+        ctx.set_materialize_grads(False)
+        blocks = _rec_blocks(rec.shape[1], n_classes, endpoint)
+        ctx.blocks, ctx.n, ctx.dev = blocks, rec.shape[0], rec.device
+        r = rec.detach()
+        return tuple(r[:, a:b] if b - a > 1 else r[:, a] for _, a, b in blocks)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        parts = [_zero_block(ctx.n, b - a, ctx.dev) if g is None else g.reshape(ctx.n, b - a) for (_, a, b), g in zip(ctx.blocks, grads)]
+        return torch.cat(parts, 1), None, None
+
+
+def split_rec(rec, n_classes=0, endpoint=False):
+    """dict of the record's maps: rgb [N,3], disp [N], acc [N], albedo [N,3], shading [N], residual [N,3], depth [N],
+    (sem [N,C]), (feat [N,128]) - views of `rec`; under autograd through SplitRecFn."""
+    blocks = _rec_blocks(rec.shape[1], n_classes, endpoint)
+    if torch.is_grad_enabled() and rec.requires_grad:
+        outs = SplitRecFn.apply(rec, n_classes, endpoint)
+    else:
+        outs = tuple(rec[:, a:b] if b - a > 1 else rec[:, a] for _, a, b in blocks)
+    return {name: o for (name, _, _), o in zip(blocks, outs)}
 
 
 LOSS_TERMS = ("img", "chroma", "residual", "reflect_sparsity", "shading_smooth", "far_reflect", "intensity", "cluster")

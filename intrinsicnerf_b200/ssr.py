@@ -248,10 +248,11 @@ class SSRRenderer:
         rec_c, w_c = ops.composite(raw_c, z, rays_d, None, self.white_bkgd, C, False, (std, seed, False))
         ret = {"raw_coarse": raw_c}
         names = ("rgb", "disp", "acc", "depth", "albedo", "shading", "residual")
+        maps = ops.split_rec(rec_c, C, False)            # one backward kernel instead of a fill + copy + add per map
         for k in names:
-            ret[k + "_coarse"] = _split_rec(rec_c, k)
+            ret[k + "_coarse"] = maps[k]
         if C > 0:
-            ret["sem_logits_coarse"] = rec_c[:, 13:13 + C]
+            ret["sem_logits_coarse"] = maps["sem"]
         if Sf > 0:
             z_mid = .5 * (z[:, 1:] + z[:, :-1])
             z_samples = ops.sample_pdf(z_mid, w_c[:, 1:-1].detach(), Sf, None, seed=None if det else seed)[0]
@@ -259,14 +260,15 @@ class SSRRenderer:
             ep = bool(self.endpoint_feat)
             raw_f = query(z_f, self.ssr_net_fine, ep)
             rec_f, _ = ops.composite(raw_f, z_f, rays_d, None, self.white_bkgd, C, ep, (std, seed, True))
+            maps = ops.split_rec(rec_f, C, ep)
             for k in names:
-                ret[k + "_fine"] = _split_rec(rec_f, k)
+                ret[k + "_fine"] = maps[k]
             if C > 0:
-                ret["sem_logits_fine"] = rec_f[:, 13:13 + C]
+                ret["sem_logits_fine"] = maps["sem"]
             ret["z_std"] = z_std
             ret["raw_fine"] = raw_f
             if ep:
-                ret["feat_map_fine"] = rec_f[:, 13 + C:13 + C + 128]
+                ret["feat_map_fine"] = maps["feat"]
         return ret
 
     def render_record(self, flat_rays):

@@ -107,3 +107,23 @@ def test_struct_layouts_match_header(tmp_path):
     assert [int(out[0]), int(out[1])] == [C.sizeof(_lib.RenderCfg), C.sizeof(_lib.FramePlanes)]
     want = [getattr(_lib.RenderCfg, f).offset for f in fields_cfg] + [getattr(_lib.FramePlanes, f).offset for f in fields_pl]
     assert [int(x) for x in out[2:]] == want
+
+
+def test_split_rec_gradient_equals_slicing():
+    """ops.SplitRecFn (one concatenation in the backward) == autograd through plain column slices of the record."""
+    import torch
+    from intrinsicnerf_b200 import ops
+    torch.manual_seed(0)
+    for C, ep in ((0, False), (5, False), (5, True)):
+        W = 13 + C + (128 if ep else 0)
+        rec = torch.randn(9, W, requires_grad=True)
+        m = ops.split_rec(rec, C, ep)
+        loss = (m["rgb"] ** 2).sum() + m["shading"].sum() * 3 + (m["albedo"] * 2).sum() + (m["sem"].sum() if C else 0) + (m["feat"].mean() if ep else 0)
+        loss.backward()
+        ref = rec.detach().clone().requires_grad_(True)
+        want = (ref[:, 0:3] ** 2).sum() + ref[:, 8].sum() * 3 + (ref[:, 5:8] * 2).sum() + (ref[:, 13:13 + C].sum() if C else 0) + (ref[:, 13 + C:].mean() if ep else 0)
+        want.backward()
+        assert torch.equal(rec.grad, ref.grad)
+        assert torch.equal(m["disp"], rec.detach()[:, 3]) and m["rgb"].shape == (9, 3)
+        with torch.no_grad():
+            assert torch.equal(ops.split_rec(rec, C, ep)["residual"], rec[:, 9:12])
