@@ -74,9 +74,10 @@ enum {
   B_RAW_FREE = B_RAW_READY + 2,  // [2] both back-end warps have consumed the slot
   B_ST_DONE = B_RAW_FREE + 2,    // [4] training: the stash copy of H chunk c has left shared memory (the chunk may be rewritten)
   B_STV_DONE = B_ST_DONE + 4,    // training: the same for the two relu(views') chunks in the PE|DIR region
-  B_COUNT
+  B_ACC_FIRST,                 // [2] split hand-off (Params.split_nf): accumulator columns [0, split_nf) of a trunk layer complete
+  B_COUNT = B_ACC_FIRST + 2
 };
-static_assert(B_COUNT <= 40, "barrier area");
+static_assert(B_COUNT <= 48, "barrier area");
 
 struct Params {
   MlpArgs a;
@@ -90,6 +91,10 @@ struct Params {
   int n_iter;                     // tile iterations per CTA (identical for every CTA: cluster lock-step)
   int ts_fine;                    // TS variant: 1 = one K chunk per TMEM load batch (INRF_TC_TS=2)
   int ns;                         // weight ring stages in use (4, or 6 in the TS variant)
+  int split_nf;                   // TS / HY trunk layers 1..7: the MMAs of the LAST K chunk are issued as N = split_nf (output
+                                  // columns [0, split_nf), committed to B_ACC_FIRST) + N = 256 - split_nf, so the drain of the
+                                  // first output chunk starts split_nf/256 of a K chunk after the last input chunk arrived
+                                  // instead of a whole K chunk (512 cycles) after it.  0 = off, 64 or 128
   int fuse;                       // 1: composite (and resample) in-kernel, CTAs walk CONTIGUOUS tiles (whole rays per CTA)
   FuseArgs f;
   int* dbg;                       // [16] per-launch abort / claim words (device, cleared before every launch)
@@ -98,11 +103,19 @@ struct Params {
   int fault;                      // test hook (INRF_TC_FAULT=n, first n launches): the weight producer stops after three fills
   long long* prof;                // optional wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
+  int exp_flags;                  // timing experiments (INRF_TC_EXP): 1 = the issuer skips tcgen05.fence::after_thread_sync per fill
   int stash_abl;                  // timing experiment (INRF_TC_STASH_ABL): 1 no mask words, 2 no bulk copies, 4 no "copy has read" waits
 };
 
 __device__ int g_dbg[16];
 __device__ long long g_prof[5 * 128];
+#ifdef INRF_TC_TIMELINE
+// development build (tools/gpu_timeline.sh): clock64 stamps of the issuer and of two epilogue warps of CTA 0 for two
+// steady-state tiles; printed by the launcher.  (stamp << 4) | kind
+constexpr int TL_CAP = 1024, TL_IT0 = 10, TL_IT1 = 11;
+__device__ long long g_tl[3 * TL_CAP];
+__device__ int g_tl_n[3];
+#endif
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -241,6 +254,16 @@ struct Sync {             // lives in registers (never escapes by address)
   long long* prof;        // wait-cycle counters of this role (CTA 0, one thread per role) or nullptr
   bool dead;
   int tile;
+#ifdef INRF_TC_TIMELINE
+  long long* tl; int tl_n; int it;
+  __device__ __forceinline__ void stamp(int kind) {
+    if (tl != nullptr && (it == TL_IT0 || it == TL_IT1) && tl_n < TL_CAP) tl[tl_n++] = (clock64() << 4) | kind;
+  }
+  __device__ __forceinline__ void set_it(int i) { it = i; }
+#else
+  __device__ __forceinline__ void stamp(int) {}
+  __device__ __forceinline__ void set_it(int) {}
+#endif
   __device__ __forceinline__ uint32_t addr(int id) const { return bar0 + 8u * id; }
   __device__ __forceinline__ uint32_t take_parity(int id) {       // consume the next phase of barrier id
     const uint32_t parity = (uint32_t)((phase >> id) & 1ull);
@@ -500,7 +523,7 @@ __device__ __noinline__ void resample_ray(const Params& P, int64_t ray, const Ra
   for (int e = 0; e < 6; ++e) zo[rank[e]] = v[e];
 }
 
-// `which` = 0 / 1: front-end warps 0 and 2 share the work by ray parity (a ray is always handled by one warp, so its
+// `which` = 0 / 1: the two back-end warps share the work by ray parity (a ray is always handled by one warp, so its
 // running transmittance stays in that warp's registers)
 template <bool SAMPLER>
 __device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, int lane, RayState& rs, int which) {
@@ -619,12 +642,6 @@ struct RowAddr {
 
 template <bool STASH>
 __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
-  RayState rs;                                           // fused mode, warps 0 and 2 of the front end only
-  rs.carry = 1.f;
-  const bool backend = !STASH && P.fuse && (row < 32 || (row >= 64 && row < 96));   // (no fused back end in the training instantiation)
-  const int which = row >= 64 ? 1 : 0;
-  const int blane = row & 31;
-  const bool sampler = P.f.n_importance > 0;
   RowAddr ra;
 #pragma unroll
   for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
@@ -713,12 +730,19 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
 #pragma unroll
       for (int u = 0; u < 4; ++u) st_global_v4(g + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     }
-    if (!STASH && backend && it > 0) {           // composite (and resample) the previous tile while this one is in the pipe
-      if (sampler) ray_backend<true>(P, sy, it - 1, blane, rs, which); else ray_backend<false>(P, sy, it - 1, blane, rs, which);
-    }
   }
-  if (!STASH && backend && P.n_iter > 0) {       // the last tile of this CTA
-    if (sampler) ray_backend<true>(P, sy, P.n_iter - 1, blane, rs, which); else ray_backend<false>(P, sy, P.n_iter - 1, blane, rs, which);
+}
+
+// ray back end of the fused renderer: warps 12 and 13 (idle otherwise in the inference kernels) share the rays by parity.
+// It used to run on front-end warps 0 and 2 after each tile's encoding; the encoding alone keeps a front-end warp busy
+// for ~11 600 of a tile's ~30 000 cycles, and once the lean issuer had shortened the tile the sum no longer fitted:
+// the fused launches lost 3 us per tile waiting for gamma(x) of the next tile.
+__device__ __forceinline__ void backend_role(const Params& P, Sync& sy, int which, int lane) {
+  RayState rs;
+  rs.carry = 1.f;
+  const bool sampler = P.f.n_importance > 0;
+  for (int it = 0; it < P.n_iter; ++it) {
+    if (sampler) ray_backend<true>(P, sy, it, lane, rs, which); else ray_backend<false>(P, sy, it, lane, rs, which);
   }
 }
 
@@ -823,6 +847,7 @@ struct Issuer {
   int cl;
   int bias_mma;
   int no_weights;
+  int exp_flags;
   bool leader;
   // probe-ahead state: the barriers of the NEXT fill are tested (non-blocking) before the MMAs of
   // the current fill are issued, so the mbarrier round trip overlaps the issue of tcgen05.mma
@@ -836,6 +861,7 @@ struct Issuer {
   // start probing the fill that will be consumed next (ring slot `slot`), optionally with an activation barrier
   __device__ __forceinline__ void probe(int act_bar) {
     pa_bar = act_bar;
+    sy.stamp(14);
     pw_par = sy.take_parity(B_WFULL + slot);
     pw_ok = no_weights ? 1u : mbar_test(sy.addr(B_WFULL + slot), pw_par);
     pa_ok = 1u;
@@ -843,21 +869,38 @@ struct Issuer {
       pa_par = sy.take_parity(act_bar);
       pa_ok = mbar_test(sy.addr(act_bar), pa_par);
     }
+    sy.stamp(15);
   }
   // the probed fill is usable (falls back to blocking waits when the probe said "not yet")
   __device__ __forceinline__ void acquire() {
     if (!pw_ok) sy.slow(B_WFULL + slot, pw_par);
     if (!pa_ok) sy.slow(pa_bar, pa_par);
-    tc_fence_after();
+    sy.stamp(13);                                     // barriers passed
+    if (!(exp_flags & 1)) tc_fence_after();
+    sy.stamp(1);                                      // fill acquired (weights + activation chunk)
   }
-  __device__ __forceinline__ void release() {        // MMAs reading the slot are done -> refill
+  __device__ __forceinline__ void release_slot(int s) {   // MMAs reading slot s are done -> refill
     if (!no_weights && leader) {
-      if (cl == 1) tc_commit(sy.addr(B_WEMPTY + slot));
-      else tc_commit_mc(sy.addr(B_WEMPTY + slot), (uint16_t)((1u << cl) - 1u));
+      if (cl == 1) tc_commit(sy.addr(B_WEMPTY + s));
+      else tc_commit_mc(sy.addr(B_WEMPTY + s), (uint16_t)((1u << cl) - 1u));
     }
     __syncwarp();
   }
-  __device__ __forceinline__ void advance() { slot = (slot + 1 == ns) ? 0 : slot + 1; }
+  __device__ __forceinline__ void release() { release_slot(slot); }
+  // end of a fill: release the slot, move on, probe the next fill's barriers.  exp_flags & 2: probe BEFORE the commit
+  __device__ __forceinline__ void finish(int next_act) {
+    if (exp_flags & 2) {
+      const int old = slot;
+      advance();
+      if (next_act != -2) probe(next_act);
+      release_slot(old);
+    } else {
+      release();
+      advance();
+      if (next_act != -2) probe(next_act);
+    }
+  }
+  __device__ __forceinline__ void advance() { slot = (slot + 1 == ns) ? 0 : slot + 1; sy.stamp(2); }   // fill issued
   // K = 16*KSTEPS of A chunk `a_chunk` times the operand tile at byte offset `b_off` of slot `sl`
   template <int KSTEPS>
   __device__ __forceinline__ void mma(uint32_t a_chunk, uint32_t b_addr, int n, uint32_t col, bool first) {
@@ -887,9 +930,17 @@ struct Issuer {
   __device__ __forceinline__ void fill_mma_ts(uint32_t a_col, int n, uint32_t col, bool first, int next_act) {
     acquire();
     mma_ts<KSTEPS>(a_col, slot_addr(), n, col, first);
-    release();
-    advance();
-    if (next_act != -2) probe(next_act);
+    finish(next_act);
+  }
+  // last K chunk of a trunk layer, split hand-off: output columns [0, nf) first (N = nf, weight-tile rows [0, nf)), commit
+  // `first_bar`, then the other 256 - nf columns.  Same products, same accumulation order per column as one N = 256 MMA.
+  template <int KSTEPS>
+  __device__ __forceinline__ void fill_mma_ts_split(uint32_t a_col, int nf, uint32_t col, bool first, int first_bar, int next_act) {
+    acquire();
+    mma_ts<KSTEPS>(a_col, slot_addr(), nf, col, first);
+    commit(first_bar);
+    mma_ts<KSTEPS>(a_col, slot_addr() + (uint32_t)nf * 128u, 256 - nf, col + (uint32_t)nf, first);
+    finish(next_act);
   }
   // whole fill = one operand tile.  `next_act`: activation barrier of the FOLLOWING fill (-1 none,
   // -2: do not probe ahead - the caller probes after doing something else)
@@ -897,9 +948,7 @@ struct Issuer {
   __device__ __forceinline__ void fill_mma(uint32_t a_chunk, int n, uint32_t col, bool first, int next_act) {
     acquire();
     mma<KSTEPS>(a_chunk, slot_addr(), n, col, first);    // MMAs first: their issue is on the critical path
-    release();
-    advance();
-    if (next_act != -2) probe(next_act);                  // the probe's round trip overlaps MMA execution
+    finish(next_act);                                     // the probe's round trip overlaps MMA execution
   }
   // two N=128 accumulators initialised from the two 128-row bias sub-blocks of ONE fill (albedo1 | shading1 in TS mode)
   __device__ __forceinline__ bool bias2(uint32_t col_a, uint32_t col_b, int next_act) {
@@ -920,9 +969,7 @@ struct Issuer {
     if (bias_mma && leader)
       tc_mma(tmem + col, make_desc_flat(ones, 128, 0), make_desc_flat(slot_addr(), 128, 256), make_idesc(n), 0u);
     __syncwarp();
-    release();
-    advance();
-    if (next_act != -2) probe(next_act);
+    finish(next_act);
     return bias_mma != 0;
   }
 };
@@ -934,7 +981,7 @@ struct Issuer {
 // traffic from shared memory.
 template <bool HY>
 __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
-  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
+  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, P.exp_flags, elect_one(), 1u, 1u, 0u, 0u, -1};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
   const bool sem = P.C > 0;
   const int nv = sem ? 256 : 128;       // views' [| sem1] width
@@ -963,7 +1010,8 @@ __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_
         first = false;
       }
       for (int c = 0; c < 4; ++c) {
-        if (HY) I.fill_mma_ts<4>(((l & 1) ? A0 : A1) + 32u * c, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);   // packed output of layer l-1
+        if (HY && c == 3 && P.split_nf) I.fill_mma_ts_split<4>(((l & 1) ? A0 : A1) + 96u, P.split_nf, acc, first, B_ACC_FIRST + (l & 1), -1);
+        else if (HY) I.fill_mma_ts<4>(((l & 1) ? A0 : A1) + 32u * c, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);   // packed output of layer l-1
         else I.fill_mma<4>(H + c * CHUNK, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
         first = false;
       }
@@ -1125,7 +1173,10 @@ __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + expf(-x
 
 template <int MODE>
 __device__ __forceinline__ void epi_acc_ts(int fine, uint32_t src, uint32_t dst, int n_chunks, int jj, int lane, Sync& sy, int ready_bar0,
-                                           const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar);
+                                           const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar, int c_begin = 0);
+template <int MODE>
+__device__ __forceinline__ void epi_trunk_ts(const Params& P, int l, uint32_t R, int jj, int lane, Sync& sy,
+                                             const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar);
 
 template <bool STASH, bool HY>
 __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* smem, uint32_t smem_base, uint32_t tmem,
@@ -1160,13 +1211,15 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
     uint32_t amax = 0u;                                  // running max of every fp16 activation this thread stored
     const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;   // accumulator roles swap every tile (see issuer)
     for (int l = 0; l < 8; ++l) {
+      if (HY && l < 7) {                               // hybrid: packed halves back into the drained accumulator (see issuer)
+        epi_trunk_ts<0>(P, l, lane_addr + ((l & 1) ? A1 : A0), jj, lane, sy, nullptr, nullptr, amax, 2 + q);
+        continue;
+      }
+      if (HY && P.split_nf) sy.wait(B_ACC_FIRST + 1);  // layer 7 of the hybrid goes to shared memory two chunks per batch
       sy.wait(B_ACC_FULL + (l & 1));
       tc_fence_after();
       if (l == 7) epi_layer<1>(add_bias, lane_addr + A1, P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, s_alpha, &sig, nullptr, MSLOT(IS_H + 28), amax, ST);
-      else if (HY) {                                   // hybrid: packed halves back into the drained accumulator (see issuer)
-        const uint32_t R = lane_addr + ((l & 1) ? A1 : A0);
-        epi_acc_ts<0>(P.ts_fine, R, R, 4, jj, lane, sy, B_A_READY, nullptr, nullptr, amax, 2 + q);
-      } else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, MSLOT(IS_H + 4 * l), amax, ST);
+      else epi_layer<0>(add_bias, lane_addr + ((l & 1) ? A1 : A0), P.bias + l * 256, H, 4, ra, jj, lane, sy, -1, B_A_READY, nullptr, nullptr, nullptr, MSLOT(IS_H + 4 * l), amax, ST);
     }
     s_sig[row * 2 + jj] = sig;                         // fixed-order sum later: deterministic sigma
     // ---- relu(views') -> V (PE|DIR region; its last readers finished with accumulator 0); runs while
@@ -1259,19 +1312,23 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 // the stores.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
-  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
+  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, P.exp_flags, elect_one(), 1u, 1u, 0u, 0u, -1};
   const uint32_t PE = smem_base + SM_PE, DIR = smem_base + SM_DIR;
   I.probe(-1);
   for (int it = 0; it < P.n_iter; ++it) {
     sy.tile = it;
+    sy.set_it(it);
+    sy.stamp(3);                                      // tile begins
     const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;
     sy.wait(B_F_READY);
+    sy.stamp(4);
     {
       const bool init = I.bias(256, A0, -1);
       I.fill_mma<4>(PE, 256, A0, !init, -1);
       I.commit(B_ACC_FULL + 0);
     }
     sy.wait(B_TAIL_DONE);
+    sy.stamp(5);
     for (int l = 1; l < 8; ++l) {
       const uint32_t acc = (l & 1) ? A1 : A0, src = (l & 1) ? A0 : A1;      // input = packed output of layer l-1
       bool first = !I.bias(256, acc, l == 5 ? -1 : B_A_READY + 0);
@@ -1280,7 +1337,8 @@ __device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t sm
         first = false;
       }
       for (int c = 0; c < 4; ++c) {
-        I.fill_mma_ts<4>(src + 32u * c, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
+        if (c == 3 && P.split_nf) I.fill_mma_ts_split<4>(src + 96u, P.split_nf, acc, first, B_ACC_FIRST + (l & 1), -1);
+        else I.fill_mma_ts<4>(src + 32u * c, 256, acc, first, c < 3 ? B_A_READY + c + 1 : -1);
         first = false;
       }
       I.commit(B_ACC_FULL + (l & 1));
@@ -1310,6 +1368,7 @@ __device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t sm
     }
     // ---- residual head on relu(views') (A0[0,64)) -> A0[64,80) ---------------------------------------------------
     sy.wait(B_V_READY);
+    sy.stamp(6);
     {
       I.acquire();
       const uint32_t b_addr = I.slot_addr();
@@ -1326,6 +1385,7 @@ __device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t sm
       const uint32_t b_addr = I.slot_addr();
       for (int c = 0; c < 4; ++c) {
         sy.wait(B_A_READY + c);
+        sy.stamp(7);
         tc_fence_after();
         I.mma_ts<4>((c < 2 ? A1 + 128 + 32u * c : A0 + 128 + 32u * (c - 2)), b_addr + 2048 * c, 16, A0 + 80, c == 0);
       }
@@ -1334,6 +1394,275 @@ __device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t sm
       I.probe(-1);
     }
     I.commit(B_SMALL_FULL);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Lean issuer of the TS kernel (round 2, default).  The clock64 timeline of the first TS issuer (tools/gpu_timeline.sh,
+// DESIGN 4b) showed that the issuer warp itself paced the trunk: ~90 dependent SASS instructions per ring fill (probe-ahead
+// state machine, 64-bit parity bookkeeping with variable shifts, loop control, five R2UR per fill) took ~590 cycles against
+// 512 cycles of MMAs, on a scheduler shared with two busy epilogue warps - the tensor pipe idled between fills although
+// weights and activations were ready.  This version keeps the MMA program (and therefore every result bit) and removes the
+// bookkeeping: the tile is unrolled per accumulator parity so operand columns, barrier ids and shifts are immediates,
+// the weight-ring parity is one bit that flips when the slot wraps, and the waits are plain blocking try_waits issued
+// right after the previous fill's MMAs (which execute asynchronously for 512 cycles - nothing to probe ahead for).
+// ------------------------------------------------------------------------------------------
+struct LeanIssuer {
+  Sync& sy;
+  uint32_t ring0, tmem, ones;
+  uint32_t slot, wpar, ns;
+  uint32_t wfull0, wempty0;      // shared-memory addresses of B_WFULL[0] / B_WEMPTY[0]
+  int cl, no_weights, bias_mma;
+  bool leader;
+  __device__ __forceinline__ uint32_t slot_addr() const { return ring0 + slot * (uint32_t)TC_SLOT_BYTES; }
+  // weights of the current fill have landed
+  __device__ __forceinline__ void wait_w() {
+    if (no_weights || sy.dead) return;
+    if (!mbar_try(wfull0 + 8u * slot, wpar)) sy.slow(B_WFULL + (int)slot, wpar);
+  }
+  // the MMAs issued so far are the last readers of the current slot: hand it back to the producer(s), move on
+  __device__ __forceinline__ void next() {
+    if (!no_weights && leader) {
+      if (cl == 1) tc_commit(wempty0 + 8u * slot);
+      else tc_commit_mc(wempty0 + 8u * slot, (uint16_t)((1u << cl) - 1u));
+    }
+    __syncwarp();
+    ++slot;
+    if (slot == ns) { slot = 0; wpar ^= 1u; }
+    sy.stamp(2);
+  }
+  __device__ __forceinline__ void commit(int bar) {
+    if (leader) tc_commit(sy.addr(bar));
+    __syncwarp();
+  }
+  template <int KSTEPS>
+  __device__ __forceinline__ void mma_ts(uint32_t a_col, uint32_t b_addr, int n, uint32_t col, bool first) {
+    const uint64_t bd = make_desc(b_addr);
+    const uint32_t id = make_idesc(n);
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k)
+        tc_mma_ts(tmem + col, tmem + a_col + 8u * k, bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+    }
+    __syncwarp();
+  }
+  template <int KSTEPS>
+  __device__ __forceinline__ void mma_ss(uint32_t a_chunk, uint32_t b_addr, int n, uint32_t col, bool first) {
+    const uint64_t ad = make_desc(a_chunk), bd = make_desc(b_addr);
+    const uint32_t id = make_idesc(n);
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k)
+        tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
+    }
+    __syncwarp();
+  }
+  // accumulator columns [col, col + n) := bias (one K=16 MMA of the constant "ones" tile against the fill's bias block)
+  // (returns false when the bias is added by the epilogue instead: INRF_TC_BIASMMA=0, shared-memory-activation kernel only)
+  __device__ __forceinline__ bool bias(int n, uint32_t col, uint32_t b_off = 0) {
+    if (bias_mma && leader)
+      tc_mma(tmem + col, make_desc_flat(ones, 128, 0), make_desc_flat(slot_addr() + b_off, 128, 256), make_idesc(n), 0u);
+    __syncwarp();
+    return bias_mma != 0;
+  }
+};
+
+// one tile; PAR = it & 1 selects the accumulator roles (A0 / A1 swap every tile, see issuer<>)
+template <int PAR>
+__device__ __forceinline__ void issuer_ts_tile(const Params& P, Sync& sy, LeanIssuer& I, uint32_t PE, uint32_t DIR, const int nf) {
+  constexpr uint32_t A0 = PAR ? 256u : 0u, A1 = 256u - A0;
+  sy.stamp(3);
+  sy.wait(B_F_READY);
+  sy.stamp(4);
+  // ---- trunk layer 0: bias, then K = 64 of gamma(x) ---------------------------------------------------
+  I.wait_w(); sy.stamp(1); I.bias(256, A0); I.next();
+  I.wait_w(); sy.stamp(1); I.mma_ss<4>(PE, I.slot_addr(), 256, A0, false); I.next();
+  I.commit(B_ACC_FULL + 0);
+  sy.wait(B_TAIL_DONE);
+  sy.stamp(5);
+  // ---- trunk layers 1..7: A = packed output of layer l-1 in the other accumulator ----------------------
+#pragma unroll
+  for (int l = 1; l < 8; ++l) {
+    const uint32_t acc = (l & 1) ? A1 : A0, src = (l & 1) ? A0 : A1;
+    I.wait_w(); sy.stamp(1); I.bias(256, acc); I.next();
+    if (l == 5) { I.wait_w(); sy.stamp(1); I.mma_ss<4>(PE, I.slot_addr(), 256, acc, false); I.next(); }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      I.wait_w();
+      sy.wait(B_A_READY + c);
+      tc_fence_after();
+      sy.stamp(1);
+      if (c == 3 && nf) {          // split hand-off: columns [0, nf) first
+        I.mma_ts<4>(src + 96u, I.slot_addr(), nf, acc, false);
+        I.commit(B_ACC_FIRST + (l & 1));
+        I.mma_ts<4>(src + 96u, I.slot_addr() + (uint32_t)nf * 128u, 256 - nf, acc + (uint32_t)nf, false);
+      } else {
+        I.mma_ts<4>(src + 32u * c, I.slot_addr(), 256, acc, false);
+      }
+      I.next();
+    }
+    I.commit(B_ACC_FULL + (l & 1));
+  }
+  // ---- views' on h7 (A1[0,128)) + gamma(d) -> A0[0,128) -------------------------------------------------
+  I.wait_w(); sy.stamp(1); I.bias(128, A0); I.next();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    I.wait_w();
+    sy.wait(B_A_READY + c);
+    tc_fence_after();
+    sy.stamp(1);
+    I.mma_ts<4>(A1 + 32u * c, I.slot_addr(), 128, A0, false);
+    I.next();
+  }
+  I.wait_w(); sy.stamp(1); I.mma_ss<2>(DIR, I.slot_addr(), 128, A0, false); I.next();
+  I.commit(B_ACC_FULL + 0);
+  // ---- albedo1 -> A1[128,256), shading1 -> A0[128,256): both halves of every albedo1|shading1 weight fill -----
+  I.wait_w(); sy.stamp(1); I.bias(128, A1 + 128); I.bias(128, A0 + 128, 4096); I.next();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    I.wait_w();
+    sy.stamp(1);
+    I.mma_ts<4>(A1 + 32u * c, I.slot_addr(), 128, A1 + 128, false);
+    I.mma_ts<4>(A1 + 32u * c, I.slot_addr() + 16384, 128, A0 + 128, false);
+    I.next();
+  }
+  I.commit(B_ACC_FULL + 1);
+  // ---- residual head on relu(views') (A0[0,64)) -> A0[64,80) ---------------------------------------------------
+  sy.wait(B_V_READY);
+  sy.stamp(6);
+  I.wait_w();
+  tc_fence_after();
+  I.mma_ts<4>(A0 + 0, I.slot_addr(), 16, A0 + 64, true);
+  I.mma_ts<4>(A0 + 32, I.slot_addr() + 2048, 16, A0 + 64, false);
+  I.next();
+  I.commit(B_F_FREE);
+  // ---- albedo2 / shading2 on [relu(albedo1) (A1[128,192)) | relu(shading1) (A0[128,192))] -> A0[80,96) -----------
+  I.wait_w();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    sy.wait(B_A_READY + c);
+    sy.stamp(7);
+    tc_fence_after();
+    I.mma_ts<4>((c < 2 ? A1 + 128 + 32u * c : A0 + 128 + 32u * (c - 2)), I.slot_addr() + 2048 * c, 16, A0 + 80, c == 0);
+  }
+  I.next();
+  I.commit(B_SMALL_FULL);
+}
+
+__device__ __forceinline__ void issuer_ts_lean(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
+  LeanIssuer I{sy, smem_base + SM_RING, tmem, ones, 0u, 0u, (uint32_t)P.ns, sy.addr(B_WFULL), sy.addr(B_WEMPTY), cl, P.no_weights, P.bias_mma, elect_one()};
+  const uint32_t PE = smem_base + SM_PE, DIR = smem_base + SM_DIR;
+  const int nf = P.split_nf;
+  for (int it = 0; it < P.n_iter; ++it) {
+    sy.tile = it;
+    sy.set_it(it);
+    if (it & 1) issuer_ts_tile<1>(P, sy, I, PE, DIR, nf);
+    else issuer_ts_tile<0>(P, sy, I, PE, DIR, nf);
+  }
+}
+
+// The same for the shared-memory-activation kernel (HY = false: training forward, INRF_TC_TS=0) and the hybrid (HY = true:
+// Semantic_NeRF / endpoint-feature inference): the MMA program of issuer<HY>, fill for fill.
+template <bool HY, int PAR>
+__device__ __forceinline__ void issuer_lean_tile(const Params& P, Sync& sy, LeanIssuer& I, uint32_t smem_base) {
+  constexpr uint32_t A0 = PAR ? 256u : 0u, A1 = 256u - A0;
+  const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
+  const bool sem = P.C > 0;
+  const int nv = sem ? 256 : 128;       // views' [| sem1] width
+  sy.wait(B_F_READY);
+  // ---- trunk layer 0 ------------------------------------------------------------------------------------
+  {
+    I.wait_w(); const bool init = I.bias(256, A0); I.next();
+    I.wait_w(); I.mma_ss<4>(PE, I.slot_addr(), 256, A0, !init); I.next();
+    I.commit(B_ACC_FULL + 0);
+  }
+  sy.wait(B_TAIL_DONE);
+  // ---- trunk layers 1..7 ----------------------------------------------------------------------------------
+#pragma unroll
+  for (int l = 1; l < 8; ++l) {
+    const uint32_t acc = (l & 1) ? A1 : A0, src = (l & 1) ? A0 : A1;
+    I.wait_w(); bool first = !I.bias(256, acc); I.next();
+    if (l == 5) { I.wait_w(); I.mma_ss<4>(PE, I.slot_addr(), 256, acc, first); I.next(); first = false; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      I.wait_w();
+      sy.wait(B_A_READY + c);
+      tc_fence_after();
+      if (HY) I.mma_ts<4>(src + 32u * c, I.slot_addr(), 256, acc, first);      // packed output of layer l-1 in tensor memory
+      else I.mma_ss<4>(H + c * CHUNK, I.slot_addr(), 256, acc, first);
+      first = false;
+      I.next();
+    }
+    I.commit(B_ACC_FULL + (l & 1));
+  }
+  // ---- views' [| sem1] on the trunk output (shared memory in both variants) -> A0 ---------------------------
+  {
+    I.wait_w(); bool first = !I.bias(nv, A0); I.next();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      I.wait_w();
+      sy.wait(B_A_READY + c);
+      tc_fence_after();
+      I.mma_ss<4>(H + c * CHUNK, I.slot_addr(), nv, A0, first);
+      first = false;
+      I.next();
+    }
+    I.wait_w(); I.mma_ss<2>(DIR, I.slot_addr(), 128, A0, false); I.next();
+    I.commit(B_ACC_FULL + 0);
+  }
+  // ---- albedo1 | shading1 -> A1 --------------------------------------------------------------------------------
+  {
+    I.wait_w(); bool first = !I.bias(256, A1); I.next();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      I.wait_w();
+      I.mma_ss<4>(H + c * CHUNK, I.slot_addr(), 256, A1, first);
+      first = false;
+      I.next();
+    }
+    I.commit(B_H_FREE);
+    I.commit(B_ACC_FULL + 1);
+  }
+  // ---- residual head on relu(views') -> A0[0,16) -----------------------------------------------------------------
+  sy.wait(B_V_READY);
+  I.wait_w();
+  tc_fence_after();
+  I.mma_ss<4>(V, I.slot_addr(), 16, A0, true);
+  I.mma_ss<4>(V + CHUNK, I.slot_addr() + 2048, 16, A0, false);
+  I.next();
+  I.commit(B_F_FREE);
+  // ---- albedo2 / shading2 on relu(albedo1 | shading1) -> A0[16,32) ------------------------------------------------
+  I.wait_w();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    sy.wait(B_A_READY + c);
+    tc_fence_after();
+    I.mma_ss<4>(H + c * CHUNK, I.slot_addr() + 2048 * c, 16, A0 + 16, c == 0);
+  }
+  I.next();
+  if (sem) I.commit(B_H_FREE);
+  I.commit(B_SMALL_FULL);
+  // ---- semantic logits on relu(sem1) -> A0[32, 32 + sem_rows) ------------------------------------------------------
+  if (sem) {
+    I.wait_w();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      sy.wait(B_A_READY + c);
+      tc_fence_after();
+      I.mma_ss<4>(H + c * CHUNK, I.slot_addr() + (uint32_t)(P.sem_rows * 128 * c), P.sem_rows, A0 + 32, c == 0);
+    }
+    I.next();
+    I.commit(B_SEM2_FULL);
+  }
+}
+
+template <bool HY>
+__device__ __forceinline__ void issuer_lean(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
+  LeanIssuer I{sy, smem_base + SM_RING, tmem, ones, 0u, 0u, (uint32_t)P.ns, sy.addr(B_WFULL), sy.addr(B_WEMPTY), cl, P.no_weights, P.bias_mma, elect_one()};
+  for (int it = 0; it < P.n_iter; ++it) {
+    sy.tile = it;
+    if (it & 1) issuer_lean_tile<HY, 1>(P, sy, I, smem_base);
+    else issuer_lean_tile<HY, 0>(P, sy, I, smem_base);
   }
 }
 
@@ -1395,6 +1724,7 @@ __device__ __forceinline__ void epi_chunk_ts(uint32_t src, uint32_t dst, int col
   uint32_t v[32];
   tmem_ld32(src + jj * 32, v);
   tmem_ld_wait();
+  sy.stamp(8);                                        // chunk in registers
   switch (pair_bar) {
     case 2: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
     case 3: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
@@ -1423,25 +1753,47 @@ __device__ __forceinline__ void epi_chunk_ts(uint32_t src, uint32_t dst, int col
     pk[i] = pack_relu_sat_h2(f[2 * i], f[2 * i + 1]);
     amax = hmax2_u32(amax, pk[i]);
   }
+  sy.stamp(9);                                        // converted
   tmem_st16(dst + jj * 16, pk);
   tmem_st_wait();
   tc_fence_before();
   if (ready_bar >= 0) warp_arrive(sy.addr(ready_bar), lane);
+  sy.stamp(10);                                       // stored + arrived
 }
 
-// `n_chunks` 64-column chunks of the accumulator at `src` -> packed into `dst`, either two chunks per load batch or one
+// chunks [c_begin, n_chunks) (64 columns each) of the accumulator at `src` -> packed into `dst`, either two chunks per load
+// batch or one
 template <int MODE>
 __device__ __forceinline__ void epi_acc_ts(int fine, uint32_t src, uint32_t dst, int n_chunks, int jj, int lane, Sync& sy, int ready_bar0,
-                                           const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar) {
+                                           const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar, int c_begin) {
   if (fine) {
 #pragma unroll 1
-    for (int c = 0; c < n_chunks; ++c)
+    for (int c = c_begin; c < n_chunks; ++c)
       epi_chunk_ts<MODE>(src + 64 * c, dst + 32 * c, 64 * c, jj, lane, sy, ready_bar0 >= 0 ? ready_bar0 + c : -1, alpha_smem, sigma_acc, amax, pair_bar);
   } else {
 #pragma unroll 1
-    for (int c = 0; c < n_chunks; c += 2)
+    for (int c = c_begin; c < n_chunks; c += 2)
       epi_batch_ts<MODE>(src + 64 * c, dst + 32 * c, 64 * c, jj, lane, sy, ready_bar0 >= 0 ? ready_bar0 + c : -1, alpha_smem, sigma_acc, amax, pair_bar);
   }
+}
+
+// accumulator R of trunk layer l -> packed halves in place (the A operand of layer l+1).  With the split hand-off
+// (Params.split_nf, layers 1..7) columns [0, split_nf) are complete - and drained - before the rest of the accumulator.
+template <int MODE>
+__device__ __forceinline__ void epi_trunk_ts(const Params& P, int l, uint32_t R, int jj, int lane, Sync& sy,
+                                             const float* alpha_smem, float* sigma_acc, uint32_t& amax, int pair_bar) {
+  int c0 = 0;
+  if (l > 0 && P.split_nf) {
+    sy.wait(B_ACC_FIRST + (l & 1));
+    sy.stamp(11);                                     // first columns complete
+    tc_fence_after();
+    c0 = P.split_nf >> 6;
+    epi_acc_ts<MODE>(P.ts_fine, R, R, c0, jj, lane, sy, B_A_READY, alpha_smem, sigma_acc, amax, pair_bar, 0);
+  }
+  sy.wait(B_ACC_FULL + (l & 1));
+  sy.stamp(12);                                       // accumulator complete
+  tc_fence_after();
+  epi_acc_ts<MODE>(P.ts_fine, R, R, 4, jj, lane, sy, B_A_READY, alpha_smem, sigma_acc, amax, pair_bar, c0);
 }
 
 __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* smem, uint32_t tmem, int q, int jj, int lane) {
@@ -1454,6 +1806,8 @@ __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* 
   for (int it = 0; it < P.n_iter; ++it) {
     const int64_t tile = tile_of(P, it);
     sy.tile = (int)tile;
+    sy.set_it(it);
+    sy.stamp(3);
     const int64_t m = tile * TILE_M + row;
     const bool valid = P.fuse ? true : (m < P.a.M);
     float* grow = P.fuse ? P.f.ring + (((size_t)blockIdx.x * 2 + (it & 1)) * TILE_M + row) * P.out_ch
@@ -1462,25 +1816,26 @@ __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* 
     uint32_t amax = 0u;
     const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;
     for (int l = 0; l < 8; ++l) {
-      sy.wait(B_ACC_FULL + (l & 1));
-      tc_fence_after();
       const uint32_t R = lane_addr + ((l & 1) ? A1 : A0);
-      if (l == 7) epi_acc_ts<1>(fine, R, R, 4, jj, lane, sy, B_A_READY, s_alpha, &sig, amax, pair_bar);
-      else epi_acc_ts<0>(fine, R, R, 4, jj, lane, sy, B_A_READY, nullptr, nullptr, amax, pair_bar);
+      if (l == 7) epi_trunk_ts<1>(P, l, R, jj, lane, sy, s_alpha, &sig, amax, pair_bar);
+      else epi_trunk_ts<0>(P, l, R, jj, lane, sy, nullptr, nullptr, amax, pair_bar);
     }
     s_sig[row * 2 + jj] = sig;
     // relu(views') : A0[0,128) -> A0[0,64)
     sy.wait(B_ACC_FULL + 0);
+    sy.stamp(13);                                     // views' complete
     tc_fence_after();
     epi_acc_ts<0>(fine, lane_addr + A0, lane_addr + A0, 2, jj, lane, sy, -1, nullptr, nullptr, amax, pair_bar);
     warp_arrive(sy.addr(B_V_READY), lane);
     // relu(albedo1) : A1[128,256) -> A1[128,192) ; relu(shading1) : A0[128,256) -> A0[128,192)
     sy.wait(B_ACC_FULL + 1);
+    sy.stamp(14);                                     // albedo1 | shading1 complete
     tc_fence_after();
     epi_acc_ts<0>(fine, lane_addr + A1 + 128, lane_addr + A1 + 128, 2, jj, lane, sy, B_A_READY, nullptr, nullptr, amax, pair_bar);
     epi_acc_ts<0>(fine, lane_addr + A0 + 128, lane_addr + A0 + 128, 2, jj, lane, sy, B_A_READY + 2, nullptr, nullptr, amax, pair_bar);
     // heads -> raw row
     sy.wait(B_SMALL_FULL);
+    sy.stamp(15);                                     // narrow heads complete
     if (P.fuse) sy.wait(B_RAW_FREE + (it & 1));
     tc_fence_after();
     __syncwarp();
@@ -1513,6 +1868,7 @@ __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* 
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
     warp_arrive(sy.addr(B_TAIL_DONE), lane);
+    sy.stamp(0);                                      // tile tail done
     if (P.fuse) {
       __threadfence_block();
       warp_arrive(sy.addr(B_RAW_READY + (it & 1)), lane);
@@ -1550,6 +1906,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     for (int c = 0; c < 4; ++c) mbar_init(sy.addr(B_A_READY + c), 8);
     mbar_init(sy.addr(B_H_FREE), 1);
     mbar_init(sy.addr(B_ACC_FULL + 0), 1); mbar_init(sy.addr(B_ACC_FULL + 1), 1);
+    mbar_init(sy.addr(B_ACC_FIRST + 0), 1); mbar_init(sy.addr(B_ACC_FIRST + 1), 1);
     mbar_init(sy.addr(B_V_READY), 8);
     mbar_init(sy.addr(B_SMALL_FULL), 1); mbar_init(sy.addr(B_SEM2_FULL), 1);
     mbar_init(sy.addr(B_TAIL_DONE), 8);
@@ -1589,6 +1946,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     const int role = (threadIdx.x == 448) ? 0 : (threadIdx.x == 480 ? 1 : (threadIdx.x == 256 ? 2 : (threadIdx.x == 0 ? 3 : (threadIdx.x == 416 ? 4 : -1))));
     if (role >= 0) sy.prof = P.prof + role * 128;
   }
+#ifdef INRF_TC_TIMELINE
+  sy.tl = nullptr; sy.tl_n = 0; sy.it = -1;
+  if (blockIdx.x == 0) {
+    const int tr = (threadIdx.x == 480) ? 0 : (threadIdx.x == 0 ? 1 : (threadIdx.x == 128 ? 2 : -1));
+    if (tr >= 0 && P.n_iter > TL_IT1 + 2) sy.tl = g_tl + tr * TL_CAP;
+  }
+#endif
   const long long t_start = clock64();
   // warp roles.  The scheduler favours the highest warp id of each sub-partition, so the MMA issuer
   // (15) and the weight producer (14) sit on top of their sub-partitions; both run converged on all
@@ -1600,8 +1964,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     if (!P.no_weights) producer(P, sy, role_base, CL, rank);
   } else if (STASH && warp == 13) {
     stasher(P, sy, smem_base);
+  } else if (!STASH && P.fuse && (warp == 12 || warp == 13)) {
+    backend_role(P, sy, warp - 12, lane);
   } else if (warp == 15) {
-    if (TS) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer<HY>(P, sy, smem_base, tmem, CL, smem_base + SM_ONES);
+    if (TS) { if (P.exp_flags & 4) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer_ts_lean(P, sy, role_base, tmem, CL, smem_base + SM_ONES); } else { if (STASH || (P.exp_flags & 4)) issuer<HY>(P, sy, smem_base, tmem, CL, smem_base + SM_ONES); else issuer_lean<HY>(P, sy, smem_base, tmem, CL, smem_base + SM_ONES); }
   } else if (warp >= 8 && warp < 12) {
     front_end<STASH>(P, sy, role_base, (warp - 8) * 32 + lane);
   } else if (warp < 8) {
@@ -1609,6 +1975,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     else epilogue<STASH, HY>(P, sy, smem, smem_base, tmem, warp & 3, warp >> 2, lane);
   }
   if (sy.prof != nullptr) sy.prof[63] = clock64() - t_start;
+#ifdef INRF_TC_TIMELINE
+  if (sy.tl != nullptr) g_tl_n[(int)((sy.tl - g_tl) / TL_CAP)] = sy.tl_n;
+#endif
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into this CTA
@@ -1665,6 +2034,8 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   P.no_weights = now_env ? 1 : 0;
   static const int abl_env = getenv("INRF_TC_STASH_ABL") ? atoi(getenv("INRF_TC_STASH_ABL")) : 0;
   P.stash_abl = abl_env;
+  static const int exp_env = getenv("INRF_TC_EXP") ? atoi(getenv("INRF_TC_EXP")) : 0;
+  P.exp_flags = exp_env;
   P.prof = nullptr;
   if (prof_env) {
     long long* pp = nullptr;
@@ -1723,6 +2094,11 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   static const bool hy_env = !(getenv("INRF_TC_HY") != nullptr && getenv("INRF_TC_HY")[0] == '0');
   const bool hy = ts_env && hy_env && !ts && !a.stash_img && P.bias_mma;
   P.ns = ts ? ((ns_env >= 2 && ns_env <= tc::NS_MAX) ? ns_env : tc::NS_MAX) : tc::NS;
+  // split hand-off of the trunk layers (TS and HY kernels): INRF_TC_SPLIT = 0 (off) / 64 / 128.  The two-chunks-per-batch
+  // drain (INRF_TC_TS=1) loads chunks 0 and 1 together, so it can only use 128
+  static const int split_env = getenv("INRF_TC_SPLIT") ? atoi(getenv("INRF_TC_SPLIT")) : 0;
+  // (the lean issuer of the hybrid kernel has no split variant: there only with the first issuer, INRF_TC_EXP=4)
+  P.split_nf = (ts || (hy && (P.exp_flags & 4))) ? ((split_env == 64 && P.ts_fine) ? 64 : (split_env == 64 || split_env == 128) ? 128 : 0) : 0;
   void (*kern)(tc::Params) = a.stash_img ? (cl == 2 ? tc::k_mlp_tc<2, true> : tc::k_mlp_tc<1, true>)
                              : ts ? (cl == 2 ? tc::k_mlp_tc<2, false, true> : tc::k_mlp_tc<1, false, true>)
                              : hy ? (cl == 2 ? tc::k_mlp_tc<2, false, false, true> : tc::k_mlp_tc<1, false, false, true>)
@@ -1745,7 +2121,7 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   if (prof_env) {
     static const char* bar_names[tc::B_COUNT] = {"WFULL0","WFULL1","WFULL2","WFULL3","WFULL4","WFULL5","WEMPTY0","WEMPTY1","WEMPTY2","WEMPTY3",
       "WEMPTY4","WEMPTY5","F_READY","F_FREE","A_READY0","A_READY1","A_READY2","A_READY3","H_FREE","ACC_FULL0","ACC_FULL1","V_READY",
-      "SMALL_FULL","SEM2_FULL","TAIL_DONE","RAW_READY0","RAW_READY1","RAW_FREE0","RAW_FREE1","ST_DONE0","ST_DONE1","ST_DONE2","ST_DONE3","STV_DONE"};
+      "SMALL_FULL","SEM2_FULL","TAIL_DONE","RAW_READY0","RAW_READY1","RAW_FREE0","RAW_FREE1","ST_DONE0","ST_DONE1","ST_DONE2","ST_DONE3","STV_DONE","ACC_FIRST0","ACC_FIRST1"};
     static const char* roles[] = {"producer", "issuer", "frontend", "epilogue", "stasher"};
     long long h[5 * 128];
     INRF_CUDA(cudaStreamSynchronize(st));
@@ -1758,6 +2134,22 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
       }
     }
   }
+#ifdef INRF_TC_TIMELINE
+  if (P.n_iter > tc::TL_IT1 + 2) {
+    static long long h[3 * tc::TL_CAP];
+    int hn[3];
+    INRF_CUDA(cudaStreamSynchronize(st));
+    INRF_CUDA(cudaMemcpyFromSymbol(h, tc::g_tl, sizeof(h)));
+    INRF_CUDA(cudaMemcpyFromSymbol(hn, tc::g_tl_n, sizeof(hn)));
+    long long t0 = -1;
+    for (int r = 0; r < 3; ++r) for (int i = 0; i < hn[r]; ++i) { const long long t = h[r * tc::TL_CAP + i] >> 4; if (t0 < 0 || t < t0) t0 = t; }
+    for (int r = 0; r < 3; ++r) {
+      fprintf(stderr, "TCTL role=%d n=%d:", r, hn[r]);
+      for (int i = 0; i < hn[r]; ++i) fprintf(stderr, " %lld:%d", (h[r * tc::TL_CAP + i] >> 4) - t0, (int)(h[r * tc::TL_CAP + i] & 15));
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   if (checked) {      // debug mode (INRF_TC_CHECK=1): synchronise and report this launch's status record right away
     INRF_CUDA(cudaStreamSynchronize(st));
     return status_poll();

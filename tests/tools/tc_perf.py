@@ -25,6 +25,7 @@ a = ops.mlp_forward_rays(fine.packed(), fine.variant, C, rays[:4096], z[:4096], 
 b = ops.mlp_forward_rays(fine.packed(), fine.variant, C, rays[:4096], z[:4096], False, scale, "tc")
 torch.cuda.synchronize()
 err = (a - b).abs().max().item()
+chk = int(b.contiguous().view(torch.int32).to(torch.int64).sum().item())     # bit-level checksum: variants must agree exactly
 for _ in range(2):
     ops.mlp_forward_rays(fine.packed(), fine.variant, C, rays, z, False, scale, "tc")
 torch.cuda.synchronize()
@@ -39,4 +40,5 @@ ms = s.elapsed_time(e) / reps
 flop = n * 192 * (1318912 if variant == "object" else 2 * (692224 + 128 * C))
 print(f"TC_PERF variant={variant} cluster={os.environ.get('INRF_TC_CLUSTER', '2')} biasmma={os.environ.get('INRF_TC_BIASMMA', '1')} "
       f"rows={n * 192} ms={ms:.3f} us_per_tile={ms * 1e3 / (n * 192 / 128 / 148):.2f} TFLOPs={flop / ms / 1e9:.1f} "
-      f"rays_per_s_equiv={n / ms * 1e3 * 192 / 256:.0f} max_abs_err_vs_fp32={err:.3e}")
+      f"rays_per_s_equiv={n / ms * 1e3 * 192 / 256:.0f} max_abs_err_vs_fp32={err:.3e} checksum={chk} "
+      f"split={os.environ.get('INRF_TC_SPLIT', 'default')}")
