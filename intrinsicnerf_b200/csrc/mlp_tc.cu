@@ -113,8 +113,8 @@ __device__ long long g_prof[5 * 128];
 // development build (tools/gpu_timeline.sh): clock64 stamps of the issuer and of two epilogue warps of CTA 0 for two
 // steady-state tiles; printed by the launcher.  (stamp << 4) | kind
 constexpr int TL_CAP = 1024, TL_IT0 = 10, TL_IT1 = 11;
-__device__ long long g_tl[3 * TL_CAP];
-__device__ int g_tl_n[3];
+__device__ long long g_tl[4 * TL_CAP];
+__device__ int g_tl_n[4];
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -530,7 +530,10 @@ __device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, i
   const int slot = it & 1;
   const int64_t tile = tile_of(P, it);
   sy.tile = (int)tile;
+  sy.set_it(it);
+  sy.stamp(3);
   sy.wait(B_RAW_READY + slot);
+  sy.stamp(1);
   const float* ring = P.f.ring + ((size_t)blockIdx.x * 2 + slot) * TILE_M * P.out_ch;   // plain (coherent) loads: written by this CTA
   const int S = P.a.S;
   for (int q = 0; q < 4; ++q) {
@@ -628,11 +631,15 @@ __device__ __forceinline__ void ray_backend(const Params& P, Sync& sy, int it, i
         const int e = lane + 32 * i;
         if (e < P.C) r[INRF_REC_BASE + e] = P.f.white_bkgd ? rs.ex[i] + (1.f - accw) : rs.ex[i];   // model_utils.py:113-114
       }
+      sy.stamp(5);
       if (SAMPLER) resample_ray(P, ray, rs, lane);
+      sy.stamp(6);
     }
+    sy.stamp(2);
   }
   __syncwarp();
   if (lane == 0) mbar_arrive(sy.addr(B_RAW_FREE + slot));
+  sy.stamp(4);
 }
 
 // swizzled byte offsets of the 8 16-byte units of this thread's row inside a chunk
@@ -1796,6 +1803,48 @@ __device__ __forceinline__ void epi_trunk_ts(const Params& P, int l, uint32_t R,
   epi_acc_ts<MODE>(P.ts_fine, R, R, 4, jj, lane, sy, B_A_READY, alpha_smem, sigma_acc, amax, pair_bar, c0);
 }
 
+// Head values of a finished tile, held in registers until the tensor pipe is busy with the NEXT tile's layer 1: the sigmoids
+// and the 11 strided row stores (~2 500 cycles) used to sit between "narrow heads complete" and the drain of the next
+// tile's layer 0, i.e. on the tile-to-tile critical path with the tensor pipe idle (clock64 timeline).
+struct PendingHeads {
+  float h[7];          // pre-sigmoid residual3, albedo3, shading
+  float sigma;         // sigma head incl. bias
+  float* grow;         // destination row (caller's raw tensor or the CTA's ring slot)
+  int slot;            // fused: ring slot (it & 1)
+  bool valid, on;
+};
+
+__device__ __forceinline__ void finish_heads(const Params& P, Sync& sy, PendingHeads& pd, int jj, int lane) {
+  if (!pd.on) return;
+  pd.on = false;
+  if (jj == 0) {
+    if (P.fuse) sy.wait(B_RAW_FREE + pd.slot);        // the back end is done with this slot (two tiles ago)
+    sy.stamp(7);
+    if (pd.valid) {
+      float res[3], alb[3], sh;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) res[i] = sigmoid_(pd.h[i] + __ldg(P.bias + TCB_RES + i));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) alb[i] = sigmoid_(pd.h[3 + i] + __ldg(P.bias + TCB_ALB2 + i));
+      sh = sigmoid_(pd.h[6] + __ldg(P.bias + TCB_SH2));
+      float* grow = pd.grow;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) grow[i] = __fadd_rn(__fmul_rn(alb[i], sh), res[i]);
+      grow[3] = pd.sigma;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) grow[4 + i] = alb[i];
+      grow[7] = sh;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) grow[8 + i] = res[i];
+    }
+  }
+  if (P.fuse) {
+    __threadfence_block();
+    warp_arrive(sy.addr(B_RAW_READY + pd.slot), lane);
+  }
+  sy.stamp(6);
+}
+
 __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* smem, uint32_t tmem, int q, int jj, int lane) {
   const int row = q * 32 + lane;
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
@@ -1803,15 +1852,14 @@ __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* 
   const float* s_alpha = reinterpret_cast<const float*>(smem + SM_ALPHA);
   const int pair_bar = 2 + q;
   const int fine = P.ts_fine;
+  PendingHeads pd;
+  pd.on = false;
   for (int it = 0; it < P.n_iter; ++it) {
     const int64_t tile = tile_of(P, it);
     sy.tile = (int)tile;
     sy.set_it(it);
     sy.stamp(3);
     const int64_t m = tile * TILE_M + row;
-    const bool valid = P.fuse ? true : (m < P.a.M);
-    float* grow = P.fuse ? P.f.ring + (((size_t)blockIdx.x * 2 + (it & 1)) * TILE_M + row) * P.out_ch
-                         : P.a.raw + (m < P.a.M ? m : 0) * P.out_ch;
     float sig = 0.f;
     uint32_t amax = 0u;
     const uint32_t A0 = (it & 1) ? 256u : 0u, A1 = 256u - A0;
@@ -1819,6 +1867,8 @@ __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* 
       const uint32_t R = lane_addr + ((l & 1) ? A1 : A0);
       if (l == 7) epi_trunk_ts<1>(P, l, R, jj, lane, sy, s_alpha, &sig, amax, pair_bar);
       else epi_trunk_ts<0>(P, l, R, jj, lane, sy, nullptr, nullptr, amax, pair_bar);
+      // layer 1 now keeps the tensor pipe busy for ~2 200 cycles: the previous tile's rows are finished here
+      if (l == 0) finish_heads(P, sy, pd, jj, lane);
     }
     s_sig[row * 2 + jj] = sig;
     // relu(views') : A0[0,128) -> A0[0,64)
@@ -1833,47 +1883,35 @@ __device__ __forceinline__ void epilogue_ts(const Params& P, Sync& sy, uint8_t* 
     tc_fence_after();
     epi_acc_ts<0>(fine, lane_addr + A1 + 128, lane_addr + A1 + 128, 2, jj, lane, sy, B_A_READY, nullptr, nullptr, amax, pair_bar);
     epi_acc_ts<0>(fine, lane_addr + A0 + 128, lane_addr + A0 + 128, 2, jj, lane, sy, B_A_READY + 2, nullptr, nullptr, amax, pair_bar);
-    // heads -> raw row
+    // heads: out of tensor memory into registers, then release the accumulator (and s_sig) for the next tile at once
     sy.wait(B_SMALL_FULL);
     sy.stamp(15);                                     // narrow heads complete
-    if (P.fuse) sy.wait(B_RAW_FREE + (it & 1));
     tc_fence_after();
     __syncwarp();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");    // both sigma partials of every row are in shared memory
     if (jj == 0) {
       uint32_t v[32];
       tmem_ld32(lane_addr + A0 + 64, v);
       tmem_ld_wait();
-      if (valid) {
-        float res[3], alb[3], sh;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) res[i] = sigmoid_(__uint_as_float(v[i]) + __ldg(P.bias + TCB_RES + i));
-#pragma unroll
-        for (int i = 0; i < 3; ++i) alb[i] = sigmoid_(__uint_as_float(v[16 + i]) + __ldg(P.bias + TCB_ALB2 + i));
-        sh = sigmoid_(__uint_as_float(v[19]) + __ldg(P.bias + TCB_SH2));
-        const float sigma = (s_sig[row * 2] + s_sig[row * 2 + 1]) + __ldg(P.bias + TCB_ALPHA_B);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) grow[i] = __fadd_rn(__fmul_rn(alb[i], sh), res[i]);
-        grow[3] = sigma;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) grow[4 + i] = alb[i];
-        grow[7] = sh;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) grow[8 + i] = res[i];
-      }
+      for (int i = 0; i < 3; ++i) { pd.h[i] = __uint_as_float(v[i]); pd.h[3 + i] = __uint_as_float(v[16 + i]); }
+      pd.h[6] = __uint_as_float(v[19]);
+      pd.sigma = (s_sig[row * 2] + s_sig[row * 2 + 1]) + __ldg(P.bias + TCB_ALPHA_B);
     }
+    pd.valid = P.fuse ? true : (m < P.a.M);
+    pd.grow = P.fuse ? P.f.ring + (((size_t)blockIdx.x * 2 + (it & 1)) * TILE_M + row) * P.out_ch
+                     : P.a.raw + (m < P.a.M ? m : 0) * P.out_ch;
+    pd.slot = it & 1;
+    pd.on = true;
     if (m < P.a.M && !sy.dead && ((amax & 0xffffu) >= 0x7bffu || (amax >> 16) >= 0x7bffu)) {
       if (atomicCAS(P.dbg + 8, 0, 1) == 0) status_raise(P.status, DST_F16_ACT, 0, (int)tile, blockIdx.x);
     }
+    // s_sig is next written after the NEXT tile's layer 7, which the issuer cannot reach before all eight arrivals below
     tc_fence_before();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
     warp_arrive(sy.addr(B_TAIL_DONE), lane);
     sy.stamp(0);                                      // tile tail done
-    if (P.fuse) {
-      __threadfence_block();
-      warp_arrive(sy.addr(B_RAW_READY + (it & 1)), lane);
-    }
   }
+  finish_heads(P, sy, pd, jj, lane);                  // the CTA's last tile
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1949,7 +1987,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
 #ifdef INRF_TC_TIMELINE
   sy.tl = nullptr; sy.tl_n = 0; sy.it = -1;
   if (blockIdx.x == 0) {
-    const int tr = (threadIdx.x == 480) ? 0 : (threadIdx.x == 0 ? 1 : (threadIdx.x == 128 ? 2 : -1));
+    const int tr = (threadIdx.x == 480) ? 0 : (threadIdx.x == 0 ? 1 : (threadIdx.x == 128 ? 2 : (threadIdx.x == 384 ? 3 : -1)));
     if (tr >= 0 && P.n_iter > TL_IT1 + 2) sy.tl = g_tl + tr * TL_CAP;
   }
 #endif
@@ -2136,18 +2174,20 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   }
 #ifdef INRF_TC_TIMELINE
   if (P.n_iter > tc::TL_IT1 + 2) {
-    static long long h[3 * tc::TL_CAP];
-    int hn[3];
+    static long long h[4 * tc::TL_CAP];
+    int hn[4];
     INRF_CUDA(cudaStreamSynchronize(st));
     INRF_CUDA(cudaMemcpyFromSymbol(h, tc::g_tl, sizeof(h)));
     INRF_CUDA(cudaMemcpyFromSymbol(hn, tc::g_tl_n, sizeof(hn)));
     long long t0 = -1;
-    for (int r = 0; r < 3; ++r) for (int i = 0; i < hn[r]; ++i) { const long long t = h[r * tc::TL_CAP + i] >> 4; if (t0 < 0 || t < t0) t0 = t; }
-    for (int r = 0; r < 3; ++r) {
-      fprintf(stderr, "TCTL role=%d n=%d:", r, hn[r]);
+    for (int r = 0; r < 4; ++r) for (int i = 0; i < hn[r]; ++i) { const long long t = h[r * tc::TL_CAP + i] >> 4; if (t0 < 0 || t < t0) t0 = t; }
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "TCTL fuse=%d S=%d role=%d n=%d:", P.fuse, P.a.S, r, hn[r]);
       for (int i = 0; i < hn[r]; ++i) fprintf(stderr, " %lld:%d", (h[r * tc::TL_CAP + i] >> 4) - t0, (int)(h[r * tc::TL_CAP + i] & 15));
       fprintf(stderr, "\n");
     }
+    const int zero[4] = {0, 0, 0, 0};
+    INRF_CUDA(cudaMemcpyToSymbol(tc::g_tl_n, zero, sizeof(zero)));
   }
 #endif
   if (checked) {      // debug mode (INRF_TC_CHECK=1): synchronise and report this launch's status record right away
