@@ -103,7 +103,7 @@ struct Params {
   int fault;                      // test hook (INRF_TC_FAULT=n, first n launches): the weight producer stops after three fills
   long long* prof;                // optional wait-cycle counters of CTA 0 (INRF_TC_PROF=1)
   int no_weights;                 // timing experiment: do not wait for / stream weights (results are garbage)
-  int exp_flags;                  // timing experiments (INRF_TC_EXP): 1 = the issuer skips tcgen05.fence::after_thread_sync per fill
+  int exp_flags;                  // A/B switch (INRF_TC_EXP): 8 = ray back end on front-end warps 0 and 2 (its first placement)
   int stash_abl;                  // timing experiment (INRF_TC_STASH_ABL): 1 no mask words, 2 no bulk copies, 4 no "copy has read" waits
 };
 
@@ -649,6 +649,13 @@ struct RowAddr {
 
 template <bool STASH>
 __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t smem_base, int row) {
+  // INRF_TC_EXP & 8 (A/B): the ray back end on front-end warps 0 and 2, after each tile's encoding (its first placement)
+  RayState rs;
+  rs.carry = 1.f;
+  const bool backend = !STASH && P.fuse && (P.exp_flags & 8) && (row < 32 || (row >= 64 && row < 96));
+  const int which = row >= 64 ? 1 : 0;
+  const int blane = row & 31;
+  const bool sampler = P.f.n_importance > 0;
   RowAddr ra;
 #pragma unroll
   for (int u = 0; u < 8; ++u) ra.unit[u] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4));
@@ -737,6 +744,12 @@ __device__ __forceinline__ void front_end(const Params& P, Sync& sy, uint32_t sm
 #pragma unroll
       for (int u = 0; u < 4; ++u) st_global_v4(g + ra.unit[u], dw[4 * u], dw[4 * u + 1], dw[4 * u + 2], dw[4 * u + 3]);
     }
+    if (!STASH && backend && it > 0) {
+      if (sampler) ray_backend<true>(P, sy, it - 1, blane, rs, which); else ray_backend<false>(P, sy, it - 1, blane, rs, which);
+    }
+  }
+  if (!STASH && backend && P.n_iter > 0) {
+    if (sampler) ray_backend<true>(P, sy, P.n_iter - 1, blane, rs, which); else ray_backend<false>(P, sy, P.n_iter - 1, blane, rs, which);
   }
 }
 
@@ -854,7 +867,6 @@ struct Issuer {
   int cl;
   int bias_mma;
   int no_weights;
-  int exp_flags;
   bool leader;
   // probe-ahead state: the barriers of the NEXT fill are tested (non-blocking) before the MMAs of
   // the current fill are issued, so the mbarrier round trip overlaps the issue of tcgen05.mma
@@ -883,7 +895,7 @@ struct Issuer {
     if (!pw_ok) sy.slow(B_WFULL + slot, pw_par);
     if (!pa_ok) sy.slow(pa_bar, pa_par);
     sy.stamp(13);                                     // barriers passed
-    if (!(exp_flags & 1)) tc_fence_after();
+    tc_fence_after();
     sy.stamp(1);                                      // fill acquired (weights + activation chunk)
   }
   __device__ __forceinline__ void release_slot(int s) {   // MMAs reading slot s are done -> refill
@@ -894,18 +906,13 @@ struct Issuer {
     __syncwarp();
   }
   __device__ __forceinline__ void release() { release_slot(slot); }
-  // end of a fill: release the slot, move on, probe the next fill's barriers.  exp_flags & 2: probe BEFORE the commit
+  // end of a fill: release the slot, move on, probe the next fill's barriers (their round trip overlaps MMA execution).
+  // The issuer warp paces the kernel - ~90 dependent instructions per fill against 512 cycles of MMAs (profiles/
+  // r02_issuer_timeline.md) - so nothing is added here lightly: two run-time experiment flags in this path cost 7 % of the tile
   __device__ __forceinline__ void finish(int next_act) {
-    if (exp_flags & 2) {
-      const int old = slot;
-      advance();
-      if (next_act != -2) probe(next_act);
-      release_slot(old);
-    } else {
-      release();
-      advance();
-      if (next_act != -2) probe(next_act);
-    }
+    release();
+    advance();
+    if (next_act != -2) probe(next_act);
   }
   __device__ __forceinline__ void advance() { slot = (slot + 1 == ns) ? 0 : slot + 1; sy.stamp(2); }   // fill issued
   // K = 16*KSTEPS of A chunk `a_chunk` times the operand tile at byte offset `b_off` of slot `sl`
@@ -988,7 +995,7 @@ struct Issuer {
 // traffic from shared memory.
 template <bool HY>
 __device__ __forceinline__ void issuer(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
-  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, P.exp_flags, elect_one(), 1u, 1u, 0u, 0u, -1};
+  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
   const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
   const bool sem = P.C > 0;
   const int nv = sem ? 256 : 128;       // views' [| sem1] width
@@ -1319,7 +1326,7 @@ __device__ __forceinline__ void epilogue(const Params& P, Sync& sy, uint8_t* sme
 // the stores.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
-  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, P.exp_flags, elect_one(), 1u, 1u, 0u, 0u, -1};
+  Issuer I{sy, smem_base, tmem, 0, P.ns, ones, cl, P.bias_mma, P.no_weights, elect_one(), 1u, 1u, 0u, 0u, -1};
   const uint32_t PE = smem_base + SM_PE, DIR = smem_base + SM_DIR;
   I.probe(-1);
   for (int it = 0; it < P.n_iter; ++it) {
@@ -1401,275 +1408,6 @@ __device__ __forceinline__ void issuer_ts(const Params& P, Sync& sy, uint32_t sm
       I.probe(-1);
     }
     I.commit(B_SMALL_FULL);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Lean issuer of the TS kernel (round 2, default).  The clock64 timeline of the first TS issuer (tools/gpu_timeline.sh,
-// DESIGN 4b) showed that the issuer warp itself paced the trunk: ~90 dependent SASS instructions per ring fill (probe-ahead
-// state machine, 64-bit parity bookkeeping with variable shifts, loop control, five R2UR per fill) took ~590 cycles against
-// 512 cycles of MMAs, on a scheduler shared with two busy epilogue warps - the tensor pipe idled between fills although
-// weights and activations were ready.  This version keeps the MMA program (and therefore every result bit) and removes the
-// bookkeeping: the tile is unrolled per accumulator parity so operand columns, barrier ids and shifts are immediates,
-// the weight-ring parity is one bit that flips when the slot wraps, and the waits are plain blocking try_waits issued
-// right after the previous fill's MMAs (which execute asynchronously for 512 cycles - nothing to probe ahead for).
-// ------------------------------------------------------------------------------------------
-struct LeanIssuer {
-  Sync& sy;
-  uint32_t ring0, tmem, ones;
-  uint32_t slot, wpar, ns;
-  uint32_t wfull0, wempty0;      // shared-memory addresses of B_WFULL[0] / B_WEMPTY[0]
-  int cl, no_weights, bias_mma;
-  bool leader;
-  __device__ __forceinline__ uint32_t slot_addr() const { return ring0 + slot * (uint32_t)TC_SLOT_BYTES; }
-  // weights of the current fill have landed
-  __device__ __forceinline__ void wait_w() {
-    if (no_weights || sy.dead) return;
-    if (!mbar_try(wfull0 + 8u * slot, wpar)) sy.slow(B_WFULL + (int)slot, wpar);
-  }
-  // the MMAs issued so far are the last readers of the current slot: hand it back to the producer(s), move on
-  __device__ __forceinline__ void next() {
-    if (!no_weights && leader) {
-      if (cl == 1) tc_commit(wempty0 + 8u * slot);
-      else tc_commit_mc(wempty0 + 8u * slot, (uint16_t)((1u << cl) - 1u));
-    }
-    __syncwarp();
-    ++slot;
-    if (slot == ns) { slot = 0; wpar ^= 1u; }
-    sy.stamp(2);
-  }
-  __device__ __forceinline__ void commit(int bar) {
-    if (leader) tc_commit(sy.addr(bar));
-    __syncwarp();
-  }
-  template <int KSTEPS>
-  __device__ __forceinline__ void mma_ts(uint32_t a_col, uint32_t b_addr, int n, uint32_t col, bool first) {
-    const uint64_t bd = make_desc(b_addr);
-    const uint32_t id = make_idesc(n);
-    if (leader) {
-#pragma unroll
-      for (int k = 0; k < KSTEPS; ++k)
-        tc_mma_ts(tmem + col, tmem + a_col + 8u * k, bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
-    }
-    __syncwarp();
-  }
-  template <int KSTEPS>
-  __device__ __forceinline__ void mma_ss(uint32_t a_chunk, uint32_t b_addr, int n, uint32_t col, bool first) {
-    const uint64_t ad = make_desc(a_chunk), bd = make_desc(b_addr);
-    const uint32_t id = make_idesc(n);
-    if (leader) {
-#pragma unroll
-      for (int k = 0; k < KSTEPS; ++k)
-        tc_mma(tmem + col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), id, (first && k == 0) ? 0u : 1u);
-    }
-    __syncwarp();
-  }
-  // accumulator columns [col, col + n) := bias (one K=16 MMA of the constant "ones" tile against the fill's bias block)
-  // (returns false when the bias is added by the epilogue instead: INRF_TC_BIASMMA=0, shared-memory-activation kernel only)
-  __device__ __forceinline__ bool bias(int n, uint32_t col, uint32_t b_off = 0) {
-    if (bias_mma && leader)
-      tc_mma(tmem + col, make_desc_flat(ones, 128, 0), make_desc_flat(slot_addr() + b_off, 128, 256), make_idesc(n), 0u);
-    __syncwarp();
-    return bias_mma != 0;
-  }
-};
-
-// one tile; PAR = it & 1 selects the accumulator roles (A0 / A1 swap every tile, see issuer<>)
-template <int PAR>
-__device__ __forceinline__ void issuer_ts_tile(const Params& P, Sync& sy, LeanIssuer& I, uint32_t PE, uint32_t DIR, const int nf) {
-  constexpr uint32_t A0 = PAR ? 256u : 0u, A1 = 256u - A0;
-  sy.stamp(3);
-  sy.wait(B_F_READY);
-  sy.stamp(4);
-  // ---- trunk layer 0: bias, then K = 64 of gamma(x) ---------------------------------------------------
-  I.wait_w(); sy.stamp(1); I.bias(256, A0); I.next();
-  I.wait_w(); sy.stamp(1); I.mma_ss<4>(PE, I.slot_addr(), 256, A0, false); I.next();
-  I.commit(B_ACC_FULL + 0);
-  sy.wait(B_TAIL_DONE);
-  sy.stamp(5);
-  // ---- trunk layers 1..7: A = packed output of layer l-1 in the other accumulator ----------------------
-#pragma unroll
-  for (int l = 1; l < 8; ++l) {
-    const uint32_t acc = (l & 1) ? A1 : A0, src = (l & 1) ? A0 : A1;
-    I.wait_w(); sy.stamp(1); I.bias(256, acc); I.next();
-    if (l == 5) { I.wait_w(); sy.stamp(1); I.mma_ss<4>(PE, I.slot_addr(), 256, acc, false); I.next(); }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      I.wait_w();
-      sy.wait(B_A_READY + c);
-      tc_fence_after();
-      sy.stamp(1);
-      if (c == 3 && nf) {          // split hand-off: columns [0, nf) first
-        I.mma_ts<4>(src + 96u, I.slot_addr(), nf, acc, false);
-        I.commit(B_ACC_FIRST + (l & 1));
-        I.mma_ts<4>(src + 96u, I.slot_addr() + (uint32_t)nf * 128u, 256 - nf, acc + (uint32_t)nf, false);
-      } else {
-        I.mma_ts<4>(src + 32u * c, I.slot_addr(), 256, acc, false);
-      }
-      I.next();
-    }
-    I.commit(B_ACC_FULL + (l & 1));
-  }
-  // ---- views' on h7 (A1[0,128)) + gamma(d) -> A0[0,128) -------------------------------------------------
-  I.wait_w(); sy.stamp(1); I.bias(128, A0); I.next();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    I.wait_w();
-    sy.wait(B_A_READY + c);
-    tc_fence_after();
-    sy.stamp(1);
-    I.mma_ts<4>(A1 + 32u * c, I.slot_addr(), 128, A0, false);
-    I.next();
-  }
-  I.wait_w(); sy.stamp(1); I.mma_ss<2>(DIR, I.slot_addr(), 128, A0, false); I.next();
-  I.commit(B_ACC_FULL + 0);
-  // ---- albedo1 -> A1[128,256), shading1 -> A0[128,256): both halves of every albedo1|shading1 weight fill -----
-  I.wait_w(); sy.stamp(1); I.bias(128, A1 + 128); I.bias(128, A0 + 128, 4096); I.next();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    I.wait_w();
-    sy.stamp(1);
-    I.mma_ts<4>(A1 + 32u * c, I.slot_addr(), 128, A1 + 128, false);
-    I.mma_ts<4>(A1 + 32u * c, I.slot_addr() + 16384, 128, A0 + 128, false);
-    I.next();
-  }
-  I.commit(B_ACC_FULL + 1);
-  // ---- residual head on relu(views') (A0[0,64)) -> A0[64,80) ---------------------------------------------------
-  sy.wait(B_V_READY);
-  sy.stamp(6);
-  I.wait_w();
-  tc_fence_after();
-  I.mma_ts<4>(A0 + 0, I.slot_addr(), 16, A0 + 64, true);
-  I.mma_ts<4>(A0 + 32, I.slot_addr() + 2048, 16, A0 + 64, false);
-  I.next();
-  I.commit(B_F_FREE);
-  // ---- albedo2 / shading2 on [relu(albedo1) (A1[128,192)) | relu(shading1) (A0[128,192))] -> A0[80,96) -----------
-  I.wait_w();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    sy.wait(B_A_READY + c);
-    sy.stamp(7);
-    tc_fence_after();
-    I.mma_ts<4>((c < 2 ? A1 + 128 + 32u * c : A0 + 128 + 32u * (c - 2)), I.slot_addr() + 2048 * c, 16, A0 + 80, c == 0);
-  }
-  I.next();
-  I.commit(B_SMALL_FULL);
-}
-
-__device__ __forceinline__ void issuer_ts_lean(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
-  LeanIssuer I{sy, smem_base + SM_RING, tmem, ones, 0u, 0u, (uint32_t)P.ns, sy.addr(B_WFULL), sy.addr(B_WEMPTY), cl, P.no_weights, P.bias_mma, elect_one()};
-  const uint32_t PE = smem_base + SM_PE, DIR = smem_base + SM_DIR;
-  const int nf = P.split_nf;
-  for (int it = 0; it < P.n_iter; ++it) {
-    sy.tile = it;
-    sy.set_it(it);
-    if (it & 1) issuer_ts_tile<1>(P, sy, I, PE, DIR, nf);
-    else issuer_ts_tile<0>(P, sy, I, PE, DIR, nf);
-  }
-}
-
-// The same for the shared-memory-activation kernel (HY = false: training forward, INRF_TC_TS=0) and the hybrid (HY = true:
-// Semantic_NeRF / endpoint-feature inference): the MMA program of issuer<HY>, fill for fill.
-template <bool HY, int PAR>
-__device__ __forceinline__ void issuer_lean_tile(const Params& P, Sync& sy, LeanIssuer& I, uint32_t smem_base) {
-  constexpr uint32_t A0 = PAR ? 256u : 0u, A1 = 256u - A0;
-  const uint32_t H = smem_base + SM_H, PE = smem_base + SM_PE, DIR = smem_base + SM_DIR, V = smem_base + SM_V;
-  const bool sem = P.C > 0;
-  const int nv = sem ? 256 : 128;       // views' [| sem1] width
-  sy.wait(B_F_READY);
-  // ---- trunk layer 0 ------------------------------------------------------------------------------------
-  {
-    I.wait_w(); const bool init = I.bias(256, A0); I.next();
-    I.wait_w(); I.mma_ss<4>(PE, I.slot_addr(), 256, A0, !init); I.next();
-    I.commit(B_ACC_FULL + 0);
-  }
-  sy.wait(B_TAIL_DONE);
-  // ---- trunk layers 1..7 ----------------------------------------------------------------------------------
-#pragma unroll
-  for (int l = 1; l < 8; ++l) {
-    const uint32_t acc = (l & 1) ? A1 : A0, src = (l & 1) ? A0 : A1;
-    I.wait_w(); bool first = !I.bias(256, acc); I.next();
-    if (l == 5) { I.wait_w(); I.mma_ss<4>(PE, I.slot_addr(), 256, acc, first); I.next(); first = false; }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      I.wait_w();
-      sy.wait(B_A_READY + c);
-      tc_fence_after();
-      if (HY) I.mma_ts<4>(src + 32u * c, I.slot_addr(), 256, acc, first);      // packed output of layer l-1 in tensor memory
-      else I.mma_ss<4>(H + c * CHUNK, I.slot_addr(), 256, acc, first);
-      first = false;
-      I.next();
-    }
-    I.commit(B_ACC_FULL + (l & 1));
-  }
-  // ---- views' [| sem1] on the trunk output (shared memory in both variants) -> A0 ---------------------------
-  {
-    I.wait_w(); bool first = !I.bias(nv, A0); I.next();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      I.wait_w();
-      sy.wait(B_A_READY + c);
-      tc_fence_after();
-      I.mma_ss<4>(H + c * CHUNK, I.slot_addr(), nv, A0, first);
-      first = false;
-      I.next();
-    }
-    I.wait_w(); I.mma_ss<2>(DIR, I.slot_addr(), 128, A0, false); I.next();
-    I.commit(B_ACC_FULL + 0);
-  }
-  // ---- albedo1 | shading1 -> A1 --------------------------------------------------------------------------------
-  {
-    I.wait_w(); bool first = !I.bias(256, A1); I.next();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      I.wait_w();
-      I.mma_ss<4>(H + c * CHUNK, I.slot_addr(), 256, A1, first);
-      first = false;
-      I.next();
-    }
-    I.commit(B_H_FREE);
-    I.commit(B_ACC_FULL + 1);
-  }
-  // ---- residual head on relu(views') -> A0[0,16) -----------------------------------------------------------------
-  sy.wait(B_V_READY);
-  I.wait_w();
-  tc_fence_after();
-  I.mma_ss<4>(V, I.slot_addr(), 16, A0, true);
-  I.mma_ss<4>(V + CHUNK, I.slot_addr() + 2048, 16, A0, false);
-  I.next();
-  I.commit(B_F_FREE);
-  // ---- albedo2 / shading2 on relu(albedo1 | shading1) -> A0[16,32) ------------------------------------------------
-  I.wait_w();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    sy.wait(B_A_READY + c);
-    tc_fence_after();
-    I.mma_ss<4>(H + c * CHUNK, I.slot_addr() + 2048 * c, 16, A0 + 16, c == 0);
-  }
-  I.next();
-  if (sem) I.commit(B_H_FREE);
-  I.commit(B_SMALL_FULL);
-  // ---- semantic logits on relu(sem1) -> A0[32, 32 + sem_rows) ------------------------------------------------------
-  if (sem) {
-    I.wait_w();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      sy.wait(B_A_READY + c);
-      tc_fence_after();
-      I.mma_ss<4>(H + c * CHUNK, I.slot_addr() + (uint32_t)(P.sem_rows * 128 * c), P.sem_rows, A0 + 32, c == 0);
-    }
-    I.next();
-    I.commit(B_SEM2_FULL);
-  }
-}
-
-template <bool HY>
-__device__ __forceinline__ void issuer_lean(const Params& P, Sync& sy, uint32_t smem_base, uint32_t tmem, int cl, uint32_t ones) {
-  LeanIssuer I{sy, smem_base + SM_RING, tmem, ones, 0u, 0u, (uint32_t)P.ns, sy.addr(B_WFULL), sy.addr(B_WEMPTY), cl, P.no_weights, P.bias_mma, elect_one()};
-  for (int it = 0; it < P.n_iter; ++it) {
-    sy.tile = it;
-    if (it & 1) issuer_lean_tile<HY, 1>(P, sy, I, smem_base);
-    else issuer_lean_tile<HY, 0>(P, sy, I, smem_base);
   }
 }
 
@@ -2002,10 +1740,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_tc(const __grid_constant
     if (!P.no_weights) producer(P, sy, role_base, CL, rank);
   } else if (STASH && warp == 13) {
     stasher(P, sy, smem_base);
-  } else if (!STASH && P.fuse && (warp == 12 || warp == 13)) {
+  } else if (!STASH && P.fuse && !(P.exp_flags & 8) && (warp == 12 || warp == 13)) {
     backend_role(P, sy, warp - 12, lane);
   } else if (warp == 15) {
-    if (TS) { if (P.exp_flags & 4) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer_ts_lean(P, sy, role_base, tmem, CL, smem_base + SM_ONES); } else { if (STASH || (P.exp_flags & 4)) issuer<HY>(P, sy, smem_base, tmem, CL, smem_base + SM_ONES); else issuer_lean<HY>(P, sy, smem_base, tmem, CL, smem_base + SM_ONES); }
+    if (TS) issuer_ts(P, sy, role_base, tmem, CL, smem_base + SM_ONES); else issuer<HY>(P, sy, smem_base, tmem, CL, smem_base + SM_ONES);
   } else if (warp >= 8 && warp < 12) {
     front_end<STASH>(P, sy, role_base, (warp - 8) * 32 + lane);
   } else if (warp < 8) {
@@ -2134,9 +1872,8 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   P.ns = ts ? ((ns_env >= 2 && ns_env <= tc::NS_MAX) ? ns_env : tc::NS_MAX) : tc::NS;
   // split hand-off of the trunk layers (TS and HY kernels): INRF_TC_SPLIT = 0 (off) / 64 / 128.  The two-chunks-per-batch
   // drain (INRF_TC_TS=1) loads chunks 0 and 1 together, so it can only use 128
-  static const int split_env = getenv("INRF_TC_SPLIT") ? atoi(getenv("INRF_TC_SPLIT")) : 0;
-  // (the lean issuer of the hybrid kernel has no split variant: there only with the first issuer, INRF_TC_EXP=4)
-  P.split_nf = (ts || (hy && (P.exp_flags & 4))) ? ((split_env == 64 && P.ts_fine) ? 64 : (split_env == 64 || split_env == 128) ? 128 : 0) : 0;
+  static const int split_env = getenv("INRF_TC_SPLIT") ? atoi(getenv("INRF_TC_SPLIT")) : 64;
+  P.split_nf = (ts || hy) ? ((split_env == 64 && P.ts_fine) ? 64 : (split_env == 64 || split_env == 128) ? 128 : 0) : 0;
   void (*kern)(tc::Params) = a.stash_img ? (cl == 2 ? tc::k_mlp_tc<2, true> : tc::k_mlp_tc<1, true>)
                              : ts ? (cl == 2 ? tc::k_mlp_tc<2, false, true> : tc::k_mlp_tc<1, false, true>)
                              : hy ? (cl == 2 ? tc::k_mlp_tc<2, false, false, true> : tc::k_mlp_tc<1, false, false, true>)
