@@ -53,5 +53,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_timeline():
+    """Development variant csrc/libinrf_tl.so: mlp_tc.cu compiled with -DINRF_TC_TIMELINE (clock64 stamps of the issuer, two
+    epilogue warps and a back-end warp of CTA 0, printed by the launcher), linked with the production objects.
+    Selected with INRF_LIB=<path> (see _lib.py); never loaded otherwise."""
+    build()
+    obj = os.path.join(CSRC, "mlp_tc_tl.o")
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    subprocess.check_call([_nvcc()] + flags + ["-DINRF_TC_TIMELINE", "-c", os.path.join(CSRC, "mlp_tc.cu"), "-o", obj])
+    objs = [obj if s == "mlp_tc.cu" else os.path.join(CSRC, s.replace(".cu", ".o")) for s in SOURCES]
+    out = os.path.join(CSRC, "libinrf_tl.so")
+    subprocess.check_call([_nvcc(), "-shared", "-o", out] + objs + ["-lcudart"])
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--timeline" in sys.argv:
+        print(build_timeline())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Development: clock64 timeline (library built with -DINRF_TC_TIMELINE as csrc/libinrf_tl.so) of the issuer,
+# Development: clock64 timeline (build csrc/libinrf_tl.so first, HERE: python -m intrinsicnerf_b200.build --timeline) of the issuer,
 # two epilogue warps and back-end warp 12 of CTA 0 over two steady-state tiles - of the bare TS launch and of both fused launches
 mkdir -p gpurun_out
 export INRF_LIB=$PWD/intrinsicnerf_b200/csrc/libinrf_tl.so
