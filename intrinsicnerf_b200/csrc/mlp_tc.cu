@@ -21,7 +21,16 @@
 //                                 (SWIZZLE_128B K-major), in place, K chunk by K chunk so that the
 //                                 next layer's MMAs start as soon as chunk 0 exists; sigma head as an
 //                                 fp32 dot product on the un-rounded trunk output; sigmoid heads;
-//                                 packed raw rows to HBM
+//                                 packed raw rows to HBM (TS variant: the head values wait in registers
+//                                 and the rows are finished under the NEXT tile's layer 1, PendingHeads)
+//   warps 12-13 ray back end    : fused renderer only - compositing and hierarchical resampling of the
+//                                 previous tile's rows (ray_backend); warp 13 is the stash warp in the
+//                                 training instantiation, warp 12 also writes the constant operands
+//
+// The issuer warp paces the kernel (profiles/r02_issuer_timeline.md): ~590 cycles of dependent bookkeeping
+// per ring fill against 512 cycles of MMAs.  Do not add work to Issuer::acquire / finish / probe without measuring -
+// two run-time flags there once cost 7 % of the launch.  The sy.stamp() calls compile to nothing unless
+// -DINRF_TC_TIMELINE (python -m intrinsicnerf_b200.build --timeline).
 //
 // Why N=256 instructions: consecutive MMAs into the same accumulator are dependent; a 64-cycle
 // N=128 instruction cannot hide the accumulate latency (measured: 1.3x slower than N=256).
