@@ -565,7 +565,11 @@ def main():
     ops.poll_status()                                         # a tripped watchdog / fp16-range record would invalidate the run
     config5 = None
     if not args.no_config5:
-        config5 = train_step_record(dev, dist, rank, world)
+        try:                                                  # a secondary record must not take the headline line with it
+            config5 = train_step_record(dev, dist, rank, world)
+        except Exception as e:
+            config5 = {"workload": "replica_room0_train_step_1024rays_64+128_C28", "n_gpus": world,
+                       "failed": f"{type(e).__name__}: {e}"[:300]}
 
     comm = None
     if world > 1:

@@ -71,7 +71,8 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 1000), (3, 129), (2, 5)])
+# (8, 1024) is BASELINE config 5 at 8 ranks: 128 rays = one tile per rank; (4, 200): ranks 2 and 3 get an empty / short shard
+@pytest.mark.parametrize("world,n", [(2, 1000), (3, 129), (2, 5), (4, 200), (8, 1024)])
 def test_sharded_equals_single_process(world, n):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -82,7 +83,7 @@ def test_sharded_equals_single_process(world, n):
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=60) for _ in range(world)]
+    res = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
