@@ -1879,10 +1879,10 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t st, const FuseArgs* fuse) {
   static const bool hy_env = !(getenv("INRF_TC_HY") != nullptr && getenv("INRF_TC_HY")[0] == '0');
   const bool hy = ts_env && hy_env && !ts && !a.stash_img && P.bias_mma;
   P.ns = ts ? ((ns_env >= 2 && ns_env <= tc::NS_MAX) ? ns_env : tc::NS_MAX) : tc::NS;
-  // split hand-off of the trunk layers (TS and HY kernels): INRF_TC_SPLIT = 0 (off) / 64 / 128.  The two-chunks-per-batch
-  // drain (INRF_TC_TS=1) loads chunks 0 and 1 together, so it can only use 128
+  // split hand-off of the trunk layers (TS and HY kernels): INRF_TC_SPLIT = 0 (off) / 64 (default) / 128.  Only with the
+  // chunk-per-batch drain (the default, INRF_TC_TS=2): the two-chunks-per-batch drain (INRF_TC_TS=1) is an A/B relic
   static const int split_env = getenv("INRF_TC_SPLIT") ? atoi(getenv("INRF_TC_SPLIT")) : 64;
-  P.split_nf = (ts || hy) ? ((split_env == 64 && P.ts_fine) ? 64 : (split_env == 64 || split_env == 128) ? 128 : 0) : 0;
+  P.split_nf = ((ts || hy) && P.ts_fine && (split_env == 64 || split_env == 128)) ? split_env : 0;
   void (*kern)(tc::Params) = a.stash_img ? (cl == 2 ? tc::k_mlp_tc<2, true> : tc::k_mlp_tc<1, true>)
                              : ts ? (cl == 2 ? tc::k_mlp_tc<2, false, true> : tc::k_mlp_tc<1, false, true>)
                              : hy ? (cl == 2 ? tc::k_mlp_tc<2, false, false, true> : tc::k_mlp_tc<1, false, false, true>)

@@ -1,0 +1,59 @@
+"""The development switches of k_mlp_tc must not change a single bit: split hand-off off / 64 / 128 and the two
+placements of the fused ray back end, object (TS kernel) and SSR (hybrid kernel) networks, bare MLP launch and fused chunk.
+The switches are read once per process, so every setting runs in its own interpreter and prints checksums."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CODE = r'''
+import sys
+sys.path.insert(0, %r)
+import torch
+from intrinsicnerf_b200 import ops
+from oracle import nerf_oracle as orc
+from tests.util import build_nets
+
+
+def chk(t):
+    return int(t.contiguous().view(torch.int32).to(torch.int64).sum().item())
+
+
+dev = torch.device("cuda:0")
+n = 3001                                   # ragged: not a multiple of the 128-row tile, several tiles per CTA
+rays = orc.blender_rays(64, 64)[:n].contiguous().to(dev)
+z = torch.sort(torch.rand(n, 192, generator=torch.Generator().manual_seed(3)) * 4 + 2, dim=-1)[0].to(dev)
+out = []
+for variant, C, scale in (("object", 0, 1.0), ("ssr", 28, 10.0)):
+    coarse, fine, _, _ = build_nets(variant, C)
+    raw = ops.mlp_forward_rays(fine.packed(), fine.variant, C, rays, z, False, scale, "tc")
+    out.append(chk(raw))
+    o = ops.render_chunk(rays, coarse.packed(), fine.packed(), variant=fine.variant, n_classes=C, white_bkgd=True, pe_scalar_factor=scale)
+    out += [chk(o["rec_coarse"]), chk(o["rec_fine"])]
+torch.cuda.synchronize()
+ops.poll_status()
+print("CHK", *out)
+''' % ROOT
+
+SETTINGS = [{}, {"INRF_TC_SPLIT": "0"}, {"INRF_TC_SPLIT": "128"}, {"INRF_TC_EXP": "8"}]
+
+
+def _run(extra):
+    env = {k: v for k, v in os.environ.items() if not k.startswith("INRF_TC_")}
+    env.update(extra)
+    r = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (extra, r.stderr[-2000:])
+    lines = [l for l in r.stdout.splitlines() if l.startswith("CHK")]
+    assert lines, (extra, r.stdout[-500:], r.stderr[-1500:])
+    return lines[-1]
+
+
+@pytest.mark.gpu
+def test_kernel_switches_are_bit_identical():
+    ref = _run(SETTINGS[0])
+    assert len(ref.split()) == 7
+    for extra in SETTINGS[1:]:
+        assert _run(extra) == ref, extra
